@@ -1,0 +1,104 @@
+"""Seeded tiny configs / inputs shared by oracle/make_golden.py and tests/ (TEST
+INFRASTRUCTURE ONLY).  Weights and inputs are regenerated from seeds instead of being
+stored; golden files carry checksums of what the reference actually saw."""
+import copy
+
+import torch
+
+TINY = dict(img=128, patch=16, dims=128, heads=2, layers=4, out_indices=(0, 1, 2, 3),
+            channels=32, classes=5, patchmix_n=2)
+
+GRAD_KEYS = (
+    'backbone.cls_token', 'backbone.pos_embed', 'backbone.patch_embed.projection.bias',
+    'backbone.layers.0.ln1.weight', 'backbone.layers.0.attn.attn.in_proj_bias',
+    'backbone.layers.1.attn.attn.out_proj.weight', 'backbone.layers.3.ffn.layers.0.0.bias',
+    'backbone.layers.3.ffn.layers.1.weight', 'decode_head.norm.weight',
+    'decode_head.up_convs.0.0.conv.weight', 'decode_head.up_convs.3.0.bn.weight',
+    'decode_head.conv_seg.weight', 'decode_head.conv_seg.bias',
+    'auxiliary_head.0.up_convs.1.0.conv.weight', 'auxiliary_head.2.conv_seg.bias',
+)
+EMA_KEYS = (
+    'backbone_ema.cls_token', 'backbone_ema.layers.2.ffn.layers.1.weight',
+    'decode_head_ema.up_convs.1.0.bn.running_var', 'decode_head_ema.up_convs.1.0.bn.running_mean',
+    'decode_head_ema.conv_seg.weight', 'decode_head_ema.up_convs.2.0.bn.num_batches_tracked',
+)
+
+
+def tiny_cfg(variant='ours'):
+    """The three shipped configs (configs/setr/*_{sup,MT,MT_w_ours}.py) shrunk to TINY."""
+    t = TINY
+    norm_cfg = dict(type='SyncBN', requires_grad=True)
+    bb = dict(type='VisionTransformer', img_size=(t['img'], t['img']), patch_size=t['patch'],
+              in_channels=3, norm_cfg=dict(type='LN', eps=1e-6, requires_grad=True),
+              with_cls_token=True, interpolate_mode='bilinear', drop_rate=0.,
+              embed_dims=t['dims'], num_heads=t['heads'], num_layers=t['layers'],
+              out_indices=t['out_indices'])
+    dh = dict(type='SETRUPHead', align_corners=False, num_convs=3, in_channels=t['dims'],
+              num_classes=t['classes'], channels=t['channels'], in_index=3, dropout_ratio=0,
+              norm_cfg=norm_cfg, up_scale=2, kernel_size=3,
+              loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0))
+    # 128px / 16 = 8 tokens; 3 x2 up-convs give 64px; the reference config uses 4 (x16).
+    dh['num_convs'] = 4
+    aux = [dict(type='SETRUPHead', in_channels=t['dims'], channels=t['channels'], in_index=i,
+                num_classes=t['classes'], dropout_ratio=0, norm_cfg=norm_cfg, num_convs=2,
+                up_scale=4, kernel_size=3, align_corners=False,
+                loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=0.4))
+           for i in range(4)]
+    model = dict(type='EncoderDecoder', pretrained=None, backbone=bb, auxiliary_head=aux,
+                 decode_head=dh, test_cfg=dict(mode='whole'))
+    if variant == 'sup':      # ..._sup.py: beta = 0, EMA still on
+        model.update(backbone_ema=copy.deepcopy(bb), decode_head_ema=copy.deepcopy(dh), ema=True,
+                     ema_momentum=0.999, unsup_weight=0.0, unsup_confidence=0.95)
+    elif variant == 'mt':     # ..._MT.py: Mean Teacher + CutMix, as shipped
+        model.update(backbone_ema=copy.deepcopy(bb), decode_head_ema=copy.deepcopy(dh), ema=True,
+                     ema_momentum=0.999, unsup_weight=1.0, unsup_confidence=0.95,
+                     use_CutMix=True)
+    elif variant == 'ours':   # ..._MT_w_ours.py
+        model.update(backbone_ema=copy.deepcopy(bb), decode_head_ema=copy.deepcopy(dh), ema=True,
+                     ema_momentum=0.999, unsup_weight=1.0, unsup_confidence=0.95,
+                     attn_mask_seperate_head=True, attn_mask_weight=5, adaptive_attn_mask=True,
+                     use_PatchShuffle_w_Cutmix=True, PatchMix_N=t['patchmix_n'],
+                     negative_class_ranking=True, negative_class_ranking_mode='unsup_only')
+    else:
+        raise KeyError(variant)
+    return model
+
+
+def seeded_state_dict(template, seed=5):
+    """Deterministic weights for every key of ``template`` (shapes/dtypes kept).
+    conv_seg of the EMA head is scaled up so that a useful fraction of pixels clears
+    the 0.95 confidence threshold."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(template.keys()):
+        v = template[k]
+        if not v.dtype.is_floating_point:
+            out[k] = torch.zeros_like(v)
+            continue
+        if k.endswith('running_var'):
+            t = torch.rand(v.shape, generator=g) * 0.5 + 0.75
+        elif k.endswith('running_mean'):
+            t = torch.randn(v.shape, generator=g) * 0.1
+        elif 'bn.weight' in k or 'ln1.weight' in k or 'ln2.weight' in k or 'norm.weight' in k:
+            t = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith('bias'):
+            t = 0.02 * torch.randn(v.shape, generator=g)
+        elif 'conv_seg.weight' in k:
+            t = torch.randn(v.shape, generator=g) * (6.0 if 'ema' in k else 0.1)
+        elif v.dim() >= 2:
+            fan_in = v[0].numel()
+            t = torch.randn(v.shape, generator=g) * (1.0 / fan_in ** 0.5)
+        else:
+            t = 0.02 * torch.randn(v.shape, generator=g)
+        out[k] = t.to(v.dtype)
+    return out
+
+
+def checksum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+def tiny_batch(variant='ours', seed=1999):
+    from oracle.s4former_oracle import synthetic_batch
+    n_unsup = 0 if variant == 'sup' else 2
+    return synthetic_batch(2, n_unsup, TINY['img'], TINY['classes'], seed=seed, grid=16)

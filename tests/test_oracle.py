@@ -1,0 +1,143 @@
+"""CPU tests: the oracle (oracle/s4former_oracle.py) against (a) the reference's own
+known-answer tests for this path and (b) golden vectors produced by the unmodified
+reference (oracle/make_golden.py)."""
+import copy
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import golden_common as gc
+from oracle import s4former_oracle as O
+
+warnings.filterwarnings('ignore')
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_ce_known_answers():
+    """reference tests/test_models/test_losses/test_ce_loss.py:25-39 and :43-86."""
+    # CE([100, -100], 1) == 200
+    z = torch.tensor([[100., -100.]])
+    y = torch.tensor([1])
+    assert torch.allclose(O.cross_entropy_mean_all(z.view(1, 2, 1, 1), y.view(1, 1, 1)),
+                          torch.tensor(200.))
+    # ignore_index=255, avg_non_ignore=False  ==  F.cross_entropy(sum) / numel
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(2, 4, 10, 10, generator=g)
+    y = torch.randint(0, 4, (2, 10, 10), generator=g)
+    y[:, :2] = 255
+    want = F.cross_entropy(z, y, reduction='sum', ignore_index=255) / y.numel()
+    assert torch.allclose(O.cross_entropy_mean_all(z, y, 255), want, rtol=1e-6)
+
+
+def test_losses_and_pseudo_labels_golden(golden_dir):
+    G = _load(golden_dir, 'loss_pseudo.pt')
+    hard, conf, _ = O.pseudo_label(G['z_t'], 0.95)
+    assert torch.equal(hard, G['hard'])
+    assert torch.equal(conf, G['conf'])
+    assert torch.equal(O.patch_unconfidence(conf, G['patch']), G['u'])
+    assert torch.allclose(O.cross_entropy_mean_all(G['z_s'], hard), G['loss_seg_unsup'], rtol=1e-6)
+    assert torch.allclose(O.cross_entropy_mean_all(G['z_s'], hard, 255, 0.4), G['ce_w04'], rtol=1e-6)
+    assert torch.allclose(O.ncr_unsup_only(G['z_s'], G['z_t'], hard), G['loss_ncr_unsup'], rtol=1e-5)
+    assert torch.allclose(conf.sum().float() / conf.numel(), G['mask_ratio'])
+
+
+def test_augment_golden(golden_dir):
+    G = _load(golden_dir, 'augment.pt')
+    O.seed_host_rng(G['seed'])
+    boxes = [O.cutout_box(G['img'].shape[2:], 2) for _ in range(4)]
+    ci, cl = O.cutmix(G['img'], G['lab'], boxes)
+    assert torch.equal(ci, G['cut_img'])
+    assert torch.equal(cl, G['cut_lab'])
+    perms = O.draw_patchshuffle_perms(4, 16, 0.5)
+    assert torch.equal(perms, G['perms'])
+    assert torch.equal(O.patchshuffle(ci, perms, 16), G['shuf_img'])
+    assert torch.equal(O.token_unshuffle(G['tok'], perms, 2), G['unsh'])
+    # un-shuffle inverts the image shuffle at token granularity
+    ident = torch.arange(64).float().view(1, 64, 1).expand(4, 64, 1)
+    img_like = ident.view(4, 1, 8, 8)
+    sh = O.patchshuffle(img_like, perms, 2).reshape(4, 64, 1)
+    assert torch.equal(O.token_unshuffle(sh, perms, 2), ident)
+
+
+def _oracle(variant):
+    cfg = gc.tiny_cfg(variant)
+    m = O.OracleEncoderDecoder(**{k: v for k, v in cfg.items() if k != 'type'})
+    sd = gc.seeded_state_dict(m.state_dict(), seed=5)
+    m.load_state_dict(sd)
+    m.train()
+    return m, sd
+
+
+@pytest.mark.parametrize('variant', ['sup', 'mt', 'ours'])
+def test_train_step_golden(golden_dir, variant):
+    G = _load(golden_dir, f'step_{variant}.pt')
+    m, sd = _oracle(variant)
+    assert abs(gc.checksum(sd) - G['sd_checksum']) < 1e-6 * G['sd_checksum']
+    img, gt, metas = gc.tiny_batch(variant)
+    assert abs(float(img.double().abs().sum()) - G['img_checksum']) < 1e-9 * G['img_checksum']
+    O.seed_host_rng(1999)
+    losses = m.forward_train(img, metas, gt)
+    assert set(losses) == set(G['losses'])
+    for k, v in G['losses'].items():
+        assert torch.allclose(losses[k], v, rtol=2e-5, atol=1e-7), k
+    O.parse_losses(losses).backward()
+    named = dict(m.named_parameters())
+    for k, g in G['grads'].items():
+        rel = (named[k].grad - g).norm() / (g.norm() + 1e-12)
+        assert rel < 1e-4, (k, float(rel))
+    for k, n in G['grad_norms'].items():
+        assert abs(float(named[k].grad.norm()) - n) <= 1e-3 * n + 1e-9, k
+    post = m.state_dict()
+    for k, v in G['ema_after'].items():
+        assert torch.allclose(post[k].float(), v.float(), rtol=1e-6, atol=1e-8), k
+    for k, v in G['bn_after'].items():
+        assert torch.allclose(post[k], v, rtol=1e-4, atol=1e-6), k
+    if variant == 'ours':
+        sm = [mm for mm in metas if mm['tag'] == 'unsup_student']
+        for mm, p in zip(sm, G['perms']):
+            assert torch.equal(torch.as_tensor(mm['PatchMixIndex']), torch.as_tensor(p))
+
+
+def test_backbone_pasa_and_head_golden(golden_dir):
+    G = _load(golden_dir, 'step_ours.pt')
+    m, _ = _oracle('ours')
+    m.eval()
+    g2 = torch.Generator().manual_seed(G['vit_seed'])
+    u = torch.rand(2, 8, 8, generator=g2).mul(16).round().div(16)
+    x = torch.randn(2, 3, 128, 128, generator=g2)
+    assert torch.equal(u, G['vit_u'])
+    assert abs(float(x.double().abs().sum()) - G['vit_x_checksum']) < 1e-6
+    with torch.no_grad():
+        feats = m.backbone(x, attn_mask=u, attn_mask_weight=5, adaptive_attn_mask=True,
+                           topk_idx=G['vit_topk'])
+        plain = m.backbone(x)
+        logits = m.decode_head.forward(plain)
+    for a, b in zip(feats, G['vit_feats']):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    for a, b in zip(plain, G['vit_feats_plain']):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(logits[:, :, ::2, ::2], G['head_logits_eval'], rtol=1e-4, atol=1e-4)
+    # the PASA bias really changes the features
+    assert (feats[-1] - plain[-1]).abs().max() > 1e-3
+
+
+def test_pasa_rank1_equals_reference_mask():
+    """vit.py:519-535 materialised mask == w * gate[q] * u0[k]."""
+    g = torch.Generator().manual_seed(3)
+    u = torch.rand(2, 4, 4, generator=g)
+    w = 5.0
+    am = u.reshape(2, -1)
+    am = torch.cat((torch.zeros(2, 1), am), -1)
+    A = am.unsqueeze(1).repeat(1, am.size(-1), 1)
+    idx = torch.topk(am[:, 1:], int(0.5 * (am.size(-1) - 1)), dim=-1, largest=False)[1] + 1
+    A[torch.arange(2).unsqueeze(1), idx, :] = 0
+    A = A * w
+    u0, gate = O.pasa_gate_u0(u, True)
+    assert torch.equal(A, w * gate.unsqueeze(-1) * u0.unsqueeze(1))
