@@ -1,0 +1,226 @@
+/* s4former_b200 -- C ABI of the B200-native S4Former train-step kernels.
+ *
+ * Drop-in boundary: the reference is pure Python over PyTorch
+ * (mmseg/mmcv; no native code, setup.py:200 `ext_modules=[]`), so what a maintainer binds is
+ * this library from `torch.autograd.Function`s via ctypes.  Every entry
+ * point takes raw device pointers (`tensor.data_ptr()`), plain sizes and a `cudaStream_t`;
+ * nothing allocates, nothing throws: the return value is 0 or a negative error code and
+ * `s4_last_error()` describes the failure.  Workspace sizes come from companion
+ * `*_workspace()` functions.  All kernels are built for sm_100a only.
+ *
+ * dtype codes: 0 = float32, 1 = bfloat16.  Parameters, statistics, losses and logits are
+ * always float32; `dtype` selects the activation storage type.
+ *
+ * Each group cites the reference lines it replaces (paths relative to the reference root).
+ */
+#ifndef S4FORMER_H_
+#define S4FORMER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define S4_DTYPE_F32 0
+#define S4_DTYPE_BF16 1
+
+#define S4_ACT_NONE 0
+#define S4_ACT_GELU 1
+
+#define S4_BACKEND_AUTO 0  /* tcgen05 when the shape/dtype allows, else CUDA cores */
+#define S4_BACKEND_SIMT 1  /* CUDA-core fp32-accumulate path (validation)           */
+#define S4_BACKEND_TC 2    /* tcgen05/TMEM/TMA path, error if unsupported           */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int s4_version(void);
+int s4_built_arch(void);            /* 100 = sm_100a */
+const char* s4_last_error(void);
+
+/* ---- GEMM with fused epilogue -------------------------------------------------------------
+ * Replaces: nn.Linear / in_proj / out_proj / FFN inside mmcv MultiheadAttention and FFN as
+ * called from mmseg/models/backbones/vit.py:113-127; patch-embed Conv2d(3,768,16,16)
+ * (mmseg/models/utils/embed.py:145-153,199-201) after s4_patchify; the batched QK^T / PV
+ * contractions of nn.MultiheadAttention and all their backward forms.
+ *
+ *   C[z][m,n] = epi(alpha * sum_k A[z][m,k] * B[z][k,n]),  z = z1*nb2 + z2
+ *   epi(v): v += bias[n]; v *= gelu'(aux[m,n]); pre[m,n] = v; v = gelu(v) (act);
+ *           v += res[m,n]; v += C_old[m,n] (accumulate)
+ * Element strides; aux / pre / res share C's strides and batch strides.
+ */
+typedef struct S4GemmParams {
+  const void* a;
+  const void* b;
+  void* c;
+  const float* bias;   /* [N] or NULL */
+  const void* aux;     /* [M,N] pre-activations for the GELU-gradient epilogue, or NULL */
+  const void* res;     /* [M,N] residual, or NULL */
+  void* pre;           /* [M,N] receives the pre-activation, or NULL */
+  int M, N, K;
+  int nb1, nb2;        /* batch counts (>= 1) */
+  long long a_sm, a_sk, a_b1, a_b2;
+  long long b_sk, b_sn, b_b1, b_b2;
+  long long c_sm, c_b1, c_b2;   /* C is unit-stride in n */
+  float alpha;
+  int act;             /* S4_ACT_* */
+  int accumulate;      /* C += ... */
+  int dtype;           /* dtype of A, B, aux, res, pre */
+  int c_dtype;         /* dtype of C */
+  int backend;         /* S4_BACKEND_* */
+  int split_k;         /* tcgen05 path: >1 splits K over CTAs and accumulates atomically
+                          into a float32 C (requires accumulate=1, c_dtype=f32, no epilogue) */
+} S4GemmParams;
+
+int s4_gemm(const S4GemmParams* p, cudaStream_t stream);
+/* 1 if s4_gemm would run this problem on the tcgen05 path */
+int s4_gemm_uses_tc(const S4GemmParams* p);
+
+/* ---- LayerNorm (+ row gather) ----------------------------------------------------------------
+ * Replaces: ln1/ln2 (vit.py:119-120, eps 1e-6); head LayerNorm with the feature tap
+ * (vit.py:556-562) and PatchMix un-shuffle (decode_heads/decode_head.py:186-212,
+ * setr_up_head.py:96-103) folded in through `row_map` (dst row -> src row), NULL = identity. */
+int s4_layernorm_fwd(const void* x, const int* row_map, const float* gamma, const float* beta,
+                     void* y, float* mean, float* rstd, int rows, int D, float eps, int dtype,
+                     cudaStream_t stream);
+/* dx is written at the mapped source rows (pre-zero it when row_map skips rows); dres (optional,
+ * indexed like dx) is added to it: the gradient arriving over the residual connection;
+ * dgamma/dbeta are accumulated (+=). */
+int s4_layernorm_bwd(const void* dy, const void* x, const int* row_map, const float* gamma,
+                     const float* mean, const float* rstd, const void* dres, void* dx,
+                     float* dgamma, float* dbeta, int rows, int D, int dtype,
+                     cudaStream_t stream);
+
+/* ---- attention with the patch-adaptive (PASA) bias ---------------------------------------------
+ * Replaces: nn.MultiheadAttention core as driven by vit.py:119 with the additive float mask
+ * built at vit.py:519-535.  The mask is never materialised: bias[b,h,q,k] =
+ * w * gate[b,q] * u0[b,k] (rank 1, same for all heads and layers).
+ * qkv: [B, L, 3*H*hd] packed as torch in_proj emits it; out: [B, L, H*hd].
+ * u0/gate: [B, L] float32 or NULL.  `probs` (workspace, [B,H,L,L] in `dtype`) is kept for the
+ * backward when the unfused path runs; lse: [B,H,L] float32. */
+size_t s4_attention_workspace(int B, int H, int L, int hd, int dtype);
+int s4_attention_fwd(const void* qkv, const float* u0, const float* gate, float bias_weight,
+                     void* out, float* lse, void* workspace, size_t ws_bytes, int B, int H, int L,
+                     int hd, int dtype, int backend, cudaStream_t stream);
+int s4_attention_bwd(const void* dout, const void* qkv, const void* out, const float* lse,
+                     const float* u0, const float* gate, float bias_weight, void* dqkv,
+                     void* workspace, size_t ws_bytes, int B, int H, int L, int hd, int dtype,
+                     int backend, cudaStream_t stream);
+
+/* ---- backbone glue -------------------------------------------------------------------------- */
+/* img [B,Cin,H,W] f32 NCHW -> [B*gh*gw, Cin*P*P] (k = (c*P+ky)*P+kx), zero corner padding
+ * (embed.py:58-80, 183-204). */
+int s4_patchify(const float* img, void* out, int B, int Cin, int H, int W, int P, int dtype,
+                cudaStream_t stream);
+/* x[b,0]=cls+pos[0]; x[b,1+p]=tok[b,p]+pos[1+p]  (vit.py:486-487, 513) */
+int s4_assemble_tokens(const void* tok, const float* cls, const float* pos, void* x, int B, int L,
+                       int D, int dtype, cudaStream_t stream);
+int s4_assemble_tokens_bwd(const void* dx, void* dtok, float* dcls, float* dpos, int B, int L,
+                           int D, int dtype, cudaStream_t stream);
+/* sum[c] += sum_r x[r,c]; sumsq[c] += sum_r x[r,c]^2 (sumsq may be NULL) */
+int s4_colsum(const void* x, float* sum, float* sumsq, long long rows, int cols, int dtype,
+              cudaStream_t stream);
+int s4_cast(const void* x, void* y, long long n, int src_dtype, int dst_dtype,
+            cudaStream_t stream);
+int s4_transpose(const void* x, void* y, int batch, int rows, int cols, int dtype,
+                 cudaStream_t stream);
+
+/* ---- SETR-PUP head ---------------------------------------------------------------------------
+ * Replaces: ConvModule(conv3x3 no-bias -> SyncBN -> ReLU) + Upsample(bilinear,
+ * align_corners=False) stages and the 1x1 conv_seg (decode_heads/setr_up_head.py:49-77,
+ * 92-111; decode_head.py:107-111, 311-316; ops/wrappers.py:30-51).  Activations are NHWC. */
+/* y[B,H,W,Cout] = conv3x3(x[B,H,W,Cin], w), pad 1, stride 1.  w_packed: [Cout, 9*Cin] with
+ * k = (ky*3+kx)*Cin + ci  (s4_pack_conv3x3_weight builds it and the dgrad form). */
+int s4_conv3x3_fwd(const void* x, const void* w_packed, void* y, int B, int H, int W, int Cin,
+                   int Cout, int dtype, int backend, cudaStream_t stream);
+/* dx = conv3x3(dy, w_dgrad) with w_dgrad: [Cin, 9*Cout], taps flipped */
+int s4_conv3x3_dgrad(const void* dy, const void* w_dgrad, void* dx, int B, int H, int W, int Cin,
+                     int Cout, int dtype, int backend, cudaStream_t stream);
+/* dw[Cout,Cin,3,3] (float32, torch layout) += sum over pixels */
+int s4_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin,
+                     int Cout, int dtype, int backend, cudaStream_t stream);
+/* w [Cout,Cin,3,3] f32 -> fwd [Cout, 9*Cin] and dgrad [Cin, 9*Cout] in `dtype` */
+int s4_pack_conv3x3_weight(const float* w, void* w_fwd, void* w_dgrad, int Cin, int Cout,
+                           int dtype, cudaStream_t stream);
+/* BatchNorm statistics from (sum, sumsq, count): mean, invstd (biased var, eps), the fused
+ * affine scale = gamma*invstd, shift = beta - mean*scale, and the running-stat update with
+ * momentum (unbiased var), as torch.nn.BatchNorm2d / SyncBatchNorm.  running_* may be NULL. */
+int s4_bn_finalize(const float* sum, const float* sumsq, double count, float eps, float momentum,
+                   const float* gamma, const float* beta, float* mean, float* invstd,
+                   float* scale, float* shift, float* running_mean, float* running_var, int C,
+                   cudaStream_t stream);
+/* eval mode: scale/shift from running statistics */
+int s4_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma,
+                      const float* beta, float eps, float* scale, float* shift, int C,
+                      cudaStream_t stream);
+/* out[B,H*s,W*s,C] = bilinear_s(relu(x*scale[c] + shift[c])) */
+int s4_bn_relu_upsample_fwd(const void* x, const float* scale, const float* shift, void* out,
+                            int B, int H, int W, int C, int s, int dtype, cudaStream_t stream);
+/* dact[B,H,W,C] = relu_mask * upsample^T(dout); also dsum[c] += sum dact, ddot[c] += sum dact*xhat */
+int s4_bn_relu_upsample_bwd(const void* dout, const void* x, const float* scale,
+                            const float* shift, const float* mean, const float* invstd,
+                            void* dact, float* dsum, float* ddot, int B, int H, int W, int C,
+                            int s, int dtype, cudaStream_t stream);
+/* dy = gamma*invstd*(dact - dsum/n - xhat*ddot/n)  (training-mode BN backward) */
+int s4_bn_bwd_apply(const void* dact, const void* x, const float* gamma, const float* mean,
+                    const float* invstd, const float* dsum, const float* ddot, double count,
+                    void* dy, long long rows, int C, int dtype, cudaStream_t stream);
+/* z[B,H,W,NC] (f32) = conv1x1(relu(x*scale+shift)) + bias ; w [NC,C] f32 */
+int s4_bn_relu_conv1x1_fwd(const void* x, const float* scale, const float* shift, const float* w,
+                           const float* bias, float* z, long long rows, int C, int NC, int dtype,
+                           cudaStream_t stream);
+/* backward of the above: dact[rows,C] (relu-masked), dw[NC,C] +=, dbias[NC] +=, dsum/ddot += */
+int s4_bn_relu_conv1x1_bwd(const float* dz, const void* x, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, const float* w, void* dact,
+                           float* dw, float* dbias, float* dsum, float* ddot, long long rows,
+                           int C, int NC, int dtype, cudaStream_t stream);
+/* logits[B,NC,H*s,W*s] (NCHW f32) = bilinear_s(z[B,H,W,NC]) and its transpose */
+int s4_upsample_logits_fwd(const float* z, float* logits, int B, int H, int W, int NC, int s,
+                           cudaStream_t stream);
+int s4_upsample_logits_bwd(const float* dlogits, float* dz, int B, int H, int W, int NC, int s,
+                           cudaStream_t stream);
+
+/* ---- pseudo labels and losses ------------------------------------------------------------------
+ * s4_pseudo_label replaces encoder_decoder.py:888-901 (+ :541-542) and the patch unconfidence
+ * of :547-555: hard = argmax or 255, conf = (max softmax > thr), u = mean_{patch}(1-conf).
+ * s4_ce_ncr replaces CrossEntropyLoss (losses/cross_entropy_loss.py:45-61,
+ * losses/utils.py:65-69, avg over ALL pixels) and the NCR loop of
+ * encoder_decoder.py:936-954, forward and gradient in one pass. */
+int s4_pseudo_label(const float* logits, long long* hard, long long* conf, float* u, int B, int C,
+                    int H, int W, int patch, float threshold, cudaStream_t stream);
+size_t s4_ce_ncr_workspace(int B, int H, int W);
+/* loss_out[0..2] = (ce_weight/P * sum nll, ncr_weight/P * sum dist, #valid); dlogits (optional)
+ * = g0*dloss0/dz + g1*dloss1/dz with (g0,g1) read from the device pointer grad_scale (NULL = 1,1) */
+int s4_ce_ncr(const float* logits_s, const float* logits_t, const long long* label, float* dlogits,
+              float* loss_out, const float* grad_scale, int B, int C, int H, int W,
+              float ce_weight, float ncr_weight, int ignore_index, void* workspace,
+              size_t ws_bytes, cudaStream_t stream);
+int s4_scale_by_scalar(float* y, const float* scale_dev, size_t n, cudaStream_t stream);
+
+/* ---- augmentation (host RNG, device gathers) --------------------------------------------------
+ * generate_unsup_data.py:400-453 (CutMix with neighbour (i+1)%B) and :737-819 (PatchShuffle) */
+int s4_cutmix(const float* img, const long long* label, const int* boxes_dev, float* out_img,
+              long long* out_label, int B, int C, int H, int W, cudaStream_t stream);
+int s4_patchshuffle(const float* img, const long long* perm_dev, float* out, int B, int C, int H,
+                    int W, int block, cudaStream_t stream);
+
+/* ---- multi-tensor EMA / SGD ---------------------------------------------------------------------
+ * encoder_decoder.py:1044-1066 (t = m*t + (1-m)*s over all parameters and BN running stats) and
+ * the SGD-momentum step mmcv's OptimizerHook drives.  Tables live in device memory. */
+int s4_chunk_elems(void);
+int s4_ema_multi_tensor(void* const* dst_ptrs, void* const* src_ptrs, const long long* sizes,
+                        const int* chunk_tensor, const long long* chunk_off, int n_chunks,
+                        float momentum, float one_minus_momentum, cudaStream_t stream);
+int s4_sgd_multi_tensor(void* const* params, void* const* grads, void* const* bufs,
+                        void* const* bf16_shadow, const long long* sizes, const float* lrs,
+                        const int* chunk_tensor, const long long* chunk_off, int n_chunks,
+                        float momentum, float weight_decay, int first_step, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S4FORMER_H_ */

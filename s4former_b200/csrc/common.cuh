@@ -1,0 +1,113 @@
+// Shared helpers for the s4former_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define S4_OK 0
+#define S4_ERR_ARG (-1)
+#define S4_ERR_CUDA (-2)
+#define S4_ERR_UNSUPPORTED (-3)
+
+// dtype codes used across the C ABI
+#define S4_F32 0
+#define S4_BF16 1
+
+void s4_set_error(const char* fmt, ...);
+int s4_check_launch(const char* what);
+
+#define S4_REQUIRE(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      s4_set_error(__VA_ARGS__);         \
+      return S4_ERR_ARG;                 \
+    }                                    \
+  } while (0)
+
+static inline int s4_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum; `red` must hold >= 32 floats. Result valid in every thread.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+// exact (erf) GELU, matching torch.nn.GELU() default
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// 16-byte vector of 8 bf16 / 4 f32 helpers
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ float get(int i) const { return (&v.x)[i]; }
+  __device__ __forceinline__ void set(int i, float f) { (&v.x)[i] = f; }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  uint4 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = v; }
+  __device__ __forceinline__ float get(int i) const {
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+    return __bfloat162float(h[i]);
+  }
+  __device__ __forceinline__ void set(int i, float f) {
+    __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(&v);
+    h[i] = __float2bfloat16_rn(f);
+  }
+};

@@ -1,0 +1,659 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: the tensor-core path behind s4_gemm, s4_conv3x3_* .
+//
+// One persistent, warp-specialised kernel (grid = #SMs, 1 CTA/SM):
+//   warp 0      TMA producer   (cp.async.bulk.tensor.4d, 128B swizzle, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
+//   warp 2      TMEM allocator (2 accumulator stages of BN fp32 columns)
+//   warps 4-11  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Operand forms (bf16, fp32 accumulate):
+//   A: K-major [M][K] | MN-major [K][M] | conv window (4-D NHWC map, coordinates shifted per
+//      filter tap; TMA zero-fills the halo => implicit GEMM with no im2col buffer)
+//   B: K-major [N][K] | MN-major [K][N] | conv window (wgrad: K = pixels)
+// Epilogue: alpha, bias[n], gelu'(aux), pre-activation copy, GELU(erf), residual, accumulate,
+//           bf16 / fp32 store, or fp32 atomic accumulate (split-K weight gradients).
+//
+// Replaces the cuBLAS / cuDNN calls PyTorch makes for the reference's nn.Linear /
+// nn.MultiheadAttention / Conv2d layers (vit.py:113-127, embed.py:145-153,
+// setr_up_head.py:57-64).
+#include "common.cuh"
+#include "gemm_params.h"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                       // 64 bf16 = 128 B = one swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
+
+enum { OP_KMAJOR = 0, OP_MNMAJOR = 1, OP_CONV_K = 2, OP_CONV_MN = 3 };
+
+struct TcParams {
+  int tiles_m, tiles_n, nb, nb2, splits;
+  int M, N;
+  int kblocks, kb_per_split;
+  int a_mode, b_mode;
+  // conv geometry (a_mode == OP_CONV_K or b_mode == OP_CONV_MN)
+  int cH, cW, cTW, cTH, cblocks;   // cblocks = Cin / 64 (fwd); tile = cTH x cTW pixels
+  int rows_valid;                  // rows of the 128-row tile that are real (conv fwd)
+  int row_pitch;                   // global rows advanced per m-tile (BM, or rows_valid for conv)
+  int a_nobatch;                   // A tensor map has no batch dims (coordinates forced to 0)
+  // epilogue
+  void* c;
+  const float* bias;
+  const __nv_bfloat16* aux;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* pre;
+  long long c_sm, c_sn, c_b1, c_b2;
+  float alpha;
+  int act, accumulate, c_f32, atomic;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = BN == 256 ? 512 : (BN == 128 ? 256 : 128);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float* v) {
+  uint4 o;
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&b);
+  o.z = *reinterpret_cast<uint32_t*>(&c);
+  o.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float* v) {
+  const uint4 o = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+
+struct TileCoord {
+  int m0, n0, z1, z2, kb0, kb1;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int BN) {
+  TileCoord t;
+  const int split = tile % p.splits;
+  int r = tile / p.splits;
+  const int nt = r % p.tiles_n;
+  r /= p.tiles_n;
+  const int mt = r % p.tiles_m;
+  const int z = r / p.tiles_m;
+  t.m0 = mt * BM;
+  t.n0 = nt * BN;
+  t.z1 = z / p.nb2;
+  t.z2 = z % p.nb2;
+  t.kb0 = split * p.kb_per_split;
+  t.kb1 = min(p.kblocks, t.kb0 + p.kb_per_split);
+  return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = tc::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;            // 1024-B aligned stage ring
+  const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.nb * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      tc::mbar_init(full_bar(s), 1);
+      tc::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(tfull_bar(s), 1);
+      tc::mbar_init(tempty_bar(s), NUM_EPI_WARPS);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ==========================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t a_bytes = (p.a_mode == OP_CONV_K) ? (uint32_t)(p.cTW * p.cTH * BK * 2)
+                                                        : (uint32_t)A_STAGE_BYTES;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        // conv forward: the m-tile is a cTH x cTW pixel window of image cb
+        int cb = 0, cy0 = 0, cx0 = 0;
+        if (p.a_mode == OP_CONV_K) {
+          const int tiles_x = p.cW / p.cTW;
+          const int tiles_per_img = (p.cH / p.cTH) * tiles_x;
+          const int mt = t.m0 / BM;
+          cb = mt / tiles_per_img;
+          const int r = mt % tiles_per_img;
+          cy0 = (r / tiles_x) * p.cTH;
+          cx0 = (r % tiles_x) * p.cTW;
+        }
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          tc::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          tc::mbar_expect_tx(full_bar(stage), a_bytes + (uint32_t)C::B_STAGE_BYTES);
+          // ---- A ----
+          if (p.a_mode == OP_KMAJOR) {
+            tc::tma_load_4d(sa, &tmA, full_bar(stage), kb * BK, t.m0, t.z2, t.z1);
+          } else if (p.a_mode == OP_MNMAJOR) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tc::tma_load_4d(sa + j * (BK * 128), &tmA, full_bar(stage), t.m0 + 64 * j, kb * BK,
+                              p.a_nobatch ? 0 : t.z2, p.a_nobatch ? 0 : t.z1);
+          } else {  // OP_CONV_K: k-block = (tap, 64-channel chunk)
+            const int tap = kb / p.cblocks, cblk = kb % p.cblocks;
+            tc::tma_load_4d(sa, &tmA, full_bar(stage), cblk * 64, cx0 + tap % 3 - 1,
+                            cy0 + tap / 3 - 1, cb);
+          }
+          // ---- B ----
+          if (p.b_mode == OP_KMAJOR) {
+            tc::tma_load_4d(sb, &tmB, full_bar(stage), kb * BK, t.n0, t.z2, t.z1);
+          } else if (p.b_mode == OP_MNMAJOR) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tc::tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(stage), t.n0 + 64 * j, kb * BK,
+                              t.z2, t.z1);
+          } else {  // OP_CONV_MN (wgrad): k-block = 64 consecutive pixels, tap = z2
+            const int pix = kb * BK;
+            const int hw = p.cH * p.cW;
+            const int b = pix / hw, r = pix % hw;
+            const int y0 = r / p.cW, x0 = r % p.cW;
+            const int tap = t.z2;
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tc::tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(stage), t.n0 + 64 * j,
+                              x0 + tap % 3 - 1, y0 + tap / 3 - 1, b);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ============================================
+    const int a_mn = (p.a_mode == OP_MNMAJOR) ? 1 : 0;
+    const int b_mn = (p.b_mode == OP_MNMAJOR || p.b_mode == OP_CONV_MN) ? 1 : 0;
+    const uint32_t idesc = tc::make_idesc_bf16(BM, BN, a_mn, b_mn);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BN);
+      tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        tc::mbar_wait(full_bar(stage), phase);
+        tc::fence_after_sync();
+        if (lane == 0) {
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: advance 32 B inside the 128-B swizzle row; MN-major: 16 k-rows = 2048 B
+            const uint64_t ad = a_mn ? tc::make_desc(sa + k * 2048, BK * 128, 1024)
+                                     : tc::make_desc(sa + k * 32, 16, 1024);
+            const uint64_t bd = b_mn ? tc::make_desc(sb + k * 2048, BK * 128, 1024)
+                                     : tc::make_desc(sb + k * 32, 16, 1024);
+            tc::mma_f16_ss(d_tmem, ad, bd, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+          }
+          tc::mma_commit(empty_bar(stage));               // frees the smem slot when MMAs retire
+          if (kb == t.kb1 - 1) tc::mma_commit(tfull_bar(acc));   // accumulator ready
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ==============================================
+    const int ew = warp - 4;
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;                   // column half handled by this warp
+    constexpr int CHUNKS = BN / 32;
+    constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BN);
+      tc::mbar_wait(tfull_bar(acc), acc_phase);
+      tc::fence_after_sync();
+      const int row_in_tile = quad * 32 + lane;
+      const int row = (t.m0 / BM) * p.row_pitch + row_in_tile;
+      const bool row_ok = row < p.M && row_in_tile < p.rows_valid;
+      const size_t zoff = (size_t)t.z1 * p.c_b1 + (size_t)t.z2 * p.c_b2;
+      const size_t roff = zoff + (size_t)row * p.c_sm;
+#pragma unroll 1
+      for (int cc = 0; cc < CH_PER_WARP; ++cc) {
+        const int chunk = half * CH_PER_WARP + cc;
+        if (chunk >= CHUNKS) break;
+        const int col0 = t.n0 + chunk * 32;
+        uint32_t r[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + chunk * 32), r);
+        tc::tmem_ld_wait();
+        if (!row_ok || col0 >= p.N) continue;
+        if (p.atomic) {
+          float* cp = reinterpret_cast<float*>(p.c) + roff;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) atomicAdd(cp + (size_t)(col0 + j) * p.c_sn, p.alpha * __uint_as_float(r[j]));
+          continue;
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int col = col0 + g8 * 8;
+          if (col >= p.N) break;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = p.alpha * __uint_as_float(r[g8 * 8 + j]);
+          const bool full8 = col + 8 <= p.N;
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (full8 || col + j < p.N) v[j] += __ldg(p.bias + col + j);
+          }
+          if (full8) {
+            if (p.aux) {
+              float a[8];
+              load8_bf16(p.aux + roff + col, a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(a[j]);
+            }
+            if (p.pre) store8_bf16(p.pre + roff + col, v);
+            if (p.act == S4_ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+            }
+            if (p.res) {
+              float a[8];
+              load8_bf16(p.res + roff + col, a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += a[j];
+            }
+            if (p.c_f32) {
+              float* cp = reinterpret_cast<float*>(p.c) + roff + col;
+              if (p.accumulate) {
+                const float4 o0 = *reinterpret_cast<const float4*>(cp);
+                const float4 o1 = *reinterpret_cast<const float4*>(cp + 4);
+                v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
+                v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+              }
+              *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+              __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + roff + col;
+              if (p.accumulate) {
+                float a[8];
+                load8_bf16(cp, a);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += a[j];
+              }
+              store8_bf16(cp, v);
+            }
+          } else {
+            // ragged tail of N: scalar path
+            for (int j = 0; j < 8 && col + j < p.N; ++j) {
+              const size_t o = roff + col + j;
+              float x = v[j];
+              if (p.aux) x *= gelu_erf_grad(__bfloat162float(p.aux[o]));
+              if (p.pre) p.pre[o] = __float2bfloat16_rn(x);
+              if (p.act == S4_ACT_GELU) x = gelu_erf(x);
+              if (p.res) x += __bfloat162float(p.res[o]);
+              if (p.c_f32) {
+                float* cp = reinterpret_cast<float*>(p.c) + o;
+                if (p.accumulate) x += *cp;
+                *cp = x;
+              } else {
+                __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + o;
+                if (p.accumulate) x += __bfloat162float(*cp);
+                *cp = __float2bfloat16_rn(x);
+              }
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                             CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)f;
+  }
+  return fn;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      s4_set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return S4_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long long total = (long long)p.tiles_m * p.tiles_n * p.nb * p.splits;
+  const int grid = (int)std::min<long long>(total, s4_num_sms());
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  return s4_check_launch("gemm_tc");
+}
+
+int launch_any(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p,
+               cudaStream_t stream) {
+  if (BN == 256) return launch_bn<256>(ta, tb, p, stream);
+  if (BN == 128) return launch_bn<128>(ta, tb, p, stream);
+  return launch_bn<64>(ta, tb, p, stream);
+}
+
+int pick_bn(int M, int N, int nb, int splits) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  const long long tm = (M + BM - 1) / BM;
+  const int sms = s4_num_sms();
+  auto eff = [&](int bn) {
+    const long long tiles = tm * ((N + bn - 1) / bn) * nb * splits;
+    const long long waves = (tiles + sms - 1) / sms;
+    // useful work / occupied tile slots (accounts for the N tail too)
+    return (double)((double)tm * N * nb * splits) / ((double)waves * sms * bn);
+  };
+  const double e256 = eff(256), e128 = eff(128);
+  return e256 >= 0.97 * e128 ? 256 : 128;
+}
+
+bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+}  // namespace
+
+int s4_make_tmap_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4],
+                      const uint64_t strides_elems[3], const uint32_t box[4]) {
+  EncodeFn fn = get_encode_fn();
+  if (!fn) {
+    s4_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return S4_ERR_CUDA;
+  }
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < 3; ++i) gstr[i] = strides_elems[i] * 2;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, bx,
+                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    s4_set_error("cuTensorMapEncodeTiled failed (%d): dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] box=[%u,%u,%u,%u]",
+                 (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                 (unsigned long long)dims[2], (unsigned long long)dims[3],
+                 (unsigned long long)strides_elems[0], (unsigned long long)strides_elems[1],
+                 (unsigned long long)strides_elems[2], box[0], box[1], box[2], box[3]);
+    return S4_ERR_CUDA;
+  }
+  return S4_OK;
+}
+
+static int env_tc_disable_mn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("S4_TC_NO_MNMAJOR");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
+bool s4_gemm_tc_supported(const S4GemmParams& p) {
+  if (p.dtype != S4_BF16) return false;
+  if (p.M < 1 || p.N < 1 || p.K < 1) return false;
+  if (!aligned16(p.a) || !aligned16(p.b) || !aligned16(p.c)) return false;
+  const bool a_k = p.a_sk == 1, a_mn = p.a_sm == 1 && !a_k;
+  const bool b_k = p.b_sk == 1, b_mn = p.b_sn == 1 && !b_k;
+  if (!(a_k || a_mn) || !(b_k || b_mn)) return false;
+  if ((a_mn || b_mn) && env_tc_disable_mn()) return false;
+  const long long a_ld = a_k ? p.a_sm : p.a_sk, b_ld = b_k ? p.b_sn : p.b_sk;
+  if (a_ld % 8 || b_ld % 8) return false;
+  if (p.nb1 > 1 && (p.a_b1 % 8 || p.b_b1 % 8)) return false;
+  if (p.nb2 > 1 && (p.a_b2 % 8 || p.b_b2 % 8)) return false;
+  const int cvec = p.c_dtype == S4_F32 ? 4 : 8;
+  if (p.c_sm % cvec) return false;
+  if (p.nb1 > 1 && p.c_b1 % cvec) return false;
+  if (p.nb2 > 1 && p.c_b2 % cvec) return false;
+  if ((p.aux && !aligned16(p.aux)) || (p.res && !aligned16(p.res)) || (p.pre && !aligned16(p.pre)))
+    return false;
+  if ((p.aux || p.res || p.pre) && p.c_sm % 8) return false;
+  if (p.split_k > 1 && !(p.accumulate && p.c_dtype == S4_F32 && !p.bias && !p.aux && !p.res &&
+                         !p.pre && p.act == S4_ACT_NONE))
+    return false;
+  if ((long long)p.nb1 * p.nb2 > 65535) return false;
+  return true;
+}
+
+int s4_gemm_tc_launch(const S4GemmParams& g, cudaStream_t stream) {
+  const bool a_mn = g.a_sk != 1, b_mn = g.b_sk != 1;
+  const int nb = g.nb1 * g.nb2;
+  const int kblocks = (g.K + BK - 1) / BK;
+  int splits = g.split_k > 1 ? g.split_k : 1;
+  if (splits > kblocks) splits = kblocks;
+  int kb_per = (kblocks + splits - 1) / splits;
+  splits = (kblocks + kb_per - 1) / kb_per;
+  const int BN = pick_bn(g.M, g.N, nb, splits);
+
+  CUtensorMap ta, tb;
+  int rc;
+  {
+    // strides of size-1 batch dims only need to be legal (16-B multiples); the coordinate is 0
+    const uint64_t ld = a_mn ? g.a_sk : g.a_sm;
+    const uint64_t inner = a_mn ? g.M : g.K, outer = a_mn ? g.K : g.M;
+    const uint64_t dims[4] = {inner, outer, (uint64_t)g.nb2, (uint64_t)g.nb1};
+    const uint64_t s2[3] = {ld, g.nb2 > 1 ? (uint64_t)g.a_b2 : ld * 8, g.nb1 > 1 ? (uint64_t)g.a_b1 : ld * 8};
+    const uint32_t box[4] = {64, a_mn ? (uint32_t)BK : (uint32_t)BM, 1, 1};
+    if ((rc = s4_make_tmap_bf16(&ta, g.a, dims, s2, box))) return rc;
+  }
+  {
+    const uint64_t ld = b_mn ? g.b_sk : g.b_sn;
+    const uint64_t inner = b_mn ? g.N : g.K, outer = b_mn ? g.K : g.N;
+    const uint64_t dims[4] = {inner, outer, (uint64_t)g.nb2, (uint64_t)g.nb1};
+    uint64_t s2[3] = {ld, g.nb2 > 1 ? (uint64_t)g.b_b2 : ld * 8, g.nb1 > 1 ? (uint64_t)g.b_b1 : ld * 8};
+    const uint32_t box[4] = {64, b_mn ? (uint32_t)BK : (uint32_t)BN, 1, 1};
+    if ((rc = s4_make_tmap_bf16(&tb, g.b, dims, s2, box))) return rc;
+  }
+  TcParams p{};
+  p.tiles_m = (g.M + BM - 1) / BM;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  p.nb = nb; p.nb2 = g.nb2; p.splits = splits;
+  p.M = g.M; p.N = g.N;
+  p.kblocks = kblocks; p.kb_per_split = kb_per;
+  p.a_mode = a_mn ? OP_MNMAJOR : OP_KMAJOR;
+  p.b_mode = b_mn ? OP_MNMAJOR : OP_KMAJOR;
+  p.rows_valid = BM; p.row_pitch = BM;
+  p.c = g.c; p.bias = g.bias;
+  p.aux = (const __nv_bfloat16*)g.aux; p.res = (const __nv_bfloat16*)g.res; p.pre = (__nv_bfloat16*)g.pre;
+  p.c_sm = g.c_sm; p.c_sn = 1; p.c_b1 = g.c_b1; p.c_b2 = g.c_b2;
+  p.alpha = g.alpha; p.act = g.act; p.accumulate = g.accumulate;
+  p.c_f32 = g.c_dtype == S4_F32; p.atomic = splits > 1;
+  return launch_any(BN, ta, tb, p, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// 3x3 convolution (NHWC bf16) as implicit GEMM
+// ------------------------------------------------------------------------------------------
+static bool conv_tile_shape(int H, int W, int& TW, int& TH) {
+  if (W >= 128) {
+    // widest divisor of W that is <= 128 and a multiple of 8
+    TW = 0;
+    for (int t = 128; t >= 8; t -= 8)
+      if (W % t == 0) { TW = t; break; }
+    TH = 1;
+    return TW >= 64;
+  }
+  TW = W;
+  TH = 128 / W;
+  while (TH > 1 && H % TH) --TH;
+  return TW % 8 == 0 && TH >= 1 && TW * TH >= 64;
+}
+
+bool s4_conv3x3_tc_supported(int B, int H, int W, int Cin, int Cout, int dtype) {
+  if (dtype != S4_BF16) return false;
+  if (Cin % 64 || Cout % 8) return false;
+  int TW, TH;
+  return conv_tile_shape(H, W, TW, TH);
+}
+
+int s4_conv3x3_tc(const void* x, const void* w_packed, void* y, int B, int H, int W, int Cin,
+                  int Cout, cudaStream_t stream) {
+  int TW, TH;
+  if (!conv_tile_shape(H, W, TW, TH)) {
+    s4_set_error("conv3x3_tc: unsupported spatial shape %dx%d", H, W);
+    return S4_ERR_UNSUPPORTED;
+  }
+  const int K = 9 * Cin;
+  const int tiles_m = B * (H / TH) * (W / TW);
+  const int BN = pick_bn(tiles_m * BM, Cout, 1, 1);
+  CUtensorMap ta, tb;
+  int rc;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
+    const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+    if ((rc = s4_make_tmap_bf16(&ta, x, dims, str, box))) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)K, (uint64_t)Cout, 1, 1};
+    const uint64_t str[3] = {(uint64_t)K, (uint64_t)K * 8, (uint64_t)K * 8};
+    const uint32_t box[4] = {64, (uint32_t)BN, 1, 1};
+    if ((rc = s4_make_tmap_bf16(&tb, w_packed, dims, str, box))) return rc;
+  }
+  TcParams p{};
+  p.tiles_m = tiles_m;
+  p.tiles_n = (Cout + BN - 1) / BN;
+  p.nb = 1; p.nb2 = 1; p.splits = 1;
+  // tile mt covers pixels [mt*rows_valid, (mt+1)*rows_valid): contiguous in NHWC because
+  // either TW == W (whole rows) or TH == 1 (a row segment)
+  p.rows_valid = TW * TH; p.row_pitch = TW * TH;
+  p.M = B * H * W;
+  p.N = Cout;
+  p.kblocks = 9 * (Cin / 64);
+  p.kb_per_split = p.kblocks;
+  p.a_mode = OP_CONV_K; p.b_mode = OP_KMAJOR;
+  p.cH = H; p.cW = W; p.cTW = TW; p.cTH = TH; p.cblocks = Cin / 64;
+  p.c = y;
+  p.c_sm = Cout; p.c_sn = 1; p.c_b1 = 0; p.c_b2 = 0;
+  p.alpha = 1.f; p.c_f32 = 0;
+  return launch_any(BN, ta, tb, p, stream);
+}
+
+// dw[co][ci][tap] += sum_pix dy[pix][co] * x[pix+tap][ci]   (split over pixels, fp32 atomics)
+bool s4_conv3x3_wgrad_tc_supported(int B, int H, int W, int Cin, int Cout, int dtype) {
+  if (dtype != S4_BF16 || env_tc_disable_mn()) return false;
+  if (Cin % 8 || Cout % 8) return false;
+  // a k-block is 64 consecutive pixels inside one image: a row segment, or whole rows
+  if (W >= 64) return W % 64 == 0;
+  return 64 % W == 0 && H % (64 / W) == 0 && W % 8 == 0;
+}
+
+int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin,
+                        int Cout, cudaStream_t stream) {
+  const long long P = (long long)B * H * W;
+  const int TWk = W >= 64 ? 64 : W, THk = 64 / TWk;
+  const int kblocks = (int)(P / 64);
+  const int BN = Cin >= 256 ? 256 : (Cin >= 128 ? 128 : 64);
+  CUtensorMap ta, tb;
+  int rc;
+  {
+    // A = dy^T, MN-major: inner = Cout, outer = pixels
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)P, 1, 1};
+    const uint64_t str[3] = {(uint64_t)Cout, (uint64_t)Cout * 8, (uint64_t)Cout * 8};
+    const uint32_t box[4] = {64, (uint32_t)BK, 1, 1};
+    if ((rc = s4_make_tmap_bf16(&ta, dy, dims, str, box))) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
+    const uint32_t box[4] = {64, (uint32_t)TWk, (uint32_t)THk, 1};
+    if ((rc = s4_make_tmap_bf16(&tb, x, dims, str, box))) return rc;
+  }
+  TcParams p{};
+  p.tiles_m = (Cout + BM - 1) / BM;
+  p.tiles_n = (Cin + BN - 1) / BN;
+  p.nb = 9; p.nb2 = 9;
+  const int base_tiles = p.tiles_m * p.tiles_n * 9;
+  int splits = (2 * s4_num_sms() + base_tiles - 1) / base_tiles;
+  if (splits > kblocks) splits = kblocks;
+  if (splits < 1) splits = 1;
+  int kb_per = (kblocks + splits - 1) / splits;
+  splits = (kblocks + kb_per - 1) / kb_per;
+  p.splits = splits;
+  p.M = Cout; p.N = Cin;
+  p.kblocks = kblocks; p.kb_per_split = kb_per;
+  p.a_mode = OP_MNMAJOR; p.b_mode = OP_CONV_MN;
+  p.cH = H; p.cW = W; p.cTW = TWk; p.cTH = THk; p.cblocks = 1;
+  p.rows_valid = BM; p.row_pitch = BM; p.a_nobatch = 1;
+  p.c = dw;
+  p.c_sm = (long long)Cin * 9; p.c_sn = 9; p.c_b1 = 0; p.c_b2 = 1;   // z2 = tap
+  p.alpha = 1.f; p.c_f32 = 1; p.atomic = 1; p.accumulate = 1;
+  return launch_any(BN, ta, tb, p, stream);
+}

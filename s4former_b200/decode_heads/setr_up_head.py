@@ -1,0 +1,146 @@
+"""SETR-PUP / Naive head -- B200-native mirror of
+``mmseg/models/decode_heads/setr_up_head.py:10-111`` (same kwargs and ``state_dict`` keys:
+``norm.*``, ``up_convs.{j}.0.conv.weight``, ``up_convs.{j}.0.bn.*``, ``conv_seg.*``).
+
+Execution plan (NHWC, compute dtype):
+  tokens --[row-gathered LayerNorm = feature tap + PatchMix un-shuffle + LN]--> [B,g,g,C]
+  stage j < n-1 : conv3x3 -> BN stats -> fused BN+ReLU+bilinear(x s)
+  last stage    : conv3x3 -> BN stats -> fused BN+ReLU+conv_seg(1x1) -> bilinear(x s) -> NCHW fp32
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..builder import HEADS
+from .decode_head import BaseDecodeHead
+
+
+class _ConvModule(nn.Module):
+    """Parameter holder named like mmcv ``ConvModule`` (conv without bias -> bn -> ReLU)."""
+
+    def __init__(self, cin, cout, k, norm_cfg):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=(k - 1) // 2, bias=False)
+        cfg = dict(norm_cfg)
+        typ = cfg.pop('type')
+        cfg.pop('requires_grad', None)
+        if typ not in ('BN', 'SyncBN'):
+            raise NotImplementedError(f'norm {typ}: only BN / SyncBN ConvModules are on the hot path')
+        self.sync = typ == 'SyncBN'
+        self.bn = nn.BatchNorm2d(cout, **cfg)
+        nn.init.kaiming_normal_(self.conv.weight, a=0, mode='fan_out', nonlinearity='relu')
+
+
+class _Upsample(nn.Module):
+    def __init__(self, scale_factor, mode, align_corners):
+        super().__init__()
+        self.scale_factor, self.mode, self.align_corners = float(scale_factor), mode, align_corners
+
+
+@HEADS.register_module()
+class SETRUPHead(BaseDecodeHead):
+    def __init__(self, norm_layer=dict(type='LN', eps=1e-6, requires_grad=True), num_convs=1,
+                 up_scale=4, kernel_size=3, use_addition_up_scale=False,
+                 init_cfg=[dict(type='Constant', val=1.0, bias=0, layer='LayerNorm'),
+                           dict(type='Normal', std=0.01, override=dict(name='conv_seg'))],
+                 **kwargs):
+        assert kernel_size in [1, 3], 'kernel_size must be 1 or 3.'
+        super().__init__(init_cfg=init_cfg, **kwargs)
+        assert isinstance(self.in_channels, int)
+        if kernel_size != 3 or use_addition_up_scale or self.align_corners:
+            raise NotImplementedError('SETR-PUP path: kernel_size=3, align_corners=False, no extra upscale')
+        if self.norm_cfg is None or self.act_cfg is None or self.act_cfg.get('type') != 'ReLU':
+            raise NotImplementedError('ConvModule must be conv -> BN/SyncBN -> ReLU')
+        if int(up_scale) != up_scale or num_convs < 1:
+            raise NotImplementedError('integer up_scale and num_convs >= 1 required')
+        self.norm = nn.LayerNorm(self.in_channels, eps=norm_layer.get('eps', 1e-5))
+        self.up_scale = int(up_scale)
+        self.up_convs = nn.ModuleList()
+        cin = self.in_channels
+        for _ in range(num_convs):
+            self.up_convs.append(nn.Sequential(
+                _ConvModule(cin, self.channels, kernel_size, self.norm_cfg),
+                _Upsample(up_scale, 'bilinear', self.align_corners)))
+            cin = self.channels
+        self._row_maps = {}
+
+    def init_weights(self):
+        nn.init.constant_(self.norm.weight, 1.0)
+        nn.init.constant_(self.norm.bias, 0.)
+        nn.init.normal_(self.conv_seg.weight, mean=0, std=0.01)
+        nn.init.constant_(self.conv_seg.bias, 0)
+        for uc in self.up_convs:
+            nn.init.kaiming_normal_(uc[0].conv.weight, a=0, mode='fan_out', nonlinearity='relu')
+            nn.init.constant_(uc[0].bn.weight, 1.)
+            nn.init.constant_(uc[0].bn.bias, 0.)
+
+    # -- row map: dst token row -> src row of the backbone's [B*L, D] matrix ------------------
+    def _row_map(self, B, g, has_cls, device, PatchMix_N, PatchMixIndex):
+        """Feature tap (+1 skips the cls row, vit.py:556-562) and, when PatchMix_N != 0, the
+        inverse block permutation of decode_head.py:186-212: out_block[perm[p]] = in_block[p]."""
+        Ls = g * g + (1 if has_cls else 0)
+        off = 1 if has_cls else 0
+        if PatchMix_N == 0:
+            key = (B, g, has_cls, str(device))
+            m = self._row_maps.get(key)
+            if m is None:
+                pos = torch.arange(g * g, dtype=torch.int64)
+                m = (torch.arange(B, dtype=torch.int64).view(B, 1) * Ls + off + pos.view(1, -1))
+                m = m.reshape(-1).to(torch.int32).to(device)
+                self._row_maps[key] = m
+            return m
+        n = int(PatchMix_N)
+        gb = g // n
+        perm = torch.as_tensor(PatchMixIndex).to('cpu', torch.int64).reshape(B, gb * gb)
+        inv = torch.empty_like(perm)
+        inv.scatter_(1, perm, torch.arange(gb * gb, dtype=torch.int64).expand(B, -1))
+        ty, tx = torch.meshgrid(torch.arange(g), torch.arange(g), indexing='ij')
+        qb = (ty // n) * gb + (tx // n)                      # destination block of each token
+        src_blk = inv[:, qb.reshape(-1)]                     # [B, g*g] source block
+        sy = (src_blk // gb) * n + (ty % n).reshape(1, -1)
+        sx = (src_blk % gb) * n + (tx % n).reshape(1, -1)
+        m = torch.arange(B, dtype=torch.int64).view(B, 1) * Ls + off + sy * g + sx
+        return m.reshape(-1).to(torch.int32).to(device, non_blocking=True)
+
+    def _group_info(self):
+        if self.up_convs[0][0].sync and self.training:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                return dict(world=dist.get_world_size(), group=None)
+        return None
+
+    def forward(self, x, PatchMix_N=0, PatchMixIndex=None, return_last_feat=False):
+        """setr_up_head.py:92-111."""
+        if return_last_feat:
+            raise NotImplementedError('return_last_feat is a visualisation path')
+        x = self._transform_inputs(x)
+        tok = getattr(x, '_s4_tokens', None)
+        if tok is not None:
+            x2d, B, L = tok
+            g = int(math.isqrt(L - 1))
+            has_cls = True
+        else:   # a foreign NCHW tensor: flatten to tokens (copy) in the compute dtype
+            B, Cc, h, w = x.shape
+            assert h == w, 'square feature maps expected'
+            g = h
+            x2d = ops.cast(x.permute(0, 2, 3, 1).reshape(B * h * w, Cc).contiguous(), ops.compute_dtype())
+            has_cls = False
+        row_map = self._row_map(B, g, has_cls, x2d.device, PatchMix_N, PatchMixIndex)
+        Ltok = g * g + 1
+        y = ops.HeadLNFn.apply(x2d, self, row_map, B, Ltok)
+        H = W = g
+        s = self.up_scale
+        gi = self._group_info()
+        n = len(self.up_convs)
+        for j, uc in enumerate(self.up_convs):
+            if j < n - 1:
+                y = ops.ConvBNReLUUpFn.apply(y, uc[0], B, H, W, s, self.training, gi)
+                H, W = H * s, W * s
+            else:
+                y = ops.ConvBNReLUClsUpFn.apply(y, uc[0], self.conv_seg, B, H, W, s, self.training, gi)
+        return y
+
+    def cls_seg(self, feat):
+        raise NotImplementedError('cls_seg is fused into the last up-conv stage of forward()')

@@ -1,0 +1,637 @@
+"""Host-side operator layer: thin Python wrappers and ``torch.autograd.Function``s over the
+C ABI (``include/s4former.h``).  PyTorch is used for device memory, streams and autograd
+bookkeeping only; every arithmetic step of the path runs in the CUDA library.
+
+Gradient convention: weight/bias gradients are ACCUMULATED IN PLACE into ``param.grad``
+(float32, allocated as zeros on first use) by the wgrad kernels; ``Function.backward`` returns
+``None`` for them.  This removes one read-modify-write pass per parameter per student pass
+(three passes share the weights in the S4Former step) and lets the data-parallel reducer
+consume a contiguous gradient buffer.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+_cfg = {'compute_dtype': torch.bfloat16, 'backend': L.BACKEND_AUTO, 'wgrad_split_k': 0}
+
+
+def set_compute_dtype(dtype):
+    """torch.bfloat16 (speed mode, tcgen05) or torch.float32 (validation mode, CUDA cores)."""
+    assert dtype in (torch.bfloat16, torch.float32)
+    _cfg['compute_dtype'] = dtype
+
+
+def compute_dtype():
+    return _cfg['compute_dtype']
+
+
+def set_backend(backend):
+    _cfg['backend'] = {'auto': L.BACKEND_AUTO, 'simt': L.BACKEND_SIMT, 'tc': L.BACKEND_TC}.get(backend, backend)
+
+
+def backend():
+    return _cfg['backend']
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _code(dtype):
+    return L.BF16 if dtype == torch.bfloat16 else L.F32
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.S4Error('s4former_b200 ops need CUDA tensors: there is no CPU fallback')
+
+
+# ----------------------------------------------------------------------------------------------
+# low-precision / repacked weight cache
+# ----------------------------------------------------------------------------------------------
+def bump_generation(p):
+    """Call after a raw-pointer kernel (EMA / SGD) has modified ``p`` in place."""
+    p._s4_gen = getattr(p, '_s4_gen', 0) + 1
+
+
+def _cache(p, key, make):
+    tag = (p._version, getattr(p, '_s4_gen', 0), p.data_ptr(), compute_dtype())
+    store = p.__dict__.setdefault('_s4_cache', {})
+    hit = store.get(key)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    val = make()
+    store[key] = (tag, val)
+    return val
+
+
+def cast(x, dtype):
+    if x.dtype == dtype:
+        return x
+    _require_cuda(x)
+    x = x.contiguous()
+    y = torch.empty_like(x, dtype=dtype)
+    L.call('s4_cast', _p(x), _p(y), x.numel(), _code(x.dtype), _code(dtype), _st())
+    return y
+
+
+def transpose2d(x):
+    """[R, C] -> [C, R] contiguous."""
+    r, c = x.shape
+    y = torch.empty((c, r), dtype=x.dtype, device=x.device)
+    L.call('s4_transpose', _p(x), _p(y), 1, r, c, _code(x.dtype), _st())
+    return y
+
+
+def lowp(p):
+    """The weight in the compute dtype ([out, in] as stored)."""
+    return _cache(p, 'lp', lambda: cast(p.detach().reshape(p.shape[0], -1), compute_dtype()))
+
+
+def lowp_t(p):
+    """The transposed weight ([in, out]) in the compute dtype, for dgrad."""
+    return _cache(p, 'lpt', lambda: transpose2d(lowp(p)))
+
+
+def conv_packed(p):
+    """(fwd [Cout, 9*Cin], dgrad [Cin, 9*Cout]) repacks of a [Cout, Cin, 3, 3] weight."""
+    def make():
+        cout, cin = p.shape[0], p.shape[1]
+        dt = compute_dtype()
+        wf = torch.empty((cout, 9 * cin), dtype=dt, device=p.device)
+        wd = torch.empty((cin, 9 * cout), dtype=dt, device=p.device)
+        L.call('s4_pack_conv3x3_weight', _p(p.detach()), _p(wf), _p(wd), cin, cout, _code(dt), _st())
+        return wf, wd
+    return _cache(p, 'conv', make)
+
+
+def grad_buffer(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+# ----------------------------------------------------------------------------------------------
+# GEMM
+# ----------------------------------------------------------------------------------------------
+def gemm(a, b, c, M, N, K, a_str, b_str, c_sm, batch=(1, 1), a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0),
+         bias=None, aux=None, res=None, pre=None, alpha=1.0, act=L.ACT_NONE, accumulate=False,
+         split_k=1, dtype=None, backend_override=None):
+    """C = epi(alpha * A @ B) with element strides a_str=(sm, sk), b_str=(sk, sn)."""
+    g = L.GemmParams()
+    g.a, g.b, g.c = _p(a), _p(b), _p(c)
+    g.bias, g.aux, g.res, g.pre = _p(bias), _p(aux), _p(res), _p(pre)
+    g.M, g.N, g.K = M, N, K
+    g.nb1, g.nb2 = batch
+    g.a_sm, g.a_sk = a_str
+    g.a_b1, g.a_b2 = a_bs
+    g.b_sk, g.b_sn = b_str
+    g.b_b1, g.b_b2 = b_bs
+    g.c_sm = c_sm
+    g.c_b1, g.c_b2 = c_bs
+    g.alpha, g.act, g.accumulate = alpha, act, int(accumulate)
+    g.dtype = _code(a.dtype if dtype is None else dtype)
+    g.c_dtype = _code(c.dtype)
+    g.backend = backend() if backend_override is None else backend_override
+    g.split_k = split_k
+    L.check(L.load().s4_gemm(C.byref(g), _st()), 's4_gemm')
+
+
+def _wgrad_split(M_out, N_out, K_red):
+    """split-K factor for weight gradients: enough CTAs to fill the machine."""
+    if _cfg['wgrad_split_k']:
+        return _cfg['wgrad_split_k']
+    tiles = ((M_out + 127) // 128) * ((N_out + 255) // 256)
+    kblocks = (K_red + 63) // 64
+    return max(1, min(kblocks, (2 * 148 + tiles - 1) // tiles))
+
+
+def linear_fwd(x, w_lp, bias, act=L.ACT_NONE, res=None, want_pre=False):
+    """y = act(x @ w^T + bias) + res ; x [M,K], w_lp [N,K]."""
+    M, K = x.shape
+    N = w_lp.shape[0]
+    y = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    pre = torch.empty_like(y) if want_pre else None
+    gemm(x, w_lp, y, M, N, K, (K, 1), (1, K), N, bias=bias, res=res, pre=pre, act=act)
+    return (y, pre) if want_pre else y
+
+
+def linear_dgrad(dy, w_lp_t, aux=None):
+    """dx = (dy @ w) * gelu'(aux) ; dy [M,N], w_lp_t [K,N] (transposed weight, K-major)."""
+    M, N = dy.shape
+    K = w_lp_t.shape[0]
+    dx = torch.empty((M, K), dtype=dy.dtype, device=dy.device)
+    gemm(dy, w_lp_t, dx, M, K, N, (N, 1), (1, N), K, aux=aux)
+    return dx
+
+
+def linear_wgrad(dy, x, w_param, b_param):
+    """w.grad [N,K] += dy^T x ; b.grad [N] += colsum(dy)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    gw = grad_buffer(w_param)
+    gemm(dy, x, gw, N, K, M, (1, N), (K, 1), K, accumulate=True, split_k=_wgrad_split(N, K, M))
+    if b_param is not None:
+        gb = grad_buffer(b_param)
+        L.call('s4_colsum', _p(dy), _p(gb), None, M, N, _code(dy.dtype), _st())
+
+
+# ----------------------------------------------------------------------------------------------
+# LayerNorm
+# ----------------------------------------------------------------------------------------------
+def layernorm_fwd(x2d, gamma, beta, eps, row_map=None, out_rows=None):
+    D = x2d.shape[1]
+    rows = x2d.shape[0] if out_rows is None else out_rows
+    y = torch.empty((rows, D), dtype=x2d.dtype, device=x2d.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    rstd = torch.empty_like(mean)
+    L.call('s4_layernorm_fwd', _p(x2d), _p(row_map), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd),
+           rows, D, eps, _code(x2d.dtype), _st())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x2d, gamma_p, beta_p, mean, rstd, row_map=None, dres=None, dx=None):
+    rows, D = dy.shape
+    if dx is None:
+        dx = torch.zeros_like(x2d) if row_map is not None else torch.empty_like(x2d)
+    L.call('s4_layernorm_bwd', _p(dy), _p(x2d), _p(row_map), _p(gamma_p.detach()), _p(mean), _p(rstd),
+           _p(dres), _p(dx), _p(grad_buffer(gamma_p)), _p(grad_buffer(beta_p)), rows, D,
+           _code(dy.dtype), _st())
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag='ws'):
+    """A growing scratch buffer per (device, stream, tag); contents are never kept across ops."""
+    key = (device, torch.cuda.current_stream().cuda_stream, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def attention_fwd(qkv, B, L_, H, hd, u0, gate, w):
+    out = torch.empty((B * L_, H * hd), dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty((B, H, L_), dtype=torch.float32, device=qkv.device)
+    dt = _code(qkv.dtype)
+    nbytes = L.load().s4_attention_workspace(B, H, L_, hd, dt)
+    ws = workspace(nbytes, qkv.device, 'attn')
+    L.call('s4_attention_fwd', _p(qkv), _p(u0), _p(gate), float(w), _p(out), _p(lse), _p(ws), nbytes,
+           B, H, L_, hd, dt, backend(), _st())
+    return out, lse
+
+
+def attention_bwd(dout, qkv, out, lse, B, L_, H, hd, u0, gate, w):
+    dqkv = torch.empty_like(qkv)
+    dt = _code(qkv.dtype)
+    nbytes = L.load().s4_attention_workspace(B, H, L_, hd, dt)
+    ws = workspace(nbytes, qkv.device, 'attn')
+    L.call('s4_attention_bwd', _p(dout), _p(qkv), _p(out), _p(lse), _p(u0), _p(gate), float(w),
+           _p(dqkv), _p(ws), nbytes, B, H, L_, hd, dt, backend(), _st())
+    return dqkv
+
+
+# ----------------------------------------------------------------------------------------------
+# transformer encoder layer (reference vit.py:113-127) as ONE autograd node
+# ----------------------------------------------------------------------------------------------
+class EncoderLayerFn(torch.autograd.Function):
+    """x + OutProj(Attn(LN1(x))) then + FFN(LN2(.)); ``layer`` supplies the parameters."""
+
+    @staticmethod
+    def forward(ctx, x, layer, B, Ltok, u0, gate, w):
+        M, D = x.shape
+        H = layer.num_heads
+        hd = D // H
+        mha = layer.attn.attn
+        fc1, fc2 = layer.ffn.layers[0][0], layer.ffn.layers[1]
+        eps = layer.ln1.eps
+        xl1, mean1, rstd1 = layernorm_fwd(x, layer.ln1.weight, layer.ln1.bias, eps)
+        qkv = linear_fwd(xl1, lowp(mha.in_proj_weight), mha.in_proj_bias)
+        att, lse = attention_fwd(qkv, B, Ltok, H, hd, u0, gate, w)
+        xm = linear_fwd(att, lowp(mha.out_proj.weight), mha.out_proj.bias, res=x)
+        xl2, mean2, rstd2 = layernorm_fwd(xm, layer.ln2.weight, layer.ln2.bias, eps)
+        h, pre = linear_fwd(xl2, lowp(fc1.weight), fc1.bias, act=L.ACT_GELU, want_pre=True)
+        y = linear_fwd(h, lowp(fc2.weight), fc2.bias, res=xm)
+        ctx.layer, ctx.dims, ctx.w = layer, (B, Ltok, H, hd), w
+        ctx.save_for_backward(x, xl1, mean1, rstd1, qkv, att, lse, xm, xl2, mean2, rstd2, pre, h, u0, gate)
+        layer._s4_pending = getattr(layer, '_s4_pending', 0) + 1
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        (x, xl1, mean1, rstd1, qkv, att, lse, xm, xl2, mean2, rstd2, pre, h, u0, gate) = ctx.saved_tensors
+        B, Ltok, H, hd = ctx.dims
+        mha = layer.attn.attn
+        fc1, fc2 = layer.ffn.layers[0][0], layer.ffn.layers[1]
+        dy = dy.contiguous()
+        # FFN
+        dpre = linear_dgrad(dy, lowp_t(fc2.weight), aux=pre)           # (dy W2) * gelu'(pre)
+        linear_wgrad(dy, h, fc2.weight, fc2.bias)
+        dxl2 = linear_dgrad(dpre, lowp_t(fc1.weight))
+        linear_wgrad(dpre, xl2, fc1.weight, fc1.bias)
+        dxm = layernorm_bwd(dxl2, xm, layer.ln2.weight, layer.ln2.bias, mean2, rstd2, dres=dy)
+        # attention block
+        datt = linear_dgrad(dxm, lowp_t(mha.out_proj.weight))
+        linear_wgrad(dxm, att, mha.out_proj.weight, mha.out_proj.bias)
+        dqkv = attention_bwd(datt, qkv, att, lse, B, Ltok, H, hd, u0, gate, ctx.w)
+        dxl1 = linear_dgrad(dqkv, lowp_t(mha.in_proj_weight))
+        linear_wgrad(dqkv, xl1, mha.in_proj_weight, mha.in_proj_bias)
+        dx = layernorm_bwd(dxl1, x, layer.ln1.weight, layer.ln1.bias, mean1, rstd1, dres=dxm)
+        layer._s4_pending -= 1
+        if layer._s4_pending == 0:
+            hook = getattr(layer, '_s4_grad_ready_hook', None)
+            if hook is not None:
+                hook(layer)
+        return dx, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# patch embedding + cls/pos assembly (reference embed.py:183-204, vit.py:483-513)
+# ----------------------------------------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cls_token, bb, img):
+        _require_cuda(img)
+        B, Cin, Himg, Wimg = img.shape
+        P = bb.patch_size
+        gh, gw = (Himg + P - 1) // P, (Wimg + P - 1) // P
+        proj = bb.patch_embed.projection
+        D = proj.weight.shape[0]
+        dt = compute_dtype()
+        a = torch.empty((B * gh * gw, Cin * P * P), dtype=dt, device=img.device)
+        L.call('s4_patchify', _p(img.contiguous()), _p(a), B, Cin, Himg, Wimg, P, _code(dt), _st())
+        tok = linear_fwd(a, lowp(proj.weight), proj.bias)
+        Ltok = gh * gw + 1
+        x = torch.empty((B * Ltok, D), dtype=dt, device=img.device)
+        L.call('s4_assemble_tokens', _p(tok), _p(cls_token.detach()), _p(bb.pos_embed.detach()), _p(x),
+               B, Ltok, D, _code(dt), _st())
+        ctx.bb, ctx.dims = bb, (B, Ltok, D)
+        ctx.save_for_backward(a)
+        bb._s4_pending = getattr(bb, '_s4_pending', 0) + 1
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        bb = ctx.bb
+        (a,) = ctx.saved_tensors
+        B, Ltok, D = ctx.dims
+        dx = dx.contiguous()
+        dtok = torch.empty((B * (Ltok - 1), D), dtype=dx.dtype, device=dx.device)
+        gcls = torch.zeros_like(bb.cls_token)
+        L.call('s4_assemble_tokens_bwd', _p(dx), _p(dtok), _p(gcls), _p(grad_buffer(bb.pos_embed)),
+               B, Ltok, D, _code(dx.dtype), _st())
+        proj = bb.patch_embed.projection
+        linear_wgrad(dtok, a, proj.weight, proj.bias)
+        bb._s4_pending -= 1
+        if bb._s4_pending == 0:
+            hook = getattr(bb, '_s4_grad_ready_hook', None)
+            if hook is not None:
+                hook(bb)
+        return gcls, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# SETR-PUP head stages
+# ----------------------------------------------------------------------------------------------
+def _all_reduce_stats(t, group_info):
+    """SyncBN: sum the per-rank statistics over the data-parallel group (reference N2)."""
+    if group_info is not None and group_info.get('world', 1) > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, group=group_info.get('group'))
+    return t
+
+
+class HeadLNFn(torch.autograd.Function):
+    """Feature tap (drop cls) + PatchMix un-shuffle + LayerNorm, as a row-gathered LN
+    (reference setr_up_head.py:96-104, decode_head.py:186-212)."""
+
+    @staticmethod
+    def forward(ctx, x_tokens, head, row_map, B, Ltok):
+        D = x_tokens.shape[1]
+        rows = B * (Ltok - 1)
+        y, mean, rstd = layernorm_fwd(x_tokens, head.norm.weight, head.norm.bias, head.norm.eps,
+                                      row_map=row_map, out_rows=rows)
+        ctx.head = head
+        ctx.save_for_backward(x_tokens, mean, rstd, row_map)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_tokens, mean, rstd, row_map = ctx.saved_tensors
+        head = ctx.head
+        dx = layernorm_bwd(dy.contiguous(), x_tokens, head.norm.weight, head.norm.bias, mean, rstd,
+                           row_map=row_map)
+        return dx, None, None, None, None
+
+
+def _bn_scale_shift(conv_bn, y2d, rows, training, group_info):
+    """BatchNorm statistics of the conv output (training: batch stats, all-reduced for SyncBN;
+    eval: running stats).  Returns (scale, shift, mean, invstd, count)."""
+    bn = conv_bn.bn
+    Cc = y2d.shape[1]
+    dev = y2d.device
+    scale = torch.empty(Cc, dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    if not training:
+        L.call('s4_bn_eval_affine', _p(bn.running_mean), _p(bn.running_var), _p(bn.weight.detach()),
+               _p(bn.bias.detach()), bn.eps, _p(scale), _p(shift), Cc, _st())
+        return scale, shift, None, None, 0.0
+    stats = torch.zeros((2, Cc), dtype=torch.float32, device=dev)
+    L.call('s4_colsum', _p(y2d), _p(stats[0]), _p(stats[1]), rows, Cc, _code(y2d.dtype), _st())
+    count = float(rows)
+    if group_info is not None and group_info.get('world', 1) > 1:
+        _all_reduce_stats(stats, group_info)
+        count *= group_info['world']
+    mean = torch.empty_like(scale)
+    invstd = torch.empty_like(scale)
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    L.call('s4_bn_finalize', _p(stats[0]), _p(stats[1]), count, bn.eps, mom, _p(bn.weight.detach()),
+           _p(bn.bias.detach()), _p(mean), _p(invstd), _p(scale), _p(shift), _p(bn.running_mean),
+           _p(bn.running_var), Cc, _st())
+    bn.num_batches_tracked += 1
+    return scale, shift, mean, invstd, count
+
+
+class ConvBNReLUUpFn(torch.autograd.Function):
+    """conv3x3(no bias) -> BN -> ReLU -> bilinear x s  (one SETR-PUP stage, NHWC)."""
+
+    @staticmethod
+    def forward(ctx, x, stage, B, H, W, s, training, group_info):
+        conv = stage.conv
+        Cout, Cin = conv.weight.shape[0], conv.weight.shape[1]
+        wf, _ = conv_packed(conv.weight)
+        dt = _code(x.dtype)
+        y = torch.empty((B * H * W, Cout), dtype=x.dtype, device=x.device)
+        L.call('s4_conv3x3_fwd', _p(x), _p(wf), _p(y), B, H, W, Cin, Cout, dt, backend(), _st())
+        scale, shift, mean, invstd, count = _bn_scale_shift(stage, y, B * H * W, training, group_info)
+        out = torch.empty((B * H * s * W * s, Cout), dtype=x.dtype, device=x.device)
+        L.call('s4_bn_relu_upsample_fwd', _p(y), _p(scale), _p(shift), _p(out), B, H, W, Cout, s, dt, _st())
+        ctx.stage, ctx.dims, ctx.group_info, ctx.count = stage, (B, H, W, s, Cin, Cout), group_info, count
+        if training:
+            ctx.save_for_backward(x, y, scale, shift, mean, invstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, scale, shift, mean, invstd = ctx.saved_tensors
+        stage = ctx.stage
+        B, H, W, s, Cin, Cout = ctx.dims
+        dt = _code(x.dtype)
+        dout = dout.contiguous()
+        dact = torch.empty_like(y)
+        sums = torch.zeros((2, Cout), dtype=torch.float32, device=x.device)
+        L.call('s4_bn_relu_upsample_bwd', _p(dout), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd),
+               _p(dact), _p(sums[0]), _p(sums[1]), B, H, W, Cout, s, dt, _st())
+        dx = _conv_bn_backward(stage, x, y, dact, sums, mean, invstd, ctx.count, ctx.group_info,
+                               B, H, W, Cin, Cout, need_dx=ctx.needs_input_grad[0])
+        return dx, None, None, None, None, None, None, None
+
+
+def _conv_bn_backward(stage, x, y, dact, sums, mean, invstd, count, group_info, B, H, W, Cin, Cout,
+                      need_dx=True):
+    """Shared tail of the stage backward: BN backward (local dgamma/dbeta, global reduction of the
+    two sums under SyncBN) -> conv wgrad / dgrad."""
+    bn, conv = stage.bn, stage.conv
+    dt = _code(x.dtype)
+    grad_buffer(bn.bias).add_(sums[0])      # dbeta  = sum dact        (local, like torch SyncBN)
+    grad_buffer(bn.weight).add_(sums[1])    # dgamma = sum dact * xhat
+    gsums = sums
+    if group_info is not None and group_info.get('world', 1) > 1:
+        gsums = _all_reduce_stats(sums.clone(), group_info)
+    dyc = torch.empty_like(y)
+    L.call('s4_bn_bwd_apply', _p(dact), _p(y), _p(bn.weight.detach()), _p(mean), _p(invstd),
+           _p(gsums[0]), _p(gsums[1]), count, _p(dyc), B * H * W, Cout, dt, _st())
+    L.call('s4_conv3x3_wgrad', _p(x), _p(dyc), _p(grad_buffer(conv.weight)), B, H, W, Cin, Cout, dt,
+           backend(), _st())
+    dx = None
+    if need_dx:
+        _, wd = conv_packed(conv.weight)
+        dx = torch.empty_like(x)
+        L.call('s4_conv3x3_dgrad', _p(dyc), _p(wd), _p(dx), B, H, W, Cin, Cout, dt, backend(), _st())
+    return dx
+
+
+class ConvBNReLUClsUpFn(torch.autograd.Function):
+    """Last stage: conv3x3 -> BN -> ReLU -> conv_seg (1x1) -> bilinear x s -> NCHW fp32 logits.
+    conv_seg is applied before the upsample (they commute), so the 256-channel full-resolution
+    tensor of the reference never exists."""
+
+    @staticmethod
+    def forward(ctx, x, stage, conv_seg, B, H, W, s, training, group_info):
+        conv = stage.conv
+        Cout, Cin = conv.weight.shape[0], conv.weight.shape[1]
+        NC = conv_seg.weight.shape[0]
+        wf, _ = conv_packed(conv.weight)
+        dt = _code(x.dtype)
+        rows = B * H * W
+        y = torch.empty((rows, Cout), dtype=x.dtype, device=x.device)
+        L.call('s4_conv3x3_fwd', _p(x), _p(wf), _p(y), B, H, W, Cin, Cout, dt, backend(), _st())
+        scale, shift, mean, invstd, count = _bn_scale_shift(stage, y, rows, training, group_info)
+        z = torch.empty((rows, NC), dtype=torch.float32, device=x.device)
+        w2 = conv_seg.weight.detach().reshape(NC, Cout)
+        L.call('s4_bn_relu_conv1x1_fwd', _p(y), _p(scale), _p(shift), _p(w2), _p(conv_seg.bias.detach()),
+               _p(z), rows, Cout, NC, dt, _st())
+        logits = torch.empty((B, NC, H * s, W * s), dtype=torch.float32, device=x.device)
+        L.call('s4_upsample_logits_fwd', _p(z), _p(logits), B, H, W, NC, s, _st())
+        ctx.stage, ctx.conv_seg, ctx.group_info, ctx.count = stage, conv_seg, group_info, count
+        ctx.dims = (B, H, W, s, Cin, Cout, NC)
+        if training:
+            ctx.save_for_backward(x, y, scale, shift, mean, invstd)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x, y, scale, shift, mean, invstd = ctx.saved_tensors
+        stage, conv_seg = ctx.stage, ctx.conv_seg
+        B, H, W, s, Cin, Cout, NC = ctx.dims
+        dt = _code(x.dtype)
+        rows = B * H * W
+        dlogits = dlogits.contiguous()
+        dz = torch.empty((rows, NC), dtype=torch.float32, device=x.device)
+        L.call('s4_upsample_logits_bwd', _p(dlogits), _p(dz), B, H, W, NC, s, _st())
+        dact = torch.empty_like(y)
+        sums = torch.zeros((2, Cout), dtype=torch.float32, device=x.device)
+        w2 = conv_seg.weight.detach().reshape(NC, Cout)
+        L.call('s4_bn_relu_conv1x1_bwd', _p(dz), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd),
+               _p(w2), _p(dact), _p(grad_buffer(conv_seg.weight)), _p(grad_buffer(conv_seg.bias)),
+               _p(sums[0]), _p(sums[1]), rows, Cout, NC, dt, _st())
+        dx = _conv_bn_backward(stage, x, y, dact, sums, mean, invstd, ctx.count, ctx.group_info,
+                               B, H, W, Cin, Cout, need_dx=ctx.needs_input_grad[0])
+        return dx, None, None, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# losses / pseudo labels / augmentation / EMA
+# ----------------------------------------------------------------------------------------------
+class CeNcrFn(torch.autograd.Function):
+    """(loss_ce, loss_ncr) = (w_ce/P * sum_valid nll, w_ncr/P * sum_valid ||p_s - p_t + eps||)."""
+
+    @staticmethod
+    def forward(ctx, logits_s, logits_t, label, ce_w, ncr_w, ignore_index):
+        _require_cuda(logits_s, label)
+        logits_s = logits_s.contiguous()
+        assert logits_s.dtype == torch.float32 and label.dtype == torch.int64
+        B, Cc, H, W = logits_s.shape
+        label = label.reshape(B, H, W).contiguous()
+        if logits_t is not None:
+            logits_t = logits_t.contiguous()
+        out = torch.empty(3, dtype=torch.float32, device=logits_s.device)
+        nbytes = L.load().s4_ce_ncr_workspace(B, H, W)
+        ws = workspace(nbytes, logits_s.device, 'loss')
+        L.call('s4_ce_ncr', _p(logits_s), _p(logits_t), _p(label), None, _p(out), None, B, Cc, H, W,
+               float(ce_w), float(ncr_w), int(ignore_index), _p(ws), nbytes, _st())
+        ctx.args = (float(ce_w), float(ncr_w), int(ignore_index))
+        ctx.save_for_backward(logits_s, logits_t, label)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_ce, g_ncr, _g_cnt):
+        logits_s, logits_t, label = ctx.saved_tensors
+        ce_w, ncr_w, ignore_index = ctx.args
+        B, Cc, H, W = logits_s.shape
+        dev = logits_s.device
+        gs = torch.stack([g_ce if g_ce is not None else torch.zeros((), device=dev),
+                          g_ncr if g_ncr is not None else torch.zeros((), device=dev)]).float().contiguous()
+        dz = torch.empty_like(logits_s)
+        nbytes = L.load().s4_ce_ncr_workspace(B, H, W)
+        ws = workspace(nbytes, dev, 'loss')
+        L.call('s4_ce_ncr', _p(logits_s), _p(logits_t), _p(label), _p(dz), None, _p(gs), B, Cc, H, W,
+               ce_w, ncr_w, ignore_index, _p(ws), nbytes, _st())
+        return dz, None, None, None, None, None
+
+
+def cross_entropy(logits, label, loss_weight=1.0, ignore_index=255):
+    return CeNcrFn.apply(logits, None, label, loss_weight, 0.0, ignore_index)[0]
+
+
+def pseudo_label(logits_t, threshold, patch=16):
+    """-> (hard [B,H,W] i64 with 255 where unconfident, conf [B,H,W] i64, u [B,H/p,W/p] f32)."""
+    _require_cuda(logits_t)
+    logits_t = logits_t.contiguous()
+    B, Cc, H, W = logits_t.shape
+    dev = logits_t.device
+    hard = torch.empty((B, H, W), dtype=torch.int64, device=dev)
+    conf = torch.empty_like(hard)
+    u = torch.empty((B, H // patch, W // patch), dtype=torch.float32, device=dev)
+    L.call('s4_pseudo_label', _p(logits_t), _p(hard), _p(conf), _p(u), B, Cc, H, W, patch,
+           float(threshold), _st())
+    return hard, conf, u
+
+
+def cutmix(img, label, boxes):
+    """boxes: list of (y0, y1, x0, x1) from the host RNG."""
+    _require_cuda(img)
+    B, Cc, H, W = img.shape
+    bx = torch.tensor(boxes, dtype=torch.int32).reshape(B, 4).to(img.device, non_blocking=True)
+    out_img = torch.empty_like(img)
+    out_lab = torch.empty_like(label) if label is not None else None
+    L.call('s4_cutmix', _p(img.contiguous()), _p(label.contiguous() if label is not None else None),
+           _p(bx), _p(out_img), _p(out_lab), B, Cc, H, W, _st())
+    return out_img, out_lab
+
+
+def patchshuffle(img, perms, block):
+    _require_cuda(img)
+    B, Cc, H, W = img.shape
+    pm = perms.to(device=img.device, dtype=torch.int64, non_blocking=True).contiguous()
+    out = torch.empty_like(img)
+    L.call('s4_patchshuffle', _p(img.contiguous()), _p(pm), _p(out), B, Cc, H, W, int(block), _st())
+    return out
+
+
+class TensorTable:
+    """Device-resident pointer/chunk table for the multi-tensor kernels."""
+
+    def __init__(self, lists, device, lrs=None):
+        chunk = L.load().s4_chunk_elems()
+        sizes = [t.numel() for t in lists[0]]
+        for lst in lists:
+            assert [t.numel() for t in lst] == sizes
+        self.ptrs = [torch.tensor([t.data_ptr() for t in lst], dtype=torch.int64).to(device) for lst in lists]
+        self.sizes = torch.tensor(sizes, dtype=torch.int64).to(device)
+        ct, co = [], []
+        for i, n in enumerate(sizes):
+            for off in range(0, n, chunk):
+                ct.append(i)
+                co.append(off)
+        self.chunk_tensor = torch.tensor(ct, dtype=torch.int32).to(device)
+        self.chunk_off = torch.tensor(co, dtype=torch.int64).to(device)
+        self.n_chunks = len(ct)
+        self.lrs = None if lrs is None else torch.tensor(lrs, dtype=torch.float32).to(device)
+        self.key = tuple(t.data_ptr() for lst in lists for t in lst)
+        self.keep = lists
+
+
+def ema_update(table, momentum):
+    """dst = m*dst + (1-m)*src over every tensor pair of the table (one launch)."""
+    L.call('s4_ema_multi_tensor', _p(table.ptrs[0]), _p(table.ptrs[1]), _p(table.sizes),
+           _p(table.chunk_tensor), _p(table.chunk_off), table.n_chunks, float(momentum),
+           float(1 - momentum), _st())
+    for t in table.keep[0]:
+        bump_generation(t)
+
+
+def sgd_step(table, momentum, weight_decay, first_step, lrs=None):
+    if lrs is not None:
+        table.lrs.copy_(torch.tensor(lrs, dtype=torch.float32), non_blocking=True)
+    shadow = table.ptrs[3] if len(table.ptrs) > 3 else None
+    L.call('s4_sgd_multi_tensor', _p(table.ptrs[0]), _p(table.ptrs[1]), _p(table.ptrs[2]), _p(shadow),
+           _p(table.sizes), _p(table.lrs), _p(table.chunk_tensor), _p(table.chunk_off), table.n_chunks,
+           float(momentum), float(weight_decay), int(first_step), _st())
+    for t in table.keep[0]:
+        bump_generation(t)

@@ -1,0 +1,358 @@
+"""``EncoderDecoder`` with the S4Former semi-supervised train step -- B200-native mirror of
+``mmseg/models/segmentors/encoder_decoder.py`` (reference file:line cited per method).
+
+The Python control flow of ``forward_train`` (:386-514) and ``foward_unsup_train`` (:516-687)
+is kept (same kwargs, same loss-dict keys, same host RNG call order); the arithmetic is
+dispatched to the CUDA library:
+
+  EMA update (:1044-1066)                    -> one multi-tensor kernel          (ops.ema_update)
+  teacher pseudo labels (:875-904, :541-542) -> one fused kernel incl. the patch
+  + patch unconfidence (:547-555)               unconfidence                     (ops.pseudo_label)
+  masked CE + NCR (:906-954)                 -> one fused fwd/bwd kernel         (ops.CeNcrFn)
+  CutMix / PatchShuffle (:633-638)           -> two gather kernels               (utils.generate_unsup_data)
+
+Options outside the shipped configs (unimatch, ClassMix, CutOut, fdrop, soft labels, neck,
+projection heads, sup-branch NCR, ...) raise ``NotImplementedError`` at construction.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import builder, ops
+from ..builder import SEGMENTORS
+from ..utils.generate_unsup_data import generate_unsup_cutmix_data, generate_unsup_patchmix_data
+from ..utils.structual_utils import add_prefix, dict_split, weighted_loss
+from .base import BaseSegmentor
+
+
+@SEGMENTORS.register_module()
+class EncoderDecoder(BaseSegmentor):
+    def __init__(self,
+                 backbone, decode_head, neck=None, auxiliary_head=None, projection_head=None,
+                 backbone_ema=None, decode_head_ema=None, neck_ema=None, auxiliary_head_ema=None,
+                 projection_head_ema=None, backbone_pretrain=None, pretrained=None, train_cfg=None,
+                 test_cfg=None, init_cfg=None,
+                 ema=False, sup_ema=False, ema_momentum=0.999, attn_frozen=False, attn_frozen_rate=0.0,
+                 momentum_backbone=None, momentum_head=None, momentum_head_dropout=0.0,
+                 momentum_head_exp=0.0, momentum_exp=0.0, ema_test=False,
+                 sup_ClassMix=False, sup_cutmix=False,
+                 unsup_weight=2.0, unsup_confidence=0.75, unsup_soft=False, unsup_temperature=1.0,
+                 iter_unsup_start=0,
+                 strong_aug_prob=0.5, cutout_area=2, use_CutMix=False, use_CutOut=False,
+                 use_ClassMix=False, mix_with_labeled=False, patchwise=False,
+                 use_PatchShuffle=False, PatchMix_N=8, patchmix_ratio=0.5, patchsize=16,
+                 use_PatchShuffle_w_Classmix=False, use_PatchShuffle_w_Cutmix=False,
+                 no_pos_embed=False, avg_pos_emd=False, duplicate_pos_emd=False,
+                 adaptive_attn_mask=False, attn_mask_weight=50, attn_mask_seperate_head=False,
+                 attn_mask_w_fdrop=False,
+                 negative_class_ranking=False, negative_class_ranking_mode='sup_only',
+                 use_fdrop=False, unimatch=False, fdrop_loss_weight=0.5, use_cutmix_adaptive=False):
+        super().__init__(init_cfg)
+        unsupported = dict(
+            neck=neck, projection_head=projection_head, neck_ema=neck_ema,
+            auxiliary_head_ema=auxiliary_head_ema, projection_head_ema=projection_head_ema,
+            backbone_pretrain=backbone_pretrain, sup_ema=sup_ema, attn_frozen=attn_frozen,
+            momentum_head_dropout=momentum_head_dropout, momentum_head_exp=momentum_head_exp,
+            momentum_exp=momentum_exp, sup_ClassMix=sup_ClassMix, sup_cutmix=sup_cutmix,
+            unsup_soft=unsup_soft, use_CutOut=use_CutOut, use_ClassMix=use_ClassMix,
+            mix_with_labeled=mix_with_labeled, patchwise=patchwise, use_PatchShuffle=use_PatchShuffle,
+            use_PatchShuffle_w_Classmix=use_PatchShuffle_w_Classmix, no_pos_embed=no_pos_embed,
+            avg_pos_emd=avg_pos_emd, duplicate_pos_emd=duplicate_pos_emd,
+            attn_mask_w_fdrop=attn_mask_w_fdrop, use_fdrop=use_fdrop, unimatch=unimatch,
+            use_cutmix_adaptive=use_cutmix_adaptive)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad or unsup_temperature != 1.0:
+            raise NotImplementedError(
+                f'options outside the S4Former train-step scope (SURVEY.md section 8): {bad}'
+                + (' unsup_temperature' if unsup_temperature != 1.0 else ''))
+        if negative_class_ranking and negative_class_ranking_mode != 'unsup_only':
+            raise NotImplementedError("only negative_class_ranking_mode='unsup_only' (the shipped config)")
+        if pretrained is not None:
+            assert backbone.get('pretrained') is None, 'both backbone and segmentor set pretrained weight'
+            backbone = dict(backbone, pretrained=pretrained)
+        self.backbone = builder.build_backbone(backbone)
+        self._init_decode_head(decode_head)
+        self._init_auxiliary_head(auxiliary_head)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.unsup_weight, self.unsup_confidence = unsup_weight, unsup_confidence
+        self.unsup_soft, self.unsup_temperature = unsup_soft, unsup_temperature
+        self.iter_unsup_start = iter_unsup_start
+        self.ema, self.momentum = ema, ema_momentum
+        self.momentum_backbone = momentum_backbone if momentum_backbone is not None else ema_momentum
+        self.momentum_head = momentum_head if momentum_head is not None else ema_momentum
+        self.ema_test = ema_test
+        self.use_CutMix, self.cutout_area, self.strong_aug_prob = use_CutMix, cutout_area, strong_aug_prob
+        self.PatchMix_N, self.patchmix_ratio, self.patchsize = PatchMix_N, patchmix_ratio, patchsize
+        self.use_PatchShuffle_w_Cutmix = use_PatchShuffle_w_Cutmix
+        self.negative_class_ranking = negative_class_ranking
+        self.negative_class_ranking_mode = negative_class_ranking_mode
+        self.fdrop_loss_weight = fdrop_loss_weight
+        self.use_fdrop = False
+        self.with_auxiliary_head_ema = False
+        if self.ema:
+            self._init_ema_model(pretrained, backbone_ema, decode_head_ema)
+        assert self.with_decode_head
+        self.attn_mask_weight, self.adaptive_attn_mask = attn_mask_weight, adaptive_attn_mask
+        self.attn_mask_seperate_head = attn_mask_seperate_head
+        self._ema_tables = {}
+        self._topk_override = None   # parity tests may inject the PASA top-k index set
+
+    # ------------------------------------------------------------------ construction (:164-246)
+    def _init_ema_model(self, pretrained, backbone_ema, decode_head_ema):
+        if pretrained is not None:
+            backbone_ema = dict(backbone_ema, pretrained=pretrained)
+        self.backbone_ema = builder.build_backbone(backbone_ema)
+        for param in self.backbone_ema.parameters():
+            param.detach_()
+        self.decode_head_ema = builder.build_head(decode_head_ema)
+        for param in self.decode_head_ema.parameters():
+            param.detach_()
+
+    def _init_decode_head(self, decode_head):
+        self.decode_head = builder.build_head(decode_head)
+        self.align_corners = self.decode_head.align_corners
+        self.num_classes = self.decode_head.num_classes
+
+    def _init_auxiliary_head(self, auxiliary_head):
+        if auxiliary_head is not None:
+            if isinstance(auxiliary_head, list):
+                self.auxiliary_head = nn.ModuleList([builder.build_head(c) for c in auxiliary_head])
+            else:
+                self.auxiliary_head = builder.build_head(auxiliary_head)
+
+    def init_weights(self):
+        for m in self.children():
+            if hasattr(m, 'init_weights'):
+                m.init_weights()
+            elif isinstance(m, nn.ModuleList):
+                for mm in m:
+                    if hasattr(mm, 'init_weights'):
+                        mm.init_weights()
+
+    # ------------------------------------------------------------------ features (:248-270)
+    def extract_feat(self, img, no_pos_embed=False, avg_pos_emd=False, duplicate_pos_emd=False,
+                     use_fdrop=False, attn_mask=None, attn_mask_weight=5, adaptive_attn_mask=False):
+        return self.backbone(img, no_pos_embed=no_pos_embed, avg_pos_emd=avg_pos_emd,
+                             duplicate_pos_emd=duplicate_pos_emd, use_fdrop=use_fdrop,
+                             attn_mask=attn_mask, attn_mask_weight=attn_mask_weight,
+                             adaptive_attn_mask=adaptive_attn_mask, topk_idx=self._topk_override)
+
+    def extract_feat_ema(self, img):
+        return self.backbone_ema(img)
+
+    def encode_decode(self, img, img_metas, adaptive_attn_mask=False, return_last_feat=False):
+        raise NotImplementedError('inference is outside the train-step scope (and broken as shipped, '
+                                  'SURVEY.md section 2.3 hazard 5)')
+
+    def _decode_head_forward_train(self, x, img_metas, gt_semantic_seg):
+        loss_decode = self.decode_head.forward_train(x, img_metas, gt_semantic_seg, self.train_cfg)
+        return add_prefix(loss_decode, 'decode')
+
+    def _auxiliary_head_forward_train(self, x, img_metas, gt_semantic_seg):
+        losses = dict()
+        if isinstance(self.auxiliary_head, nn.ModuleList):
+            for idx, aux_head in enumerate(self.auxiliary_head):
+                loss_aux = aux_head.forward_train(x, img_metas, gt_semantic_seg, self.train_cfg)
+                losses.update(add_prefix(loss_aux, f'aux_{idx}'))
+        else:
+            loss_aux = self.auxiliary_head.forward_train(x, img_metas, gt_semantic_seg, self.train_cfg)
+            losses.update(add_prefix(loss_aux, 'aux'))
+        return losses
+
+    # ------------------------------------------------------------------ forward_train (:386-514)
+    def forward_train(self, img, img_metas, **kwargs):
+        current_iter = kwargs.pop('iter')
+        self.current_iter = current_iter
+        kwargs.update({'img': img})
+        kwargs.update({'img_metas': img_metas})
+        kwargs.update({'tag': [meta['tag'] for meta in img_metas]})
+        data_groups = dict_split(kwargs, 'tag')
+        for _, v in data_groups.items():
+            v.pop('tag')
+
+        self.losses = dict()
+        if self.ema:
+            with torch.no_grad():
+                self.update_ema_variables(self.backbone, self.backbone_ema, self.momentum_backbone)
+                self.update_ema_variables(self.decode_head, self.decode_head_ema, self.momentum_head)
+
+        sup_imgs = sup_gts = None
+        if 'sup' in data_groups:
+            sup_imgs = data_groups['sup']['img']
+            sup_gts = data_groups['sup']['gt_semantic_seg']
+            labeled_features = self.extract_feat(sup_imgs)
+            loss_decode_sup = self._decode_head_forward_train(
+                labeled_features, data_groups['sup']['img_metas'], sup_gts)
+            if self.with_auxiliary_head:
+                loss_aux = self._auxiliary_head_forward_train(
+                    labeled_features, data_groups['sup']['img_metas'], sup_gts)
+                self.losses.update(loss_aux)
+            self.losses.update(loss_decode_sup)
+
+        if ('unsup_student' in data_groups) and self.unsup_weight != 0:
+            unsup_loss = weighted_loss(
+                self.foward_unsup_train(data_groups['unsup_teacher'], data_groups['unsup_student'],
+                                        sup_imgs, sup_gts),
+                weight=self.unsup_weight)
+            if self.iter_unsup_start != 0:
+                if current_iter > self.iter_unsup_start:
+                    self.losses.update(unsup_loss)
+            else:
+                self.losses.update(unsup_loss)
+        return self.losses
+
+    # ------------------------------------------------------------------ unsup branch (:516-687)
+    def foward_unsup_train(self, teacher_data, student_data, sup_imgs, sup_gts):
+        loss_unsup = {}
+        tnames = [meta['filename'] for meta in teacher_data['img_metas']]
+        snames = [meta['filename'] for meta in student_data['img_metas']]
+        tidx = [tnames.index(name) for name in snames]
+
+        with torch.no_grad():
+            self.set_eval(self.ema)
+            timg = teacher_data['img']
+            if tidx != list(range(len(tidx))):
+                timg = timg[torch.tensor(tidx, device=timg.device)]
+            tmetas = [teacher_data['img_metas'][idx] for idx in tidx]
+            if not self.ema:
+                teacher_info = self.extract_teacher_info(timg, tmetas)
+            else:
+                teacher_info = self.extract_teacher_info_ema(timg, tmetas)
+            self.set_train(self.ema)
+        # (:541-542) hard[conf==0] = 255 is already folded into the pseudo-label kernel
+
+        student_info = self.extract_student_info(**student_data)
+
+        if self.attn_mask_seperate_head:
+            attn_mask = self._patch_unconfidence(teacher_info, student_info)
+            unlabled_feat = self.extract_feat(
+                student_info['img'], attn_mask=attn_mask, attn_mask_weight=self.attn_mask_weight,
+                adaptive_attn_mask=self.adaptive_attn_mask)
+            student_info['backbone_feature'] = unlabled_feat
+            loss_unsup['loss_seg_unsup_attn_mask'] = \
+                self.compute_pseudo_loss(student_info, teacher_info, want_ncr=False)['loss_seg_unsup'] * 0.5
+
+        if self.use_CutMix:
+            if np.random.uniform(0, 1) < self.strong_aug_prob:
+                teacher_info, student_info = generate_unsup_cutmix_data(
+                    teacher_info, student_info, ratio=self.cutout_area, patchwise=False)
+
+        if self.use_PatchShuffle_w_Cutmix:
+            if np.random.uniform(0, 1) < self.strong_aug_prob:
+                teacher_info, student_info = generate_unsup_cutmix_data(
+                    teacher_info, student_info, ratio=self.cutout_area, patchwise=False)
+            student_info, teacher_info = generate_unsup_patchmix_data(
+                student_info, teacher_info, PatchMix_N=self.PatchMix_N,
+                patchmix_ratio=self.patchmix_ratio)
+
+        if not self.attn_mask_seperate_head:
+            # Mean-Teacher config as shipped (:650-670): a PASA student pass whose features feed
+            # no loss (hazard 4) -- executed for fidelity of the as-shipped step.
+            attn_mask = self._patch_unconfidence(teacher_info, student_info)
+            unlabled_feat = self.extract_feat(
+                student_info['img'], attn_mask=attn_mask, attn_mask_weight=self.attn_mask_weight,
+                adaptive_attn_mask=self.adaptive_attn_mask)
+        else:
+            unlabled_feat = self.extract_feat(student_info['img'])
+        student_info['backbone_feature'] = unlabled_feat
+
+        if self.use_fdrop or self.attn_mask_seperate_head:
+            losses = self.compute_pseudo_loss(student_info, teacher_info)
+            if self.negative_class_ranking:
+                loss_unsup['loss_ncr_unsup'] = losses['loss_ncr_unsup'] * 0.5
+            loss_unsup['loss_seg_unsup'] = losses['loss_seg_unsup'] * self.fdrop_loss_weight
+        return loss_unsup
+
+    def _patch_unconfidence(self, teacher_info, student_info):
+        """(:547-555) u = mean over each patch of (1 - conf); produced by the pseudo-label kernel."""
+        if teacher_info['conf_mask'].shape[-1] != student_info['img'].shape[-1]:
+            raise NotImplementedError('MiT-style 1/4-resolution teacher maps are a "next" row (SegFormer)')
+        return teacher_info['patch_unconf']
+
+    def extract_student_info(self, img, img_metas, gt_semantic_seg, **kwargs):
+        """(:832-850)"""
+        if 'valid' in img_metas[0]:
+            raise NotImplementedError("'valid' masks are not produced by the shipped pipelines")
+        return dict(img=img, img_metas=img_metas, gt_semantic_seg=gt_semantic_seg[0])
+
+    def _teacher_outputs(self, seg_logits, unsup_confidence):
+        thr = unsup_confidence if unsup_confidence is not None else self.unsup_confidence
+        if thr is None or thr == 0:
+            raise NotImplementedError('unsup_confidence=0 (no confidence mask) is not a shipped setting')
+        hard, conf, u = ops.pseudo_label(seg_logits, thr, self.patchsize)
+        return hard, conf, u
+
+    def extract_teacher_info(self, img, img_metas, unsup_confidence=None):
+        """(:852-873) teacher = student weights (ema=False)."""
+        feat = self.extract_feat(img)
+        seg_logits = self.decode_head.forward_get_logits(feat, self.train_cfg, img_metas)
+        hard, conf, u = self._teacher_outputs(seg_logits, unsup_confidence)
+        return dict(backbone_feature=feat, seg_logits=seg_logits, hard_seg_label=hard, conf_mask=conf,
+                    patch_unconf=u, img_metas=img_metas)
+
+    def extract_teacher_info_ema(self, img, img_metas, unsup_confidence=None):
+        """(:875-904)"""
+        feat = self.extract_feat_ema(img)
+        seg_logits = self.decode_head_ema.forward_get_logits(feat, self.train_cfg, img_metas)
+        hard, conf, u = self._teacher_outputs(seg_logits, unsup_confidence)
+        return dict(backbone_feature=feat, seg_logits=seg_logits, hard_seg_label=hard, conf_mask=conf,
+                    patch_unconf=u, img_metas=img_metas)
+
+    def compute_pseudo_loss(self, student_info, teacher_info, want_ncr=True):
+        """(:906-954) masked CE (mean over ALL pixels) and, in 'unsup_only' mode, NCR.
+        ``want_ncr=False`` skips the NCR value the reference computes and discards (:567)."""
+        loss_unsup = {}
+        students_prediction = self.decode_head.forward_get_logits(
+            student_info['backbone_feature'], self.train_cfg, student_info['img_metas'])
+        ncr = self.negative_class_ranking and want_ncr and \
+            self.negative_class_ranking_mode in ('unsup_only', 'both')
+        zt = teacher_info['seg_logits'] if ncr else None
+        loss_ce, loss_ncr, _ = ops.CeNcrFn.apply(students_prediction, zt, teacher_info['hard_seg_label'],
+                                                 1.0, 1.0 if ncr else 0.0, 255)
+        loss_unsup['loss_seg_unsup'] = loss_ce
+        if ncr:
+            loss_unsup['loss_ncr_unsup'] = loss_ncr
+        return loss_unsup
+
+    # ------------------------------------------------------------------ EMA (:1044-1066)
+    def update_ema_variables(self, model, ema_model, momentum=0.999, dropout=0.0, attn_frozen=False):
+        if dropout != 0 or attn_frozen:
+            raise NotImplementedError('EMA dropout / attn_frozen are not used by the shipped configs')
+        key = (id(model), id(ema_model))
+        table = self._ema_tables.get(key)
+        src = [p for _, p in model.named_parameters()]
+        dst = [p for _, p in ema_model.named_parameters()]
+        for (sn, sb), (_, tb) in zip(model.named_buffers(), ema_model.named_buffers()):
+            if 'bn' in sn and 'num_batches_tracked' not in sn:
+                src.append(sb)
+                dst.append(tb)
+        ptr_key = tuple(t.data_ptr() for t in dst) + tuple(t.data_ptr() for t in src)
+        if table is None or table.key != ptr_key:
+            if not dst[0].is_cuda:
+                raise RuntimeError('s4former_b200 needs CUDA tensors: there is no CPU fallback')
+            table = ops.TensorTable([[t.data for t in dst], [t.data for t in src]], dst[0].device)
+            table.targets = dst
+            self._ema_tables[key] = table
+        ops.ema_update(table, momentum)
+        for t in table.targets:
+            ops.bump_generation(t)
+
+    def set_eval(self, ema=False):
+        if not ema:
+            self.backbone.eval()
+            self.decode_head.eval()
+            if self.with_auxiliary_head:
+                self.auxiliary_head.eval()
+        else:
+            self.backbone_ema.eval()
+            self.decode_head_ema.eval()
+
+    def set_train(self, ema=False):
+        if not ema:
+            self.backbone.train()
+            self.decode_head.train()
+            if self.with_auxiliary_head:
+                self.auxiliary_head.train()
+        else:
+            self.backbone_ema.train()
+            self.decode_head_ema.train()

@@ -1,0 +1,369 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes) and compared
+with the oracle / plain fp32 math on the same seeded inputs.  Integer outputs are bit-exact;
+fp32 within 1e-3 relative (validation mode); bf16 within 2e-2 relative."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import s4former_oracle as O  # noqa: E402  (the checker)
+from s4former_b200 import _lib as L  # noqa: E402
+from s4former_b200 import ops  # noqa: E402
+
+DEV = 'cuda'
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def gen(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.fixture(autouse=True)
+def _sync():
+    yield
+    torch.cuda.synchronize()
+
+
+def test_library_loads_on_gpu():
+    lib = L.load()
+    assert lib.s4_built_arch() == 100
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+# ------------------------------------------------------------------------------------------ LN
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize('D', [128, 768])
+def test_layernorm_fwd_bwd(dtype, tol, D):
+    g = gen(1)
+    rows = 77
+    x = torch.randn(rows, D, generator=g)
+    gamma = torch.randn(D, generator=g) * 0.1 + 1
+    beta = torch.randn(D, generator=g) * 0.1
+    dy = torch.randn(rows, D, generator=g)
+    dres = torch.randn(rows, D, generator=g)
+    xd = x.to(DEV, dtype)
+    xr = xd.float().cpu().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (D,), gr, br, 1e-6)
+    dyd = dy.to(DEV, dtype)
+    yr.backward(dyd.float().cpu())
+    gp = torch.nn.Parameter(gamma.to(DEV))
+    bp = torch.nn.Parameter(beta.to(DEV))
+    y, mean, rstd = ops.layernorm_fwd(xd, gp, bp, 1e-6)
+    assert rel(y.float(), yr) < tol
+    dresd = dres.to(DEV, dtype)
+    dx = ops.layernorm_bwd(dyd, xd, gp, bp, mean, rstd, dres=dresd)
+    assert rel(dx.float(), xr.grad + dresd.float().cpu()) < max(tol, 1e-4)
+    assert rel(gp.grad, gr.grad) < max(tol, 1e-4)
+    assert rel(bp.grad, br.grad) < max(tol, 1e-4)
+
+
+def test_layernorm_row_map():
+    g = gen(2)
+    x = torch.randn(50, 128, generator=g).to(DEV)
+    rm = torch.randperm(50, generator=g)[:30].to(torch.int32).to(DEV)
+    gp = torch.nn.Parameter(torch.ones(128, device=DEV))
+    bp = torch.nn.Parameter(torch.zeros(128, device=DEV))
+    y, mean, rstd = ops.layernorm_fwd(x, gp, bp, 1e-6, row_map=rm, out_rows=30)
+    want = F.layer_norm(x[rm.long()], (128,), None, None, 1e-6)
+    assert rel(y, want) < 1e-5
+    dy = torch.randn(30, 128, generator=g).to(DEV)
+    dx = ops.layernorm_bwd(dy, x, gp, bp, mean, rstd, row_map=rm)
+    xr = x.clone().requires_grad_(True)
+    F.layer_norm(xr[rm.long()], (128,), None, None, 1e-6).backward(dy)
+    assert rel(dx, xr.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def _gemm_case(M, N, K, dtype, backend, a_mn=False, b_mn=False, bias=False, act=False, res=False,
+               aux=False, c32=False, accumulate=False, split_k=1, batch=(1, 1), alpha=1.0, seed=3):
+    g = gen(seed)
+    nb = batch[0] * batch[1]
+    A = torch.randn(nb, M, K, generator=g).to(DEV, dtype)
+    Bm = torch.randn(nb, K, N, generator=g).to(DEV, dtype)      # logical [K, N]
+    ref = alpha * torch.bmm(A.float(), Bm.float())
+    a_store = A.transpose(1, 2).contiguous() if a_mn else A    # MN-major: stored [K, M]
+    b_store = Bm if b_mn else Bm.transpose(1, 2).contiguous()   # K-major: stored [N, K]
+    a_str = (1, M) if a_mn else (K, 1)
+    b_str = (N, 1) if b_mn else (1, K)
+    cdt = torch.float32 if c32 else dtype
+    c = torch.randn(nb, M, N, generator=g).to(DEV, cdt) if accumulate else torch.empty(nb, M, N, device=DEV, dtype=cdt)
+    kw = {}
+    if bias:
+        bv = torch.randn(N, generator=g).to(DEV)
+        ref = ref + bv
+        kw['bias'] = bv
+    if aux:
+        av = torch.randn(nb, M, N, generator=g).to(DEV, dtype)
+        xa = av.float()
+        cdf = 0.5 * (1 + torch.erf(xa / math.sqrt(2)))
+        ref = ref * (cdf + xa * torch.exp(-0.5 * xa * xa) / math.sqrt(2 * math.pi))
+        kw['aux'] = av
+    pre = None
+    if act:
+        pre = torch.empty(nb, M, N, device=DEV, dtype=dtype)
+        kw['pre'] = pre
+        pre_ref = ref
+        ref = F.gelu(ref)
+        kw['act'] = L.ACT_GELU
+    if res:
+        rv = torch.randn(nb, M, N, generator=g).to(DEV, dtype)
+        ref = ref + rv.float()
+        kw['res'] = rv
+    if accumulate:
+        ref = ref + c.float()
+    ops.gemm(a_store, b_store, c, M, N, K, a_str, b_str, N, batch=batch,
+             a_bs=(batch[1] * M * K, M * K), b_bs=(batch[1] * K * N, K * N), c_bs=(batch[1] * M * N, M * N),
+             alpha=alpha, accumulate=accumulate, split_k=split_k, backend_override=backend, **kw)
+    torch.cuda.synchronize()
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    r = rel(c.float(), ref)
+    assert r < tol, f'rel err {r}'
+    if act:
+        assert rel(pre.float(), pre_ref) < tol
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('a_mn,b_mn', [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_simt_layouts(dtype, a_mn, b_mn):
+    _gemm_case(100, 72, 50, dtype, L.BACKEND_SIMT, a_mn=a_mn, b_mn=b_mn, c32=(dtype == torch.float32))
+
+
+def test_gemm_simt_epilogues_and_batch():
+    _gemm_case(65, 40, 33, torch.float32, L.BACKEND_SIMT, bias=True, act=True, res=True, c32=True, batch=(2, 3))
+    _gemm_case(65, 40, 33, torch.float32, L.BACKEND_SIMT, aux=True, c32=True, accumulate=True, alpha=0.5)
+    _gemm_case(65, 40, 33, torch.bfloat16, L.BACKEND_SIMT, bias=True, res=True, c32=True)
+
+
+# ------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize('pasa', [False, True])
+def test_attention_composed(dtype, tol, pasa):
+    g = gen(5)
+    B, H, Lt, hd = 2, 2, 65, 64
+    D = H * hd
+    qkv = (torch.randn(B * Lt, 3 * D, generator=g) * 0.5).to(DEV, dtype)
+    u0 = gate = None
+    w = 0.0
+    if pasa:
+        u = torch.rand(B, 8, 8, generator=g)
+        u0, gate = O.pasa_gate_u0(u, True)
+        u0, gate, w = u0.to(DEV), gate.to(DEV), 5.0
+    old = ops.backend()
+    ops.set_backend('simt')
+    try:
+        out, lse = ops.attention_fwd(qkv, B, Lt, H, hd, u0, gate, w)
+        dout = torch.randn(B * Lt, D, generator=g).to(DEV, dtype)
+        dqkv = ops.attention_bwd(dout, qkv, out, lse, B, Lt, H, hd, u0, gate, w)
+    finally:
+        ops.set_backend(old)
+    qr = qkv.float().cpu().requires_grad_(True)
+    q, k, v = qr.view(B, Lt, 3 * D).split(D, dim=-1)
+    q = q.view(B, Lt, H, hd).transpose(1, 2) / math.sqrt(hd)
+    k = k.view(B, Lt, H, hd).transpose(1, 2)
+    v = v.view(B, Lt, H, hd).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    if pasa:
+        s = s + (w * gate.cpu().unsqueeze(-1) * u0.cpu().unsqueeze(1)).unsqueeze(1)
+    o = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * Lt, D)
+    o.backward(dout.float().cpu())
+    assert rel(out.float(), o) < tol
+    assert rel(dqkv.float(), qr.grad) < tol
+
+
+# ------------------------------------------------------------------------------------------ head
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_conv3x3_simt(dtype, tol):
+    g = gen(6)
+    B, H, W, Cin, Cout = 2, 8, 8, 16, 24
+    x = torch.randn(B, H, W, Cin, generator=g).to(DEV, dtype)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.2).to(DEV)
+    dy = torch.randn(B, H, W, Cout, generator=g).to(DEV, dtype)
+    code = L.BF16 if dtype == torch.bfloat16 else L.F32
+    wf = torch.empty(Cout, 9 * Cin, device=DEV, dtype=dtype)
+    wd = torch.empty(Cin, 9 * Cout, device=DEV, dtype=dtype)
+    st = torch.cuda.current_stream().cuda_stream
+    L.call('s4_pack_conv3x3_weight', w.data_ptr(), wf.data_ptr(), wd.data_ptr(), Cin, Cout, code, st)
+    y = torch.empty(B, H, W, Cout, device=DEV, dtype=dtype)
+    L.call('s4_conv3x3_fwd', x.data_ptr(), wf.data_ptr(), y.data_ptr(), B, H, W, Cin, Cout, code, L.BACKEND_SIMT, st)
+    dx = torch.empty_like(x)
+    L.call('s4_conv3x3_dgrad', dy.data_ptr(), wd.data_ptr(), dx.data_ptr(), B, H, W, Cin, Cout, code, L.BACKEND_SIMT, st)
+    dw = torch.zeros(Cout, Cin, 3, 3, device=DEV)
+    L.call('s4_conv3x3_wgrad', x.data_ptr(), dy.data_ptr(), dw.data_ptr(), B, H, W, Cin, Cout, code, L.BACKEND_SIMT, st)
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wr = wf.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, padding=1)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel(y.float().permute(0, 3, 1, 2), yr) < tol
+    assert rel(dx.float().permute(0, 3, 1, 2), xr.grad) < tol
+    assert rel(dw, wr.grad) < tol
+
+
+class _Stage(torch.nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(cin, cout, 3, padding=1, bias=False)
+        self.bn = torch.nn.BatchNorm2d(cout)
+
+
+@pytest.mark.parametrize('s', [2, 4])
+def test_conv_bn_relu_upsample_stage_fp32(s):
+    ops.set_compute_dtype(torch.float32)
+    try:
+        g = gen(7)
+        B, H, W, Cin, Cout = 2, 8, 8, 16, 32
+        stage = _Stage(Cin, Cout).to(DEV)
+        ref = _Stage(Cin, Cout)
+        with torch.no_grad():
+            stage.bn.weight.copy_(torch.rand(Cout, generator=g) + 0.5)
+            stage.bn.bias.copy_(torch.randn(Cout, generator=g) * 0.1)
+        ref.load_state_dict({k: v.cpu() for k, v in stage.state_dict().items()})
+        x = torch.randn(B, H, W, Cin, generator=g)
+        xd = x.to(DEV).reshape(B * H * W, Cin).requires_grad_(True)
+        out = ops.ConvBNReLUUpFn.apply(xd, stage, B, H, W, s, True, None)
+        dout = torch.randn(B * H * s * W * s, Cout, generator=g)
+        out.backward(dout.to(DEV))
+        xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+        yr = F.interpolate(F.relu(ref.bn(ref.conv(xr))), scale_factor=s, mode='bilinear', align_corners=False)
+        yr.backward(dout.view(B, H * s, W * s, Cout).permute(0, 3, 1, 2))
+        assert rel(out.view(B, H * s, W * s, Cout).permute(0, 3, 1, 2), yr) < 1e-4
+        assert rel(xd.grad.view(B, H, W, Cin).permute(0, 3, 1, 2), xr.grad) < 1e-3
+        assert rel(stage.conv.weight.grad, ref.conv.weight.grad) < 1e-3
+        assert rel(stage.bn.weight.grad, ref.bn.weight.grad) < 1e-3
+        assert rel(stage.bn.bias.grad, ref.bn.bias.grad) < 1e-3
+        assert rel(stage.bn.running_mean, ref.bn.running_mean) < 1e-4
+        assert rel(stage.bn.running_var, ref.bn.running_var) < 1e-4
+    finally:
+        ops.set_compute_dtype(torch.bfloat16)
+
+
+def test_conv_bn_relu_cls_upsample_stage_fp32():
+    ops.set_compute_dtype(torch.float32)
+    try:
+        g = gen(8)
+        B, H, W, Cin, Cout, NC, s = 2, 8, 8, 16, 32, 5, 2
+        stage = _Stage(Cin, Cout).to(DEV)
+        seg = torch.nn.Conv2d(Cout, NC, 1).to(DEV)
+        ref, rseg = _Stage(Cin, Cout), torch.nn.Conv2d(Cout, NC, 1)
+        ref.load_state_dict({k: v.cpu() for k, v in stage.state_dict().items()})
+        rseg.load_state_dict({k: v.cpu() for k, v in seg.state_dict().items()})
+        x = torch.randn(B, H, W, Cin, generator=g)
+        xd = x.to(DEV).reshape(B * H * W, Cin).requires_grad_(True)
+        out = ops.ConvBNReLUClsUpFn.apply(xd, stage, seg, B, H, W, s, True, None)
+        dout = torch.randn(B, NC, H * s, W * s, generator=g)
+        out.backward(dout.to(DEV))
+        xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+        # the reference order: upsample THEN conv_seg
+        yr = rseg(F.interpolate(F.relu(ref.bn(ref.conv(xr))), scale_factor=s, mode='bilinear', align_corners=False))
+        yr.backward(dout)
+        assert rel(out, yr) < 1e-4
+        assert rel(xd.grad.view(B, H, W, Cin).permute(0, 3, 1, 2), xr.grad) < 1e-3
+        assert rel(stage.conv.weight.grad, ref.conv.weight.grad) < 1e-3
+        assert rel(seg.weight.grad, rseg.weight.grad) < 1e-3
+        assert rel(seg.bias.grad, rseg.bias.grad) < 1e-3
+        assert rel(stage.bn.weight.grad, ref.bn.weight.grad) < 1e-3
+    finally:
+        ops.set_compute_dtype(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------ losses
+def test_pseudo_label_bit_exact(golden_dir):
+    G = torch.load(os.path.join(golden_dir, 'loss_pseudo.pt'), weights_only=False)
+    hard, conf, u = ops.pseudo_label(G['z_t'].to(DEV), 0.95, patch=G['patch'])
+    assert torch.equal(hard.cpu(), G['hard'])
+    assert torch.equal(conf.cpu(), G['conf'])
+    assert torch.equal(u.cpu(), G['u'])
+
+
+def test_pseudo_label_large_random():
+    g = gen(9)
+    z = (torch.randn(2, 21, 128, 256, generator=g) * 4)
+    hard, conf, u = ops.pseudo_label(z.to(DEV), 0.95, 16)
+    h0, c0, mv = O.pseudo_label(z, 0.95)
+    near = (mv - 0.95).abs() < 1e-6          # 1-ulp band where expf implementations may differ
+    assert torch.equal(conf.cpu()[~near], c0[~near])
+    assert torch.equal(hard.cpu()[~near], h0[~near])
+    assert int(near.sum()) < 16
+    if int(near.sum()) == 0:
+        assert torch.equal(u.cpu(), O.patch_unconfidence(c0, 16))
+
+
+def test_ce_ncr_golden_and_grad(golden_dir):
+    G = torch.load(os.path.join(golden_dir, 'loss_pseudo.pt'), weights_only=False)
+    zs = G['z_s'].to(DEV).requires_grad_(True)
+    zt = G['z_t'].to(DEV)
+    hard = G['hard'].to(DEV)
+    ce, ncr, _ = ops.CeNcrFn.apply(zs, zt, hard, 1.0, 1.0, 255)
+    assert abs(float(ce) - float(G['loss_seg_unsup'])) < 1e-5 * abs(float(G['loss_seg_unsup']))
+    assert abs(float(ncr) - float(G['loss_ncr_unsup'])) < 1e-4 * abs(float(G['loss_ncr_unsup']))
+    (0.5 * ce + 0.25 * ncr).backward()
+    zr = G['z_s'].clone().requires_grad_(True)
+    lo = 0.5 * O.cross_entropy_mean_all(zr, G['hard']) + 0.25 * O.ncr_unsup_only(zr, G['z_t'], G['hard'])
+    lo.backward()
+    assert rel(zs.grad, zr.grad) < 1e-4
+    w = ops.cross_entropy(G['z_s'].to(DEV), hard, 0.4, 255)
+    assert abs(float(w) - float(G['ce_w04'])) < 1e-5 * abs(float(G['ce_w04']))
+
+
+def test_ce_known_answers_gpu():
+    """reference tests/test_models/test_losses/test_ce_loss.py:25-39 through the CUDA kernel."""
+    z = torch.tensor([[100., -100.]]).view(1, 2, 1, 1).to(DEV)
+    y = torch.tensor([1]).view(1, 1, 1).to(DEV)
+    assert abs(float(ops.cross_entropy(z, y, 1.0, 255)) - 200.0) < 1e-4
+    y255 = torch.full((1, 1, 1), 255, dtype=torch.int64, device=DEV)
+    assert float(ops.cross_entropy(z, y255, 1.0, 255)) == 0.0
+
+
+# ------------------------------------------------------------------------------------------ augment / EMA
+def test_augment_golden(golden_dir):
+    G = torch.load(os.path.join(golden_dir, 'augment.pt'), weights_only=False)
+    from s4former_b200.utils import generate_unsup_data as gud
+    O.seed_host_rng(G['seed'])
+    t, s = gud.generate_unsup_cutmix_data(dict(hard_seg_label=G['lab'].to(DEV)), dict(img=G['img'].to(DEV)))
+    assert torch.equal(s['img'].cpu(), G['cut_img'])
+    assert torch.equal(t['hard_seg_label'].cpu(), G['cut_lab'])
+    metas = [dict() for _ in range(4)]
+    res = dict(img=s['img'], img_metas=metas)
+    res, _ = gud.generate_unsup_patchmix_data(res, t, PatchMix_N=1, patchmix_ratio=0.5)
+    assert torch.equal(torch.stack([m['PatchMixIndex'] for m in metas]), G['perms'])
+    assert torch.equal(res['img'].cpu(), G['shuf_img'])
+
+
+def test_token_unshuffle_rowmap(golden_dir):
+    G = torch.load(os.path.join(golden_dir, 'augment.pt'), weights_only=False)
+    import s4former_b200 as s4
+    head = s4.SETRUPHead(in_channels=16, channels=8, num_classes=3, num_convs=1, up_scale=2, in_index=0,
+                         dropout_ratio=0, norm_cfg=dict(type='BN'))
+    rm = head._row_map(4, 8, False, 'cpu', 2, G['perms'])
+    got = G['tok'].reshape(4 * 64, 16)[rm.long()].view(4, 64, 16)
+    assert torch.equal(got, G['unsh'])
+
+
+def test_ema_multi_tensor():
+    g = gen(10)
+    shapes = [(1000,), (33, 7), (70000,), (5,)]
+    src = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+    dst = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+    want = [d.clone().mul_(0.999).add_(s, alpha=1 - 0.999) for d, s in zip(dst, src)]
+    table = ops.TensorTable([dst, src], DEV)
+    ops.ema_update(table, 0.999)
+    for d, w in zip(dst, want):
+        assert torch.allclose(d, w, rtol=1e-6, atol=1e-7)
+
+
+def test_patchify_and_tokens():
+    g = gen(11)
+    img = torch.randn(2, 3, 64, 64, generator=g).to(DEV)
+    a = torch.empty(2 * 16, 768, device=DEV)
+    L.call('s4_patchify', img.data_ptr(), a.data_ptr(), 2, 3, 64, 64, 16, L.F32, torch.cuda.current_stream().cuda_stream)
+    want = F.unfold(img, 16, stride=16).transpose(1, 2).reshape(32, 768)
+    assert torch.equal(a, want)

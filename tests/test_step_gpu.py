@@ -1,0 +1,142 @@
+"""End-to-end parity of the S4Former train step (forward_train + backward + EMA) on the GPU
+against (a) golden vectors produced by the unmodified reference and (b) the oracle run on the
+same seeded inputs.  fp32 validation mode: losses/grads within 1e-3 relative; bf16 mode: 2e-2
+(north_star tolerances); pseudo-label masks bit-exact given identical logits."""
+import copy
+import os
+import warnings
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings('ignore')
+
+import s4former_b200 as s4  # noqa: E402
+from oracle import golden_common as gc  # noqa: E402
+from oracle import s4former_oracle as O  # noqa: E402
+from s4former_b200 import ops  # noqa: E402
+
+DEV = 'cuda'
+
+
+def _build(variant):
+    m = s4.build_segmentor(gc.tiny_cfg(variant))
+    sd = gc.seeded_state_dict(m.state_dict(), seed=5)
+    m.load_state_dict(sd)
+    return m.to(DEV).train(), sd
+
+
+def _run(variant, dtype, topk=None):
+    ops.set_compute_dtype(dtype)
+    try:
+        m, sd = _build(variant)
+        img, gt, metas = gc.tiny_batch(variant)
+        O.seed_host_rng(1999)
+        m._topk_override = topk
+        losses = m.forward_train(img.to(DEV), metas, gt_semantic_seg=gt.to(DEV), iter=0)
+        total, log_vars = m._parse_losses(losses)
+        total.backward()
+        torch.cuda.synchronize()
+        return m, losses, log_vars, metas
+    finally:
+        ops.set_compute_dtype(torch.bfloat16)
+
+
+def _golden(golden_dir, variant):
+    return torch.load(os.path.join(golden_dir, f'step_{variant}.pt'), weights_only=False)
+
+
+def _reference_topk(variant):
+    """Top-k index set of the PASA gate as the CPU reference chose it (tie order is device
+    specific, Appendix B-1): recomputed by the oracle on the same inputs."""
+    if variant == 'sup':
+        return None
+    cfg = gc.tiny_cfg(variant)
+    orc = O.OracleEncoderDecoder(**{k: v for k, v in cfg.items() if k != 'type'})
+    orc.load_state_dict(gc.seeded_state_dict(orc.state_dict(), seed=5))
+    orc.train()
+    img, gt, metas = gc.tiny_batch(variant)
+    O.seed_host_rng(1999)
+    with torch.no_grad():
+        O.ema_update(orc.backbone, orc.backbone_ema, orc.momentum)
+        O.ema_update(orc.decode_head, orc.decode_head_ema, orc.momentum)
+        sel = [i for i, mm in enumerate(metas) if mm['tag'] == 'unsup_teacher']
+        orc.backbone_ema.eval()
+        orc.decode_head_ema.eval()
+        z = orc.decode_head_ema.forward(orc.backbone_ema(img[sel]))
+        _, conf, _ = O.pseudo_label(z, 0.95)
+        u = O.patch_unconfidence(conf, 16).reshape(len(sel), -1)
+    return torch.topk(u, int(0.5 * u.shape[-1]), dim=-1, largest=False)[1]
+
+
+@pytest.mark.parametrize('variant', ['sup', 'mt', 'ours'])
+def test_train_step_fp32_vs_reference_golden(golden_dir, variant):
+    G = _golden(golden_dir, variant)
+    m, losses, log_vars, metas = _run(variant, torch.float32, topk=_reference_topk(variant))
+    assert set(losses) == set(G['losses'])
+    for k, v in G['losses'].items():
+        got = float(losses[k])
+        assert abs(got - float(v)) <= 1e-3 * abs(float(v)) + 1e-6, (k, got, float(v))
+    named = dict(m.named_parameters())
+    for k, g in G['grads'].items():
+        r = float((named[k].grad.cpu() - g).norm() / (g.norm() + 1e-12))
+        assert r < 1e-3, (k, r)
+    for k, n in G['grad_norms'].items():
+        got = float(named[k].grad.norm())
+        assert abs(got - n) <= 2e-3 * n + 1e-8, (k, got, n)
+    post = m.state_dict()
+    for k, v in G['ema_after'].items():
+        assert torch.allclose(post[k].float().cpu(), v.float(), rtol=1e-5, atol=1e-7), k
+    for k, v in G['bn_after'].items():
+        assert torch.allclose(post[k].cpu(), v, rtol=1e-3, atol=1e-5), k
+    if variant == 'ours':
+        sm = [mm for mm in metas if mm['tag'] == 'unsup_student']
+        for mm, p in zip(sm, G['perms']):
+            assert torch.equal(torch.as_tensor(mm['PatchMixIndex']), torch.as_tensor(p))
+
+
+@pytest.mark.parametrize('variant', ['sup', 'ours'])
+def test_train_step_bf16_vs_reference_golden(golden_dir, variant):
+    G = _golden(golden_dir, variant)
+    m, losses, log_vars, metas = _run(variant, torch.bfloat16, topk=_reference_topk(variant))
+    for k, v in G['losses'].items():
+        got = float(losses[k])
+        assert abs(got - float(v)) <= 2e-2 * abs(float(v)) + 1e-3, (k, got, float(v))
+    named = dict(m.named_parameters())
+    bad = []
+    for k, g in G['grads'].items():
+        r = float((named[k].grad.cpu() - g).norm() / (g.norm() + 1e-12))
+        if r > 5e-2:
+            bad.append((k, r))
+    assert not bad, bad
+
+
+def test_backbone_head_forward_fp32_vs_golden(golden_dir):
+    G = _golden(golden_dir, 'ours')
+    ops.set_compute_dtype(torch.float32)
+    try:
+        m, _ = _build('ours')
+        m.eval()
+        g2 = torch.Generator().manual_seed(G['vit_seed'])
+        u = torch.rand(2, 8, 8, generator=g2).mul(16).round().div(16)
+        x = torch.randn(2, 3, 128, 128, generator=g2)
+        with torch.no_grad():
+            feats = m.backbone(x.to(DEV), attn_mask=u.to(DEV), attn_mask_weight=5, adaptive_attn_mask=True,
+                               topk_idx=G['vit_topk'])
+            plain = m.backbone(x.to(DEV))
+            logits = m.decode_head.forward(plain)
+        for a, b in zip(feats, G['vit_feats']):
+            assert torch.allclose(a.float().cpu(), b, rtol=1e-3, atol=1e-4)
+        for a, b in zip(plain, G['vit_feats_plain']):
+            assert torch.allclose(a.float().cpu(), b, rtol=1e-3, atol=1e-4)
+        assert torch.allclose(logits[:, :, ::2, ::2].cpu(), G['head_logits_eval'], rtol=1e-3, atol=1e-3)
+    finally:
+        ops.set_compute_dtype(torch.bfloat16)
+
+
+def test_missing_cuda_tensor_fails_loudly():
+    m, _ = _build('sup')
+    img, gt, metas = gc.tiny_batch('sup')
+    with pytest.raises(Exception):
+        m.cpu().forward_train(img, metas, gt_semantic_seg=gt, iter=0)
