@@ -41,6 +41,7 @@ typedef struct CUstream_st* cudaStream_t;
 int s4_version(void);
 int s4_built_arch(void);            /* 100 = sm_100a */
 const char* s4_last_error(void);
+long long s4_launch_count(void);     /* kernels launched by this library in this process */
 
 /* ---- GEMM with fused epilogue -------------------------------------------------------------
  * Replaces: nn.Linear / in_proj / out_proj / FFN inside mmcv MultiheadAttention and FFN as

@@ -151,6 +151,19 @@ def main():
                 d = float((p.grad - grads[k]).norm() / (grads[k].norm() + 1e-12))
                 worst = max(worst, d)
         print('    worst grad rel diff', worst)
+        # what PyTorch's own bf16 autocast of the same step loses against fp32: the yardstick for
+        # the bf16 gradient gate on this tiny, noisy problem (tests/test_step_gpu.py)
+        orb = O.OracleEncoderDecoder(**{k: v for k, v in cfg.items() if k != 'type'})
+        orb.load_state_dict(sd)
+        orb.train()
+        O.seed_host_rng(1999)
+        with torch.autocast('cpu', dtype=torch.bfloat16):
+            lb = orb.forward_train(img, copy.deepcopy(metas), gt)
+        O.parse_losses(lb).backward()
+        nb = dict(orb.named_parameters())
+        rec['bf16_autocast_err'] = {k: float((nb[k].grad - g).norm() / (g.norm() + 1e-12))
+                                    for k, g in gsel.items()}
+        torch.save(rec, os.path.join(OUT, f'step_{variant}.pt'))
     sz = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print('golden bytes', sz)
 

@@ -38,6 +38,7 @@ _SPEC = {
     's4_version': (_I, []),
     's4_built_arch': (_I, []),
     's4_last_error': (C.c_char_p, []),
+    's4_launch_count': (C.c_longlong, []),
     's4_gemm': (_I, [C.POINTER(GemmParams), _P]),
     's4_gemm_uses_tc': (_I, [C.POINTER(GemmParams)]),
     's4_layernorm_fwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P]),

@@ -15,7 +15,8 @@
 #define S4_BF16 1
 
 void s4_set_error(const char* fmt, ...);
-int s4_check_launch(const char* what);
+int s4_check_launch(const char* what);   // also counts one kernel launch
+void s4_count_launches(int n);           // extra launches behind a single check
 
 #define S4_REQUIRE(cond, ...)            \
   do {                                   \

@@ -214,6 +214,7 @@ extern "C" int s4_ce_ncr(const float* logits_s, const float* logits_t, const lon
   ce_ncr_kernel<<<nblk, 256, 0, stream>>>(logits_s, logits_t, label, dlogits, (float*)workspace, C,
                                           (size_t)H * W, npix, ce_weight / P, ncr_weight / P,
                                           ignore_index, grad_scale);
+  if (loss_out) s4_count_launches(1);
   if (loss_out)
     ce_ncr_finalize_kernel<<<1, 256, 0, stream>>>((const float*)workspace, nblk, loss_out,
                                                   ce_weight / P, ncr_weight / P);

@@ -368,6 +368,7 @@ class HeadLNFn(torch.autograd.Function):
                                       row_map=row_map, out_rows=rows)
         ctx.head = head
         ctx.save_for_backward(x_tokens, mean, rstd, row_map)
+        head._s4_pending = getattr(head, '_s4_pending', 0) + 1
         return y
 
     @staticmethod
@@ -376,6 +377,11 @@ class HeadLNFn(torch.autograd.Function):
         head = ctx.head
         dx = layernorm_bwd(dy.contiguous(), x_tokens, head.norm.weight, head.norm.bias, mean, rstd,
                            row_map=row_map)
+        head._s4_pending -= 1
+        if head._s4_pending == 0:      # the LayerNorm is the last node of the head's backward
+            hook = getattr(head, '_s4_grad_ready_hook', None)
+            if hook is not None:
+                hook(head)
         return dx, None, None, None, None
 
 

@@ -1,0 +1,87 @@
+"""Flat parameter/gradient storage, the fused SGD-momentum step and the poly LR schedule
+(the step either side of the hot path).
+
+Reference behaviour reproduced: ``torch.optim.SGD(lr=1e-3, momentum=0.9, weight_decay=0)`` with
+mmcv's ``DefaultOptimizerConstructor`` ``custom_keys={'head': dict(lr_mult=10.)}``
+(configs/setr/*_MT_w_ours.py:259-262) and the ``poly`` policy (power 0.9, min_lr 1e-4,
+by_epoch=False; configs/_base_/schedules/schedule_80k_pascal_1over8.py:2-5).
+"""
+import torch
+
+from . import ops
+
+
+class FlatGrads:
+    """All gradients of ``params`` as views of ONE contiguous float32 buffer: zeroing is one
+    memset, the data-parallel reducer all-reduces slices of it, the optimizer reads it in one
+    multi-tensor launch."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.offsets = {}
+        off = 0
+        for p in self.params:
+            self.offsets[id(p)] = (off, p.numel())
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+        for p in self.params:            # a foreign zero_grad(set_to_none=True) would detach the views
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + self.offsets[id(p)][0] * 4:
+                off, n = self.offsets[id(p)]
+                p.grad = self.flat[off:off + n].view_as(p)
+
+
+def poly_lr(base_lr, it, max_iters, power=0.9, min_lr=1e-4):
+    """mmcv PolyLrUpdaterHook: (base - min) * (1 - it/max)^power + min."""
+    coeff = (1 - it / max_iters) ** power
+    return (base_lr - min_lr) * coeff + min_lr
+
+
+class FusedSGD:
+    """SGD with momentum over named parameters in one multi-tensor kernel launch."""
+
+    def __init__(self, named_params, lr=1e-3, momentum=0.9, weight_decay=0.0, custom_keys=None,
+                 max_iters=80000, power=0.9, min_lr=1e-4):
+        named = [(n, p) for n, p in named_params if p.requires_grad]
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        self.base_lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.max_iters, self.power, self.min_lr = max_iters, power, min_lr
+        custom_keys = custom_keys or {}
+        self.lr_mult = []
+        for n in self.names:
+            mult = 1.0
+            for key in sorted(custom_keys, key=len, reverse=True):   # mmcv: longest key first
+                if key in n:
+                    mult = custom_keys[key].get('lr_mult', 1.0)
+                    break
+            self.lr_mult.append(mult)
+        self.grads = FlatGrads(self.params)
+        self.bufs = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.steps = 0
+        self._table = None
+
+    def zero_grad(self):
+        self.grads.zero()
+
+    def current_lrs(self, it=None):
+        it = self.steps if it is None else it
+        # mmcv applies the schedule to each group's own initial lr (base*mult), min_lr is absolute
+        return [poly_lr(self.base_lr * m, it, self.max_iters, self.power, self.min_lr) for m in self.lr_mult]
+
+    def step(self, it=None):
+        if self._table is None:
+            dev = self.params[0].device
+            self._table = ops.TensorTable([[p.data for p in self.params], [p.grad for p in self.params],
+                                           self.bufs], dev, lrs=self.current_lrs(it))
+            self._table.targets = self.params
+        ops.sgd_step(self._table, self.momentum, self.weight_decay, first_step=(self.steps == 0),
+                     lrs=self.current_lrs(it))
+        for p in self.params:
+            ops.bump_generation(p)
+        self.steps += 1

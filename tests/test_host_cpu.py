@@ -216,3 +216,69 @@ def test_parse_losses_single_process():
     from s4former_b200.segmentors.base import BaseSegmentor
     loss, lv = BaseSegmentor._parse_losses({'a.loss_ce': torch.tensor([1., 3.]), 'x': torch.tensor(5.)})
     assert float(loss) == 2.0 and lv['loss'] == 2.0 and lv['x'] == 5.0
+
+
+def _reducer_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch.nn as nn
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from s4former_b200.optim import FlatGrads
+    from s4former_b200.parallel import GradReducer
+
+    class SETRUPHead(nn.Module):          # name-matched stand-ins: the reducer keys on class names
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Linear(8, 8)
+
+    class TransformerEncoderLayer(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = nn.Linear(16, 16)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = nn.ModuleList([TransformerEncoderLayer() for _ in range(3)])
+            self.head = SETRUPHead()
+    torch.manual_seed(0)
+    net = Net()
+    fg = FlatGrads(list(net.parameters()))
+    red = GradReducer(net, fg, bucket_bytes=600)     # several buckets
+    assert len(red.buckets) >= 3
+    for step in range(2):
+        fg.zero()
+        for i, p in enumerate(net.parameters()):
+            p.grad.add_(float(rank + 1) * (i + 1) + step)
+        red.module_ready(net.head)                   # backward order: head first, layers reversed
+        red.module_ready(net.layers[2])
+        red.module_ready(net.layers[1])
+        # layers[0] never signals: finalize() must still reduce its bucket
+        red.finalize()
+        vals = [float(p.grad.flatten()[0]) for p in net.parameters()]
+        want = [1.5 * (i + 1) + step for i in range(len(vals))]
+        assert all(abs(a - b) < 1e-6 for a, b in zip(vals, want)), (vals, want)
+    q.put(rank)
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert got == [0, 1]
+
+
+def test_poly_lr_and_lr_mult():
+    from s4former_b200.optim import poly_lr
+    assert abs(poly_lr(1e-3, 0, 80000) - 1e-3) < 1e-12
+    assert abs(poly_lr(1e-3, 80000, 80000) - 1e-4) < 1e-12
+    assert abs(poly_lr(1e-2, 40000, 80000) - ((1e-2 - 1e-4) * 0.5 ** 0.9 + 1e-4)) < 1e-12

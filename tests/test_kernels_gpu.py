@@ -199,10 +199,11 @@ def test_conv3x3_simt(dtype, tol):
     L.call('s4_conv3x3_dgrad', dy.data_ptr(), wd.data_ptr(), dx.data_ptr(), B, H, W, Cin, Cout, code, L.BACKEND_SIMT, st)
     dw = torch.zeros(Cout, Cin, 3, 3, device=DEV)
     L.call('s4_conv3x3_wgrad', x.data_ptr(), dy.data_ptr(), dw.data_ptr(), B, H, W, Cin, Cout, code, L.BACKEND_SIMT, st)
-    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
-    wr = wf.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    # reference on the CPU: cuDNN would silently use TF32 for an fp32 conv
+    xr = x.float().cpu().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wr = wf.float().cpu().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).clone().requires_grad_(True)
     yr = F.conv2d(xr, wr, padding=1)
-    yr.backward(dy.float().permute(0, 3, 1, 2))
+    yr.backward(dy.float().cpu().permute(0, 3, 1, 2))
     assert rel(y.float().permute(0, 3, 1, 2), yr) < tol
     assert rel(dx.float().permute(0, 3, 1, 2), xr.grad) < tol
     assert rel(dw, wr.grad) < tol
@@ -286,7 +287,7 @@ def test_pseudo_label_bit_exact(golden_dir):
 
 def test_pseudo_label_large_random():
     g = gen(9)
-    z = (torch.randn(2, 21, 128, 256, generator=g) * 4)
+    z = (torch.randn(2, 21, 256, 256, generator=g) * 4)
     hard, conf, u = ops.pseudo_label(z.to(DEV), 0.95, 16)
     h0, c0, mv = O.pseudo_label(z, 0.95)
     near = (mv - 0.95).abs() < 1e-6          # 1-ulp band where expf implementations may differ

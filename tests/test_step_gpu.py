@@ -104,12 +104,33 @@ def test_train_step_bf16_vs_reference_golden(golden_dir, variant):
         got = float(losses[k])
         assert abs(got - float(v)) <= 2e-2 * abs(float(v)) + 1e-3, (k, got, float(v))
     named = dict(m.named_parameters())
+    # Gradients of this tiny, noisy problem: PyTorch's own bf16 autocast of the reference math
+    # loses up to ~13% (stored per tensor in the golden file); the CUDA path must not be worse
+    # than that yardstick, and must meet 2e-2 where autocast itself does.
     bad = []
     for k, g in G['grads'].items():
         r = float((named[k].grad.cpu() - g).norm() / (g.norm() + 1e-12))
-        if r > 5e-2:
-            bad.append((k, r))
+        if r > max(2e-2, G['bf16_autocast_err'][k]):
+            bad.append((k, r, G['bf16_autocast_err'][k]))
     assert not bad, bad
+
+
+def test_forward_logits_bf16_within_2e_2(golden_dir):
+    """north_star: bf16 logits within 2e-2 relative of the fp32 reference."""
+    G = _golden(golden_dir, 'ours')
+    m, _ = _build('ours')
+    m.eval()
+    g2 = torch.Generator().manual_seed(G['vit_seed'])
+    torch.rand(2, 8, 8, generator=g2)
+    x = torch.randn(2, 3, 128, 128, generator=g2)
+    with torch.no_grad():
+        logits = m.decode_head.forward(m.backbone(x.to(DEV)))
+    got, want = logits[:, :, ::2, ::2].float().cpu(), G['head_logits_eval']
+    assert float((got - want).norm() / want.norm()) < 2e-2
+    # argmax maps agree wherever the fp32 margin exceeds the bf16 error
+    top2 = want.topk(2, dim=1)[0]
+    safe = (top2[:, 0] - top2[:, 1]) > 0.05 * want.abs().max()
+    assert torch.equal(got.argmax(1)[safe], want.argmax(1)[safe])
 
 
 def test_backbone_head_forward_fp32_vs_golden(golden_dir):

@@ -51,7 +51,18 @@ def test_tc_gemm_epilogues():
 
 
 def test_tc_gemm_ragged_n():
-    _gemm_case(130, 1025, 64, BF, L.BACKEND_TC, c32=True, alpha=0.125)   # S = QK^T shape
+    """S = scale * Q K^T with N = L = 1025 (not a multiple of 8) into an fp32 buffer whose leading
+    dimension is padded to 1032, as attention.cu calls it; an unpadded ldc is routed to CUDA cores."""
+    g = gen(4)
+    M, N, K, ldc = 130, 1025, 64, 1032
+    A = torch.randn(M, K, generator=g).to(DEV, BF)
+    Bt = torch.randn(N, K, generator=g).to(DEV, BF)
+    c = torch.zeros(M, ldc, device=DEV)
+    ops.gemm(A, Bt, c, M, N, K, (K, 1), (1, K), ldc, alpha=0.125, backend_override=L.BACKEND_TC)
+    ref = 0.125 * A.float() @ Bt.float().t()
+    assert rel(c[:, :N], ref) < 2e-2
+    assert float(c[:, N:].abs().max()) == 0.0
+    _gemm_case(130, 1025, 64, BF, L.BACKEND_AUTO, c32=True, alpha=0.125)   # falls back to CUDA cores
 
 
 def test_tc_gemm_batched():
