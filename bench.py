@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""S4Former train-step benchmark (BASELINE.json metric: train steps/s, 8 labeled + 8 unlabeled
+512x512 crops per GPU, DeiT-B SETR-PUP, fraction of the bf16 tensor-core roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle)
+
+One step = EMA update, supervised pass (backbone + main head + 4 aux heads), EMA-teacher forward,
+pseudo labels, PASA student pass, CutMix/PatchShuffle student pass, masked CE + NCR, backward,
+gradient all-reduce (N > 1), SGD-momentum step.  Synthetic data, random-init weights.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--variant', default='ours', choices=['ours', 'mt', 'sup'])
+    ap.add_argument('--sup', type=int, default=8, help='labeled crops per GPU per step')
+    ap.add_argument('--unsup', type=int, default=8, help='unlabeled crops per GPU per step')
+    ap.add_argument('--size', type=int, default=512)
+    ap.add_argument('--classes', type=int, default=21)
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-prof', action='store_true')
+    ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='reference arm wall budget')
+    return ap.parse_args()
+
+
+def workload_name(a):
+    names = dict(ours='S4Former full (MT + PASA + NCR + CutMix/PatchShuffle)', mt='Mean Teacher as shipped',
+                 sup='supervised only')
+    return (f'{names[a.variant]}: {a.sup} labeled + {a.unsup if a.variant != "sup" else 0} unlabeled '
+            f'{a.size}x{a.size} crops per GPU, {a.classes} classes, DeiT-B SETR-PUP '
+            f'(BASELINE.json configs[{dict(ours=2, mt=1, sup=0)[a.variant]}] step at the metric\'s 8L+8U batch)')
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                 '-i', str(self.index)], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=max(pw))
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+# CPU reference path (the oracle: the reference's algorithm in plain PyTorch fp32)
+# --------------------------------------------------------------------------------------------
+def cpu_reference_steps(a, n_sup, n_unsup, max_steps, warmup, budget_s):
+    """Times the oracle's train step (forward_train + backward + SGD step) on the host cores for a
+    BOUNDED sample (n_sup labeled + n_unsup unlabeled crops).  Returns (seconds/step, steps, threads)."""
+    import copy
+    import torch
+    from oracle import s4former_oracle as O            # checker / CPU baseline only
+    from s4former_b200 import configs
+    from s4former_b200.utils.synthetic import make_batch, fresh_metas
+    cfg = configs.setr_pup_deit_base(a.variant, a.size, a.classes, norm='BN')
+    torch.manual_seed(1999)
+    m = O.OracleEncoderDecoder(**{k: v for k, v in cfg.items() if k != 'type'})
+    m.init_weights()
+    if m.ema:
+        m.backbone_ema.load_state_dict(m.backbone.state_dict())
+        m.decode_head_ema.load_state_dict(m.decode_head.state_dict())
+    m.train()
+    params = [p for p in m.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9)
+    img, gt, metas = make_batch(n_sup, n_unsup if a.variant != 'sup' else 0, a.size, a.classes, seed=1999)
+    O.seed_host_rng(1999)
+    times = []
+    t_start = time.perf_counter()
+    for i in range(warmup + max_steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        losses = m.forward_train(img, fresh_metas(metas), gt)
+        loss = O.parse_losses(losses)
+        loss.backward()
+        opt.step()
+        loss.item()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        # keep the whole run inside the budget (always at least one timed step)
+        if times and (time.perf_counter() - t_start) + dt > budget_s:
+            break
+    times.sort()
+    return times[len(times) // 2], len(times), torch.get_num_threads()
+
+
+def reference_arm(a):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    s_sup, s_unsup = 1, (1 if a.variant != 'sup' else 0)
+    sec, n, threads = cpu_reference_steps(a, s_sup, s_unsup, max(1, a.steps), min(a.warmup, 1), a.cpu_budget_s)
+    frac = s_sup / a.sup                      # the sample is 1/8 of the per-GPU batch
+    value = frac / sec                        # full (8L+8U) steps per second
+    unit = 'steps/s'
+    sample = (f'{s_sup} labeled + {s_unsup} unlabeled {a.size}x{a.size} crops per step (1/{a.sup} of the '
+              f'{a.sup}L+{a.unsup}U batch; value scaled by 1/{a.sup}), fp32, PyTorch CPU kernels, oracle port of the '
+              f'reference path; median of {n} timed step(s)')
+    out = dict(impl='reference', metric='train_steps_per_s', value=value, unit=unit, n_gpus=a.gpus,
+               steps=n, warmup=min(a.warmup, 1), ms_per_step=sec * 1e3 / frac, higher_is_better=True,
+               scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+               config=dict(workload=workload_name(a), sample=sample),
+               cpu_baseline=dict(value=value, unit=unit, cores=threads, kind='port', sample=sample),
+               e2e=dict(value=value, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+               gpu_launches=0)
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------
+def calibrate_teacher(model, img_t, target=0.5):
+    """Scale decode_head_ema.conv_seg so that ~`target` of the teacher's pixels clear the 0.95
+    threshold (random-init conv_seg ~ N(0, 0.01) would leave every pixel unconfident and the
+    masked CE / NCR branches idle).  Returns the achieved mask ratio."""
+    import torch
+    from s4former_b200 import ops
+    with torch.no_grad():
+        model.set_eval(True)
+        z = model.decode_head_ema.forward_get_logits(model.extract_feat_ema(img_t), None, [dict()])
+        zs = z[:, :, ::4, ::4].float()
+        lo, hi = 1.0, 1e6
+        for _ in range(40):
+            mid = (lo * hi) ** 0.5
+            r = float((torch.softmax(zs * mid, 1).max(1)[0] > 0.95).float().mean())
+            if r < target:
+                lo = mid
+            else:
+                hi = mid
+        s = (lo * hi) ** 0.5
+        model.decode_head_ema.conv_seg.weight.mul_(s)
+        model.decode_head_ema.conv_seg.bias.mul_(s)
+        ops.bump_generation(model.decode_head_ema.conv_seg.weight)
+        z = model.decode_head_ema.forward_get_logits(model.extract_feat_ema(img_t), None, [dict()])
+        _, conf, _ = ops.pseudo_label(z, 0.95, 16)
+        model.set_train(True)
+        return float(conf.float().mean())
+
+
+def main():
+    a = parse_args()
+    if a.impl == 'reference':
+        return reference_arm(a)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if a.gpus > 1 and world == 1:      # convenience: re-launch under torchrun
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    import warnings
+    warnings.filterwarnings('ignore')
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py (impl=ours) needs a GPU: there is no CPU fallback'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import s4former_b200 as s4
+    from s4former_b200 import _lib, configs, ops
+    from s4former_b200.runner import TrainStep
+    from s4former_b200.utils.synthetic import make_batch, fresh_metas
+    lib = _lib.load()
+    ops.set_compute_dtype(torch.bfloat16 if a.dtype == 'bf16' else torch.float32)
+
+    n_unsup = a.unsup if a.variant != 'sup' else 0
+    cfg = configs.setr_pup_deit_base(a.variant, a.size, a.classes, norm='SyncBN')
+    torch.manual_seed(1999)
+    model = s4.build_segmentor(cfg)
+    model.init_weights()
+    model.backbone_ema.load_state_dict(model.backbone.state_dict())
+    model.decode_head_ema.load_state_dict(model.decode_head.state_dict())
+    model = model.to(dev).train()
+    step = TrainStep(model)
+
+    img, gt, metas = make_batch(a.sup, n_unsup, a.size, a.classes, seed=1999 + rank)
+    img_h, gt_h = img.pin_memory(), gt.pin_memory()
+    img_d, gt_d = img_h.to(dev), gt_h.to(dev)
+    mask_ratio = None
+    if n_unsup:
+        t_sel = [i for i, m in enumerate(metas) if m['tag'] == 'unsup_teacher']
+        mask_ratio = calibrate_teacher(model, img_d[t_sel])
+    import numpy as np
+    import random
+    random.seed(1999 + rank)
+    np.random.seed(1999 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    it = [0]
+
+    def run_resident(_):
+        step(img_d, fresh_metas(metas), gt_d, it[0], sync=False)
+        it[0] += 1
+
+    last = {}
+
+    def run_e2e(_):
+        loss, lv = step.step_from_host(img_h, fresh_metas(metas), gt_h, it[0])
+        last.update(lv)
+        it[0] += 1
+
+    for i in range(max(a.warmup, 3)):
+        run_resident(i)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.s4_launch_count()
+    ms = timed(run_resident, a.steps)
+    launches = (lib.s4_launch_count() - l0) // a.steps
+    run_e2e(0)
+    ms_e2e = timed(run_e2e, a.steps)
+    clk = clocks.stop() if rank == 0 else None
+    loss_val = last.get('loss')
+    assert loss_val == loss_val, 'loss is NaN'
+
+    # ---- roofline leg: per-kernel-family device time, measured live with CUDA events ---------
+    kinds = []
+    if not a.no_prof:
+        lib.s4_prof_enable(1)
+        nprof = 2
+        for i in range(nprof):
+            run_resident(i)
+        torch.cuda.synchronize()
+        import ctypes as C
+        for i in range(lib.s4_prof_num_kinds()):
+            name = C.create_string_buffer(64)
+            unit, kms, work, n = C.c_int(), C.c_double(), C.c_double(), C.c_longlong()
+            lib.s4_prof_get(i, name, 64, C.byref(unit), C.byref(kms), C.byref(work), C.byref(n))
+            kinds.append(dict(name=name.value.decode(), unit='flop' if unit.value == 0 else 'byte',
+                              ms_per_step=kms.value / nprof, work_per_step=work.value / nprof,
+                              launches_per_step=n.value / nprof))
+        lib.s4_prof_enable(0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    tc_peak = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PFLOP/s sustained'
+    flops = configs.step_flops(a.variant, a.sup, n_unsup, a.size, a.classes)
+    sec = ms / 1e3 / a.steps
+    sec_e2e = ms_e2e / 1e3 / a.steps
+    value = world / sec
+    roofline = dict(bound='tensor', achieved=None, peak=tc_peak, unit='TFLOP/s', frac=None, traffic=None,
+                    peak_source=peak_src)
+    tcs = [k for k in kinds if k['unit'] == 'flop' and k['work_per_step'] > 0 and k['ms_per_step'] > 0]
+    if tcs:
+        dom = max(tcs, key=lambda k: k['ms_per_step'])
+        ach = dom['work_per_step'] / (dom['ms_per_step'] * 1e-3) / 1e12
+        roofline.update(kernel=dom['name'], achieved=ach, frac=ach / tc_peak,
+                        launches_per_step=dom['launches_per_step'],
+                        avg_launch_ms=dom['ms_per_step'] / dom['launches_per_step'],
+                        flop_per_launch=dom['work_per_step'] / dom['launches_per_step'],
+                        share_of_step=dom['ms_per_step'] / (sec * 1e3))
+    out = dict(metric='train_steps_per_s', value=value, unit='steps/s', n_gpus=world, steps=a.steps,
+               warmup=max(a.warmup, 3), ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak',
+               vs_baseline=None, dtype=a.dtype, data='synthetic',
+               config=dict(workload=workload_name(a), parallelism=f'dp{world}',
+                           images_per_step_per_gpu=a.sup + 2 * n_unsup,
+                           l2='working set (activations > 10 GB per step) far exceeds the 126 MB L2; no flush needed',
+                           teacher_mask_ratio=mask_ratio, optimizer='SGD momentum 0.9, poly LR, head lr x10 (fused)'),
+               images_per_s=value * (a.sup + n_unsup),
+               step_tflops=flops / sec / 1e12, step_tc_frac=flops / sec / 1e12 / tc_peak,
+               flop_per_step=flops, loss=loss_val,
+               e2e=dict(value=world / sec_e2e, unit='steps/s', ms_per_step=sec_e2e * 1e3,
+                        h2d_bytes_per_step=img_h.numel() * 4 + gt_h.numel() * 8,
+                        d2h_bytes_per_step=4 * len(last)),
+               gpu_launches=int(launches) * a.steps, gpu_launches_per_step=int(launches),
+               clocks=clk, roofline=roofline,
+               kernels=sorted(kinds, key=lambda k: -k['ms_per_step'])[:12])
+    if world == 1 and not a.no_cpu_baseline:
+        s_sup, s_unsup = 1, (1 if n_unsup else 0)
+        csec, n, threads = cpu_reference_steps(a, s_sup, s_unsup, 1, 0, 40.0)
+        out['cpu_baseline'] = dict(
+            value=(s_sup / a.sup) / csec, unit='steps/s', cores=threads, kind='port',
+            sample=f'{s_sup} labeled + {s_unsup} unlabeled {a.size}x{a.size} crops, one oracle step '
+                   f'({csec:.1f} s), scaled by 1/{a.sup} to the {a.sup}L+{a.unsup}U step')
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -42,6 +42,13 @@ int s4_version(void);
 int s4_built_arch(void);            /* 100 = sm_100a */
 const char* s4_last_error(void);
 long long s4_launch_count(void);     /* kernels launched by this library in this process */
+/* Optional device timing per kernel family (bench.py's roofline leg): while enabled every
+ * family brackets its launches with a CUDA event pair on the launching stream and books its
+ * algorithmic work (unit 0 = FLOP, 1 = byte; 0 work = time only).  Reading synchronises. */
+int s4_prof_enable(int on);          /* turning on clears the totals */
+int s4_prof_num_kinds(void);
+int s4_prof_get(int idx, char* name, int name_len, int* unit, double* ms, double* work,
+                long long* launches);
 
 /* ---- GEMM with fused epilogue -------------------------------------------------------------
  * Replaces: nn.Linear / in_proj / out_proj / FFN inside mmcv MultiheadAttention and FFN as

@@ -39,6 +39,10 @@ _SPEC = {
     's4_built_arch': (_I, []),
     's4_last_error': (C.c_char_p, []),
     's4_launch_count': (C.c_longlong, []),
+    's4_prof_enable': (_I, [_I]),
+    's4_prof_num_kinds': (_I, []),
+    's4_prof_get': (_I, [_I, C.c_char_p, _I, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                         C.POINTER(C.c_longlong)]),
     's4_gemm': (_I, [C.POINTER(GemmParams), _P]),
     's4_gemm_uses_tc': (_I, [C.POINTER(GemmParams)]),
     's4_layernorm_fwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P]),

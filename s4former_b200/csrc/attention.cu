@@ -203,6 +203,7 @@ extern "C" int s4_attention_fwd(const void* qkv, const float* u0, const float* g
                                 float bias_weight, void* out, float* lse, void* workspace,
                                 size_t ws_bytes, int B, int H, int L, int hd, int dtype,
                                 int backend, cudaStream_t stream) {
+  S4ProfScope prof_("attention_fwd", 0.0, 1, stream);
   if (B * H * L == 0) return S4_OK;
   if (backend != S4_BACKEND_SIMT && s4_attention_tc_supported(B, H, L, hd, dtype))
     return s4_attention_tc_fwd(qkv, u0, gate, bias_weight, out, lse, B, H, L, hd, stream);
@@ -221,6 +222,7 @@ extern "C" int s4_attention_bwd(const void* dout, const void* qkv, const void* o
                                 float bias_weight, void* dqkv, void* workspace, size_t ws_bytes,
                                 int B, int H, int L, int hd, int dtype, int backend,
                                 cudaStream_t stream) {
+  S4ProfScope prof_("attention_bwd", 0.0, 1, stream);
   if (B * H * L == 0) return S4_OK;
   if (backend != S4_BACKEND_SIMT && s4_attention_tc_supported(B, H, L, hd, dtype))
     return s4_attention_tc_bwd(dout, qkv, out, lse, u0, gate, bias_weight, dqkv, workspace,

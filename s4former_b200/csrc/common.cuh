@@ -18,6 +18,25 @@ void s4_set_error(const char* fmt, ...);
 int s4_check_launch(const char* what);   // also counts one kernel launch
 void s4_count_launches(int n);           // extra launches behind a single check
 
+// ---- optional per-kernel-family device timing (s4_prof_* in include/s4former.h) ---------------
+// When enabled, a scope records a CUDA event pair on the launching stream around the launches
+// it brackets and books `work` (FLOPs or bytes: the ALGORITHMIC figure, not the executed one)
+// under `name`.  Disabled (the default) it costs one relaxed atomic load.
+bool s4_prof_on();
+void s4_prof_begin(const char* name, double work, int unit /*0 = flop, 1 = byte*/, cudaStream_t st,
+                   void** cookie);
+void s4_prof_end(void* cookie, cudaStream_t st);
+struct S4ProfScope {
+  void* cookie = nullptr;
+  cudaStream_t st;
+  S4ProfScope(const char* name, double work, int unit, cudaStream_t s) : st(s) {
+    if (s4_prof_on()) s4_prof_begin(name, work, unit, s, &cookie);
+  }
+  ~S4ProfScope() {
+    if (cookie) s4_prof_end(cookie, st);
+  }
+};
+
 #define S4_REQUIRE(cond, ...)            \
   do {                                   \
     if (!(cond)) {                       \

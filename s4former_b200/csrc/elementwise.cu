@@ -29,6 +29,7 @@ __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ o
 
 extern "C" int s4_patchify(const float* img, void* out, int B, int Cin, int H, int W, int P,
                            int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("patchify", 0.0, 1, stream);
   const int gh = (H + P - 1) / P, gw = (W + P - 1) / P;
   const size_t total = (size_t)B * gh * gw * Cin * P * P;
   if (total == 0) return S4_OK;
@@ -85,6 +86,7 @@ __global__ void assemble_tokens_bwd_kernel(const T* __restrict__ dx, T* __restri
 
 extern "C" int s4_assemble_tokens(const void* tok, const float* cls, const float* pos, void* x,
                                   int B, int L, int D, int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("assemble_tokens", 0.0, 1, stream);
   const size_t total = (size_t)B * L * D;
   if (total == 0) return S4_OK;
   const int grid = (int)min((total + 255) / 256, (size_t)s4_num_sms() * 16);
@@ -99,6 +101,7 @@ extern "C" int s4_assemble_tokens(const void* tok, const float* cls, const float
 // dcls / dpos are ACCUMULATED (+=)
 extern "C" int s4_assemble_tokens_bwd(const void* dx, void* dtok, float* dcls, float* dpos, int B,
                                       int L, int D, int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("assemble_tokens_bwd", 0.0, 1, stream);
   const size_t total = (size_t)L * D;
   if (total == 0 || B == 0) return S4_OK;
   const int grid = (int)min((total + 255) / 256, (size_t)s4_num_sms() * 16);
@@ -135,6 +138,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ sum,
 // sum / sumsq are ACCUMULATED (+=): zero them first when a fresh sum is wanted.
 extern "C" int s4_colsum(const void* x, float* sum, float* sumsq, long long rows, int cols,
                          int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("colsum", 0.0, 1, stream);
   if (rows == 0 || cols == 0) return S4_OK;
   const int bx = 128;
   const int gx = (cols + bx - 1) / bx;
@@ -175,6 +179,7 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float*
 
 extern "C" int s4_cast(const void* x, void* y, long long n, int src_dtype, int dst_dtype,
                        cudaStream_t stream) {
+  S4ProfScope prof_("cast", 0.0, 1, stream);
   if (n == 0) return S4_OK;
   const int grid = (int)min(((size_t)n / 4 + 255) / 256 + 1, (size_t)s4_num_sms() * 16);
   if (src_dtype == S4_F32 && dst_dtype == S4_BF16)
@@ -209,6 +214,7 @@ __global__ void transpose_kernel(const T* __restrict__ x, T* __restrict__ y, int
 
 extern "C" int s4_transpose(const void* x, void* y, int batch, int rows, int cols, int dtype,
                             cudaStream_t stream) {
+  S4ProfScope prof_("transpose", 0.0, 1, stream);
   if (batch == 0 || rows == 0 || cols == 0) return S4_OK;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch), block(32, 8);
   const size_t bs = (size_t)rows * cols;
@@ -268,6 +274,7 @@ extern "C" int s4_ema_multi_tensor(void* const* dst_ptrs, void* const* src_ptrs,
                                    const long long* sizes, const int* chunk_tensor,
                                    const long long* chunk_off, int n_chunks, float momentum,
                                    float one_minus_momentum, cudaStream_t stream) {
+  S4ProfScope prof_("ema_multi_tensor", 0.0, 1, stream);
   if (n_chunks == 0) return S4_OK;
   S4TensorTable t{dst_ptrs, src_ptrs, nullptr, sizes, nullptr, chunk_tensor, chunk_off};
   ema_multi_kernel<<<n_chunks, 256, 0, stream>>>(t, momentum, one_minus_momentum);
@@ -304,6 +311,7 @@ extern "C" int s4_sgd_multi_tensor(void* const* params, void* const* grads, void
                                    const float* lrs, const int* chunk_tensor,
                                    const long long* chunk_off, int n_chunks, float momentum,
                                    float weight_decay, int first_step, cudaStream_t stream) {
+  S4ProfScope prof_("sgd_multi_tensor", 0.0, 1, stream);
   if (n_chunks == 0) return S4_OK;
   S4TensorTable t{params, grads, bufs, sizes, lrs, chunk_tensor, chunk_off};
   sgd_multi_kernel<<<n_chunks, 256, 0, stream>>>(t, bf16_shadow, momentum, weight_decay, first_step);
@@ -338,6 +346,7 @@ __global__ void cutmix_kernel(const float* __restrict__ img, const long long* __
 extern "C" int s4_cutmix(const float* img, const long long* label, const int* boxes_dev,
                          float* out_img, long long* out_label, int B, int C, int H, int W,
                          cudaStream_t stream) {
+  S4ProfScope prof_("cutmix", 0.0, 1, stream);
   const size_t total = (size_t)B * H * W;
   if (total == 0) return S4_OK;
   const int grid = (int)min((total + 255) / 256, (size_t)s4_num_sms() * 16);
@@ -366,6 +375,7 @@ __global__ void patchshuffle_kernel(const float* __restrict__ img, const long lo
 
 extern "C" int s4_patchshuffle(const float* img, const long long* perm_dev, float* out, int B,
                                int C, int H, int W, int block, cudaStream_t stream) {
+  S4ProfScope prof_("patchshuffle", 0.0, 1, stream);
   S4_REQUIRE(block > 0 && H % block == 0 && W % block == 0, "patchshuffle: H,W must be multiples of block");
   const size_t total = (size_t)B * C * H * W;
   if (total == 0) return S4_OK;

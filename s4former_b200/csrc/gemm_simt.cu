@@ -97,6 +97,7 @@ int s4_gemm_simt_launch(const S4GemmParams& p, cudaStream_t stream) {
   if (p.M == 0 || p.N == 0 || p.nb1 * p.nb2 == 0) return S4_OK;
   dim3 grid((p.N + TN - 1) / TN, (p.M + TM - 1) / TM, p.nb1 * p.nb2);
   S4_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_simt: grid too large");
+  S4ProfScope prof("gemm_simt", 2.0 * p.M * p.N * (double)p.K * p.nb1 * p.nb2, 0, stream);
   if (p.dtype == S4_BF16) {
     if (p.c_dtype == S4_F32)
       gemm_simt_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>(p);

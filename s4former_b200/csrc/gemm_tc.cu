@@ -535,6 +535,7 @@ int s4_gemm_tc_launch(const S4GemmParams& g, cudaStream_t stream) {
   p.c_sm = g.c_sm; p.c_sn = 1; p.c_b1 = g.c_b1; p.c_b2 = g.c_b2;
   p.alpha = g.alpha; p.act = g.act; p.accumulate = g.accumulate;
   p.c_f32 = g.c_dtype == S4_F32; p.atomic = splits > 1;
+  S4ProfScope prof("gemm_tc", 2.0 * g.M * g.N * (double)g.K * nb, 0, stream);
   return launch_any(BN, ta, tb, p, stream);
 }
 
@@ -603,6 +604,7 @@ int s4_conv3x3_tc(const void* x, const void* w_packed, void* y, int B, int H, in
   p.c = y;
   p.c_sm = Cout; p.c_sn = 1; p.c_b1 = 0; p.c_b2 = 0;
   p.alpha = 1.f; p.c_f32 = 0;
+  S4ProfScope prof("conv3x3_tc", 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 0, stream);
   return launch_any(BN, ta, tb, p, stream);
 }
 
@@ -655,5 +657,6 @@ int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, 
   p.c = dw;
   p.c_sm = (long long)Cin * 9; p.c_sn = 9; p.c_b1 = 0; p.c_b2 = 1;   // z2 = tap
   p.alpha = 1.f; p.c_f32 = 1; p.atomic = 1; p.accumulate = 1;
+  S4ProfScope prof("conv3x3_wgrad_tc", 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 0, stream);
   return launch_any(BN, ta, tb, p, stream);
 }

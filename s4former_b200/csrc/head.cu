@@ -177,17 +177,20 @@ static int conv3x3_any(const void* x, const void* w, void* y, int B, int H, int 
 
 extern "C" int s4_conv3x3_fwd(const void* x, const void* w_packed, void* y, int B, int H, int W,
                               int Cin, int Cout, int dtype, int backend, cudaStream_t stream) {
+  S4ProfScope prof_("conv3x3_fwd", 0.0, 1, stream);
   return conv3x3_any(x, w_packed, y, B, H, W, Cin, Cout, dtype, backend, stream);
 }
 
 extern "C" int s4_conv3x3_dgrad(const void* dy, const void* w_dgrad, void* dx, int B, int H, int W,
                                 int Cin, int Cout, int dtype, int backend, cudaStream_t stream) {
+  S4ProfScope prof_("conv3x3_dgrad", 0.0, 1, stream);
   // dgrad of a stride-1 pad-1 3x3 conv is a 3x3 conv of dy with flipped, transposed weights
   return conv3x3_any(dy, w_dgrad, dx, B, H, W, Cout, Cin, dtype, backend, stream);
 }
 
 extern "C" int s4_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W,
                                 int Cin, int Cout, int dtype, int backend, cudaStream_t stream) {
+  S4ProfScope prof_("conv3x3_wgrad", 0.0, 1, stream);
   const long long P = (long long)B * H * W;
   if (P == 0) return S4_OK;
   if (backend != S4_BACKEND_SIMT && s4_conv3x3_wgrad_tc_supported(B, H, W, Cin, Cout, dtype))
@@ -224,6 +227,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restri
 
 extern "C" int s4_pack_conv3x3_weight(const float* w, void* w_fwd, void* w_dgrad, int Cin,
                                       int Cout, int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("pack_conv3x3_weight", 0.0, 1, stream);
   const int total = Cout * Cin * 9;
   if (total == 0) return S4_OK;
   const int grid = min((total + 255) / 256, s4_num_sms() * 8);
@@ -265,6 +269,7 @@ extern "C" int s4_bn_finalize(const float* sum, const float* sumsq, double count
                               float momentum, const float* gamma, const float* beta, float* mean,
                               float* invstd, float* scale, float* shift, float* running_mean,
                               float* running_var, int C, cudaStream_t stream) {
+  S4ProfScope prof_("bn_finalize", 0.0, 1, stream);
   if (C == 0) return S4_OK;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum, sumsq, count, eps, momentum, gamma,
                                                          beta, mean, invstd, scale, shift,
@@ -285,6 +290,7 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ rm, const float*
 extern "C" int s4_bn_eval_affine(const float* running_mean, const float* running_var,
                                  const float* gamma, const float* beta, float eps, float* scale,
                                  float* shift, int C, cudaStream_t stream) {
+  S4ProfScope prof_("bn_eval_affine", 0.0, 1, stream);
   if (C == 0) return S4_OK;
   bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, stream>>>(running_mean, running_var, gamma, beta, eps, scale, shift, C);
   return s4_check_launch("bn_eval_affine");
@@ -350,6 +356,7 @@ bn_relu_upsample_fwd_kernel(const T* __restrict__ x, const float* __restrict__ s
 extern "C" int s4_bn_relu_upsample_fwd(const void* x, const float* scale, const float* shift,
                                        void* out, int B, int H, int W, int C, int s, int dtype,
                                        cudaStream_t stream) {
+  S4ProfScope prof_("bn_relu_upsample_fwd", 0.0, 1, stream);
   const int vn = dtype == S4_BF16 ? 8 : 4;
   S4_REQUIRE(C % vn == 0 && s >= 1, "bn_relu_upsample: C=%d must be a multiple of %d", C, vn);
   const size_t total = (size_t)B * H * s * W * s * (C / vn);
@@ -444,6 +451,7 @@ extern "C" int s4_bn_relu_upsample_bwd(const void* dout, const void* x, const fl
                                        const float* shift, const float* mean, const float* invstd,
                                        void* dact, float* dsum, float* ddot, int B, int H, int W,
                                        int C, int s, int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("bn_relu_upsample_bwd", 0.0, 1, stream);
   const int vn = dtype == S4_BF16 ? 8 : 4;
   S4_REQUIRE(C % vn == 0 && s >= 1, "bn_relu_upsample_bwd: C=%d must be a multiple of %d", C, vn);
   const size_t total = (size_t)B * H * W * (C / vn);
@@ -494,6 +502,7 @@ extern "C" int s4_bn_bwd_apply(const void* dact, const void* x, const float* gam
                                const float* mean, const float* invstd, const float* dsum,
                                const float* ddot, double count, void* dy, long long rows, int C,
                                int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("bn_bwd_apply", 0.0, 1, stream);
   const int vn = dtype == S4_BF16 ? 8 : 4;
   S4_REQUIRE(C % vn == 0, "bn_bwd_apply: C=%d must be a multiple of %d", C, vn);
   const size_t total = (size_t)rows * (C / vn);
@@ -556,6 +565,7 @@ bn_relu_conv1x1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ sc
 extern "C" int s4_bn_relu_conv1x1_fwd(const void* x, const float* scale, const float* shift,
                                       const float* w, const float* bias, float* z, long long rows,
                                       int C, int NC, int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("bn_relu_conv1x1_fwd", 0.0, 1, stream);
   S4_REQUIRE(NC >= 1 && NC <= MAXNC, "conv1x1: NC=%d not in [1,%d]", NC, MAXNC);
   if (rows == 0) return S4_OK;
   const size_t smem = ((size_t)NC * C + 2 * C) * sizeof(float);
@@ -631,6 +641,7 @@ extern "C" int s4_bn_relu_conv1x1_bwd(const float* dz, const void* x, const floa
                                       const float* w, void* dact, float* dw, float* dbias,
                                       float* dsum, float* ddot, long long rows, int C, int NC,
                                       int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("bn_relu_conv1x1_bwd", 0.0, 1, stream);
   S4_REQUIRE(NC >= 1 && NC <= MAXNC, "conv1x1_bwd: NC=%d not in [1,%d]", NC, MAXNC);
   S4_REQUIRE(C >= NC && C <= 1024 && C % 32 == 0, "conv1x1_bwd: C=%d must be a multiple of 32 in [NC,1024]", C);
   if (rows == 0) return S4_OK;
@@ -701,6 +712,7 @@ upsample_logits_bwd_kernel(const float* __restrict__ dout, float* __restrict__ d
 
 extern "C" int s4_upsample_logits_fwd(const float* z, float* logits, int B, int H, int W, int NC,
                                       int s, cudaStream_t stream) {
+  S4ProfScope prof_("upsample_logits_fwd", 0.0, 1, stream);
   const size_t total = (size_t)B * NC * H * s * W * s;
   if (total == 0) return S4_OK;
   const int grid = (int)min((total + 255) / 256, (size_t)s4_num_sms() * 32);
@@ -710,6 +722,7 @@ extern "C" int s4_upsample_logits_fwd(const float* z, float* logits, int B, int 
 
 extern "C" int s4_upsample_logits_bwd(const float* dlogits, float* dz, int B, int H, int W, int NC,
                                       int s, cudaStream_t stream) {
+  S4ProfScope prof_("upsample_logits_bwd", 0.0, 1, stream);
   const size_t total = (size_t)B * NC * H * W;
   if (total == 0) return S4_OK;
   const int grid = (int)min((total + 255) / 256, (size_t)s4_num_sms() * 32);

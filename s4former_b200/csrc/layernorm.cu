@@ -162,6 +162,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
 extern "C" int s4_layernorm_fwd(const void* x, const int* row_map, const float* gamma,
                                 const float* beta, void* y, float* mean, float* rstd, int rows,
                                 int D, float eps, int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("layernorm_fwd", 0.0, 1, stream);
   const int vn = dtype == S4_BF16 ? 8 : 4;
   S4_REQUIRE(D % vn == 0 && D / vn <= 32 * LN_MAX_VPL, "layernorm: unsupported D=%d", D);
   if (rows == 0) return S4_OK;
@@ -181,6 +182,7 @@ extern "C" int s4_layernorm_bwd(const void* dy, const void* x, const int* row_ma
                                 const float* gamma, const float* mean, const float* rstd,
                                 const void* dres, void* dx, float* dgamma, float* dbeta, int rows,
                                 int D, int dtype, cudaStream_t stream) {
+  S4ProfScope prof_("layernorm_bwd", 0.0, 1, stream);
   const int vn = dtype == S4_BF16 ? 8 : 4;
   S4_REQUIRE(D % vn == 0 && D / vn <= 32 * LN_MAX_VPL, "layernorm: unsupported D=%d", D);
   if (rows == 0) return S4_OK;

@@ -61,6 +61,7 @@ pseudo_label_kernel(const float* __restrict__ z, long long* __restrict__ hard,
 extern "C" int s4_pseudo_label(const float* logits, long long* hard, long long* conf, float* u,
                                int B, int C, int H, int W, int patch, float threshold,
                                cudaStream_t stream) {
+  S4ProfScope prof_("pseudo_label", 0.0, 1, stream);
   S4_REQUIRE(C >= 1 && C <= S4_MAXC, "pseudo_label: C=%d not in [1,%d]", C, S4_MAXC);
   S4_REQUIRE(patch == 8 || patch == 16, "pseudo_label: patch must be 8 or 16 (got %d)", patch);
   S4_REQUIRE(H % 16 == 0 && W % 32 == 0, "pseudo_label: H%%16, W%%32 required (H=%d W=%d)", H, W);
@@ -205,6 +206,7 @@ extern "C" int s4_ce_ncr(const float* logits_s, const float* logits_t, const lon
                          float* dlogits, float* loss_out, const float* grad_scale, int B, int C,
                          int H, int W, float ce_weight, float ncr_weight, int ignore_index,
                          void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  S4ProfScope prof_("ce_ncr", 0.0, 1, stream);
   S4_REQUIRE(C >= 1 && C <= S4_MAXC, "ce_ncr: C=%d not in [1,%d]", C, S4_MAXC);
   const size_t npix = (size_t)B * H * W;
   S4_REQUIRE(npix > 0, "ce_ncr: empty input");
@@ -237,6 +239,7 @@ __global__ void scale_by_scalar_kernel(float* __restrict__ y, const float* __res
 }
 
 extern "C" int s4_scale_by_scalar(float* y, const float* scale_dev, size_t n, cudaStream_t stream) {
+  S4ProfScope prof_("scale_by_scalar", 0.0, 1, stream);
   if (n == 0) return S4_OK;
   const int grid = s4_num_sms() * 8;
   scale_by_scalar_kernel<<<grid, 256, 0, stream>>>(y, scale_dev, n / 4, n);
