@@ -108,9 +108,10 @@ int s4_layernorm_bwd(const void* dy, const void* x, const int* row_map, const fl
  * built at vit.py:519-535.  The mask is never materialised: bias[b,h,q,k] =
  * w * gate[b,q] * u0[b,k] (rank 1, same for all heads and layers).
  * qkv: [B, L, 3*H*hd] packed as torch in_proj emits it; out: [B, L, H*hd].
- * u0/gate: [B, L] float32 or NULL.  `probs` (workspace, [B,H,L,L] in `dtype`) is kept for the
- * backward when the unfused path runs; lse: [B,H,L] float32. */
-size_t s4_attention_workspace(int B, int H, int L, int hd, int dtype);
+ * u0/gate: [B, L] float32 or NULL; lse: [B,H,L] float32 (natural log).  bf16 with hd = 64 runs
+ * the fused tcgen05 flash kernels (forward needs no workspace; backward: rowsum(dO*O) and an fp32
+ * dQ accumulator); other cases run the composed GEMM + softmax path ([B,H,L,L] scratch). */
+size_t s4_attention_workspace(int B, int H, int L, int hd, int dtype, int backend);
 int s4_attention_fwd(const void* qkv, const float* u0, const float* gate, float bias_weight,
                      void* out, float* lse, void* workspace, size_t ws_bytes, int B, int H, int L,
                      int hd, int dtype, int backend, cudaStream_t stream);

@@ -84,10 +84,21 @@ softmax_bwd_kernel(const float* __restrict__ dP, const T* __restrict__ P, T* __r
   }
 }
 
-extern "C" size_t s4_attention_workspace(int B, int H, int L, int hd, int dtype) {
+bool s4_attention_tc_fwd_supported(int B, int H, int L, int hd, int dtype);
+bool s4_attention_tc_bwd_supported(int B, int H, int L, int hd, int dtype);
+size_t s4_attention_tc_bwd_workspace(int B, int H, int L);
+
+static size_t composed_workspace(int B, int H, int L, int dtype) {
   const size_t e = (size_t)B * H * L * pad8(L);
   const size_t ts = dtype == S4_BF16 ? 2 : 4;
   return e * 4 + 2 * e * ts + 256;
+}
+
+extern "C" size_t s4_attention_workspace(int B, int H, int L, int hd, int dtype, int backend) {
+  if (backend != S4_BACKEND_SIMT && s4_attention_tc_fwd_supported(B, H, L, hd, dtype) &&
+      s4_attention_tc_bwd_supported(B, H, L, hd, dtype))
+    return s4_attention_tc_bwd_workspace(B, H, L);
+  return composed_workspace(B, H, L, dtype);
 }
 
 static void base_params(S4GemmParams& g, int dtype, int backend) {
@@ -197,18 +208,16 @@ int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, flo
 int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, const float* lse,
                         const float* u0, const float* gate, float w, void* dqkv, void* ws,
                         size_t ws_bytes, int B, int H, int L, int hd, cudaStream_t st);
-bool s4_attention_tc_supported(int B, int H, int L, int hd, int dtype);
-
 extern "C" int s4_attention_fwd(const void* qkv, const float* u0, const float* gate,
                                 float bias_weight, void* out, float* lse, void* workspace,
                                 size_t ws_bytes, int B, int H, int L, int hd, int dtype,
                                 int backend, cudaStream_t stream) {
   S4ProfScope prof_("attention_fwd", 0.0, 1, stream);
   if (B * H * L == 0) return S4_OK;
-  if (backend != S4_BACKEND_SIMT && s4_attention_tc_supported(B, H, L, hd, dtype))
+  if (backend != S4_BACKEND_SIMT && s4_attention_tc_fwd_supported(B, H, L, hd, dtype))
     return s4_attention_tc_fwd(qkv, u0, gate, bias_weight, out, lse, B, H, L, hd, stream);
   S4_REQUIRE(backend != S4_BACKEND_TC, "attention: fused tcgen05 path does not support this shape");
-  S4_REQUIRE(ws_bytes >= s4_attention_workspace(B, H, L, hd, dtype), "attention_fwd: workspace too small");
+  S4_REQUIRE(ws_bytes >= composed_workspace(B, H, L, dtype), "attention_fwd: workspace too small");
   if (dtype == S4_BF16)
     return attention_fwd_t<__nv_bfloat16>((const __nv_bfloat16*)qkv, u0, gate, bias_weight,
                                           (__nv_bfloat16*)out, lse, workspace, B, H, L, hd, dtype,
@@ -224,11 +233,11 @@ extern "C" int s4_attention_bwd(const void* dout, const void* qkv, const void* o
                                 cudaStream_t stream) {
   S4ProfScope prof_("attention_bwd", 0.0, 1, stream);
   if (B * H * L == 0) return S4_OK;
-  if (backend != S4_BACKEND_SIMT && s4_attention_tc_supported(B, H, L, hd, dtype))
+  if (backend != S4_BACKEND_SIMT && s4_attention_tc_bwd_supported(B, H, L, hd, dtype))
     return s4_attention_tc_bwd(dout, qkv, out, lse, u0, gate, bias_weight, dqkv, workspace,
                                ws_bytes, B, H, L, hd, stream);
   S4_REQUIRE(backend != S4_BACKEND_TC, "attention: fused tcgen05 path does not support this shape");
-  S4_REQUIRE(ws_bytes >= s4_attention_workspace(B, H, L, hd, dtype), "attention_bwd: workspace too small");
+  S4_REQUIRE(ws_bytes >= composed_workspace(B, H, L, dtype), "attention_bwd: workspace too small");
   if (dtype == S4_BF16)
     return attention_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)qkv,
                                           lse, u0, gate, bias_weight, (__nv_bfloat16*)dqkv,

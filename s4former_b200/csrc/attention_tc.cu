@@ -1,18 +1,825 @@
-// Fused flash-style attention with the in-tile PASA bias on tcgen05 (placeholder dispatch:
-// until the fused kernel lands every shape is served by the composed path in attention.cu).
-#include "common.cuh"
+// Fused flash-style attention on tcgen05 / TMEM / TMA with S4Former's patch-adaptive (PASA)
+// bias applied in-tile (sm_100a).
+//
+// Reference: mmcv MultiheadAttention -> nn.MultiheadAttention as driven from
+// mmseg/models/backbones/vit.py:119 with the additive float mask of vit.py:519-535,
+//     bias[b,h,q,k] = w * gate[b,q] * u0[b,k]           (rank 1; same for all heads / layers)
+// which is added to the scaled logits inside the softmax warps: no L x L tensor ever exists.
+//
+// FORWARD.  One CTA per (batch, head, 128-query tile); two CTAs are co-resident per SM so one
+// CTA's softmax overlaps the other's MMAs.  256 threads:
+//   warp 0      TMA producer: Q tile once, then K and V tiles (128 keys x 64) through two
+//               2-stage rings (cp.async.bulk.tensor.4d, 128B swizzle, zero fill past L)
+//   warp 1      MMA issuer + TMEM owner: S = Q K^T (128 x n x 64, SS) into TMEM cols [0,128);
+//               O += P V (128 x 64 x n, P read from TMEM, V from smem) into cols [128,192)
+//   warps 4-7   softmax: one query row per thread; tcgen05.ld S -> registers, online softmax in
+//               the log2 domain with LAZY rescaling (O is only rescaled when the running max
+//               grows by more than 2^8), P packed to bf16 and stored over S with tcgen05.st
+// Register budget is moved from warps 0-3 to the softmax warps with setmaxnreg.
+// The key loop runs full 128-key tiles plus one tail tile of round_up(L % 128, 16) keys, so
+// L = 1025 (512^2 crops) costs 8 tiles + a 16-key MMA, not 9 tiles.
+#include <math.h>
+#include <stdlib.h>
 
-bool s4_attention_tc_supported(int B, int H, int L, int hd, int dtype) { return false; }
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int HD = 64;
+constexpr int TILE_BYTES = 128 * HD * 2;   // 16 KB: 128 rows x 64 bf16, 128B-swizzled
+constexpr int FWD_THREADS = 256;
+constexpr int S_COL = 0;                    // TMEM columns: S fp32 [0,128), P bf16x2 [0,64)
+constexpr int O_COL = 128;                  // O fp32 [128,192)
+constexpr int TMEM_COLS = 256;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 domain: P may grow up to 2^8 before O is rescaled
+
+struct FwdParams {
+  void* out;          // [B, L, H*64] bf16
+  float* lse;         // [B, H, L] natural-log LSE of the biased, scaled logits
+  const float* u0;    // [B, L] or null
+  const float* gate;  // [B, L] or null
+  float w;            // bias weight
+  float scale;        // 1/sqrt(hd)
+  int B, H, L;
+  int q_tiles;        // ceil(L / 128)
+  int n_full, rem, tail_n;   // key tiles: n_full x 128 + one tail of tail_n (rem valid) keys
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = tc::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sK = base + TILE_BYTES;          // 2 stages
+  const uint32_t sV = base + 3 * TILE_BYTES;      // 2 stages
+  const uint32_t bar = base + 5 * TILE_BYTES;
+  const uint32_t q_full = bar;
+  auto k_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar + 8u * (3 + s); };
+  auto v_full = [&](int s) { return bar + 8u * (5 + s); };
+  auto v_empty = [&](int s) { return bar + 8u * (7 + s); };
+  const uint32_t s_full = bar + 8u * 9;
+  const uint32_t p_full = bar + 8u * 10;
+  const uint32_t o_final = bar + 8u * 11;
+  const uint32_t tmem_slot = bar + 8u * 12;
+  uint8_t* gen = smem_raw + (base - raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 5 * TILE_BYTES + 8 * 12);
+  float* u0s = reinterpret_cast<float*>(gen + 5 * TILE_BYTES + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.q_tiles;
+  const int bh = blockIdx.x / p.q_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int n_tiles = p.n_full + (p.tail_n ? 1 : 0);
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tm_qkv);
+    tc::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(k_full(s), 1);
+      tc::mbar_init(k_empty(s), 1);
+      tc::mbar_init(v_full(s), 1);
+      tc::mbar_init(v_empty(s), 1);
+    }
+    tc::mbar_init(s_full, 1);
+    tc::mbar_init(p_full, 4);
+    tc::mbar_init(o_final, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    tc::reg_dec<40>();
+    if (warp == 0 && lane == 0) {
+      // ================================ TMA producer ========================================
+      tc::mbar_expect_tx(q_full, TILE_BYTES);
+      tc::tma_load_4d(sQ, &tm_qkv, q_full, 0, qt * BQ, h, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        tc::mbar_wait(k_empty(s), ph ^ 1u);
+        tc::mbar_expect_tx(k_full(s), TILE_BYTES);
+        tc::tma_load_4d(sK + s * TILE_BYTES, &tm_qkv, k_full(s), 0, j * BKV, p.H + h, b);
+        tc::mbar_wait(v_empty(s), ph ^ 1u);
+        tc::mbar_expect_tx(v_full(s), TILE_BYTES);
+        tc::tma_load_4d(sV + s * TILE_BYTES, &tm_qkv, v_full(s), 0, j * BKV, 2 * p.H + h, b);
+      }
+    } else if (warp == 1) {
+      // ================================ MMA issuer ==========================================
+      const uint32_t idesc_pv = tc::make_idesc_bf16(BQ, HD, 0, 1);
+      tc::mbar_wait(q_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        const int n = (j < p.n_full) ? BKV : p.tail_n;
+        tc::mbar_wait(k_full(s), ph);
+        tc::fence_after_sync();
+        if (lane == 0) {
+          const uint32_t idesc_s = tc::make_idesc_bf16(BQ, n, 0, 0);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            tc::mma_f16_ss(tmem + S_COL, tc::make_desc(sQ + k * 32, 16, 1024),
+                           tc::make_desc(sK + s * TILE_BYTES + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          tc::mma_commit(k_empty(s));
+          tc::mma_commit(s_full);
+        }
+        __syncwarp();
+        tc::mbar_wait(p_full, (uint32_t)j & 1u);
+        tc::mbar_wait(v_full(s), ph);
+        tc::fence_after_sync();
+        if (lane == 0) {
+          for (int k = 0; k < n / 16; ++k)
+            tc::mma_f16_ts(tmem + O_COL, tmem + S_COL + k * 8,
+                           tc::make_desc(sV + s * TILE_BYTES + k * 2048, 16384, 1024), idesc_pv,
+                           (j > 0 || k > 0) ? 1u : 0u);
+          tc::mma_commit(v_empty(s));
+          if (j == n_tiles - 1) tc::mma_commit(o_final);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================== softmax warps =======================================
+    tc::reg_inc<216>();
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int q = qt * BQ + row;
+    const bool q_ok = q < p.L;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    const int t128 = threadIdx.x - 128;
+    const bool has_bias = p.u0 != nullptr;
+    if (has_bias) {
+      const float* ub = p.u0 + (size_t)b * p.L;
+      for (int i = t128; i < n_tiles * BKV; i += 128) u0s[i] = (i < p.L) ? ub[i] : 0.f;
+      tc::named_bar_sync(1, 128);
+    }
+    const float c1 = p.scale * LOG2E;
+    float wgl = 0.f;
+    if (has_bias) wgl = p.w * LOG2E * ((p.gate && q_ok) ? p.gate[(size_t)b * p.L + q] : 1.f);
+    float m_ref = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const bool full = j < p.n_full;
+      const int n = full ? BKV : p.tail_n;
+      const int valid = full ? BKV : p.rem;
+      tc::mbar_wait(s_full, (uint32_t)j & 1u);
+      tc::fence_after_sync();
+      uint32_t r[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c * 32 < n) {
+          uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]);
+          tc::tmem_ld32(lane_base + S_COL + c * 32, chunk);
+        }
+      }
+      tc::tmem_ld_wait();
+      // ---- logits in the log2 domain + row max (8 independent chains) ----
+      const float* ut = u0s + j * BKV;
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+      if (full) {
+        if (has_bias) {
+#pragma unroll
+          for (int c4 = 0; c4 < 32; ++c4) {
+            const float4 u4 = *reinterpret_cast<const float4*>(ut + c4 * 4);
+            const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c4 * 4 + i;
+              const float t = fmaf(__uint_as_float(r[c]), c1, wgl * uu[i]);
+              r[c] = __float_as_uint(t);
+              mx[c & 7] = fmaxf(mx[c & 7], t);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) mx[c & 7] = fmaxf(mx[c & 7], __uint_as_float(r[c]));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 128; ++c) {
+          if (c < n) {
+            float t = __uint_as_float(r[c]) * c1;
+            if (has_bias) t = fmaf(wgl, ut[c], t);
+            if (c >= valid) t = -INFINITY;
+            r[c] = __float_as_uint(t);
+            mx[c & 7] = fmaxf(mx[c & 7], t);
+          }
+        }
+      }
+      float mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                       fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      const bool raw = full && !has_bias;        // r[] still holds unscaled q.k
+      if (raw) mt *= c1;
+      const float m_new = fmaxf(m_ref, mt);
+      const bool resc = m_new > m_ref + RESCALE_THRESHOLD;
+      float alpha = 1.f;
+      if (resc) {
+        alpha = tc::ex2(m_ref - m_new);   // 0 on the first tile (m_ref = -inf)
+        m_ref = m_new;
+        l_sum *= alpha;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, resc)) {
+        // s_full(j) was committed after PV(j-1): O is quiescent here
+        uint32_t o[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tc::tmem_ld32(lane_base + O_COL + c * 32, o);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tc::tmem_st32(lane_base + O_COL + c * 32, o);
+        }
+      }
+      // ---- P = 2^(t - m_ref) -> bf16 pairs over the S columns; 4 independent sum chains ----
+      const float mul = raw ? c1 : 1.f;
+      const float neg_m = -m_ref;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16) {
+        if (full || c16 * 16 < n) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float p0 = tc::ex2(fmaf(__uint_as_float(r[c16 * 16 + 2 * i]), mul, neg_m));
+            const float p1 = tc::ex2(fmaf(__uint_as_float(r[c16 * 16 + 2 * i + 1]), mul, neg_m));
+            ls[i & 3] += p0;
+            ls[(i + 2) & 3] += p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                       ::"r"(lane_base + S_COL + c16 * 8), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
+                         "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                       : "memory");
+        }
+      }
+      l_sum += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16, lse ----
+    tc::mbar_wait(o_final, 0);
+    tc::fence_after_sync();
+    const float inv_l = 1.f / l_sum;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                          ((size_t)b * p.L + (q_ok ? q : 0)) * (size_t)(p.H * HD) + h * HD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tc::tmem_ld32(lane_base + O_COL + c * 32, o);
+      tc::tmem_ld_wait();
+      if (q_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+          v.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+          v.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+          v.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = v;
+        }
+      }
+    }
+    if (q_ok) p.lse[((size_t)b * p.H + h) * p.L + q] = (m_ref + log2f(l_sum)) * LN2;
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+
+// =============================================================================================
+// BACKWARD.  One CTA per (batch, head, 128-key tile), 1 CTA / SM, 512 threads; the CTA walks the
+// query tiles.  Everything is computed TRANSPOSED (keys on the TMEM lanes) so that P^T and dS^T
+// are directly the TMEM A-operands of the dV / dK MMAs:
+//   S^T  = K_j Q_i^T        (128 keys x n queries, K = 64)      TMEM cols [0,128)
+//   dP^T = V_j dO_i^T                                          TMEM cols [128,256)
+//   P^T  = 2^(S^T c + bias - lse),  dS^T = P^T (dP^T - D)       (softmax warps; bf16 over S / dP)
+//   dV_j += P^T dO_i,  dK_j += dS^T Q_i   (A from TMEM)         TMEM cols [256,320), [320,384)
+//   dQ_i  = dS K_j     (A = dS^T staged in smem, MN-major)      TMEM cols [384,448)
+// dQ tiles are reduced over the key tiles with cp.reduce.async.bulk (fp32 add in L2) into a
+// [B,H,q_tiles,128,64] accumulator that a small kernel converts to bf16.
+// Warps: 0 TMA producer, 1 MMA issuer (one thread), 4-7 / 8-11 softmax for query half 0 / 1
+// (software-pipelined against each other by the issue order), 12-15 dQ epilogue.
+// =============================================================================================
+constexpr int BWD_THREADS = 512;
+constexpr int DP_COL = 128, DV_COL = 256, DK_COL = 320, DQ_COL = 384;
+
+struct BwdParams {
+  void* dqkv;            // [B, L, 3*H*64] bf16 (dK, dV written here; dQ by the convert kernel)
+  float* dq_accum;       // [B, H, q_tiles, 128, 64] fp32, zeroed
+  const float* lse;      // [B, H, L]
+  const float* delta;    // [B, H, L]  rowsum(dO * O)
+  const float* u0;
+  const float* gate;
+  float w, scale;
+  int B, H, L, q_tiles;
+};
+
+__device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ int bwd_half_n(int L, int i, int h) {
+  int qn = L - i * 128;
+  qn = qn > 128 ? 128 : ((qn + 15) & ~15);
+  if (h == 0) return qn < 64 ? qn : 64;
+  return qn > 64 ? qn - 64 : 16;    // at least a 16-wide (all masked) MMA keeps both halves in step
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = tc::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sK = base;
+  const uint32_t sV = base + TILE_BYTES;
+  const uint32_t sQ = base + 2 * TILE_BYTES;      // 2 stages
+  const uint32_t sdO = base + 4 * TILE_BYTES;     // 2 stages
+  const uint32_t sdS = base + 6 * TILE_BYTES;     // 32 KB: [2 query halves][128 keys][64 q] bf16
+  const uint32_t sdQ = base + 8 * TILE_BYTES;     // 32 KB fp32 staging
+  const uint32_t bar = base + 10 * TILE_BYTES;
+  const uint32_t kv_full = bar;
+  auto qd_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto qd_empty = [&](int s) { return bar + 8u * (3 + s); };
+  auto sdp_full = [&](int h) { return bar + 8u * (5 + h); };
+  auto pds_full = [&](int h) { return bar + 8u * (7 + h); };
+  const uint32_t dq_done = bar + 8u * 9;
+  const uint32_t dq_empty = bar + 8u * 10;
+  const uint32_t dvk_full = bar + 8u * 11;
+  const uint32_t tmem_slot = bar + 8u * 12;
+  uint8_t* gen = smem_raw + (base - raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 10 * TILE_BYTES + 8 * 12);
+  const int lpad = p.q_tiles * 128;
+  float* lse2s = reinterpret_cast<float*>(gen + 10 * TILE_BYTES + 128);
+  float* dlts = lse2s + lpad;
+  float* wgls = dlts + lpad;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv_tiles = p.q_tiles;
+  const int jt = blockIdx.x % kv_tiles;
+  const int bh = blockIdx.x / kv_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int nq = p.q_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tm_qkv);
+    tc::prefetch_tmap(&tm_do);
+    tc::mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(qd_full(s), 1);
+      tc::mbar_init(qd_empty(s), 1);
+      tc::mbar_init(sdp_full(s), 1);
+      tc::mbar_init(pds_full(s), 4);
+    }
+    tc::mbar_init(dq_done, 1);
+    tc::mbar_init(dq_empty, 4);
+    tc::mbar_init(dvk_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================ TMA producer ========================================
+      tc::mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+      tc::tma_load_4d(sK, &tm_qkv, kv_full, 0, jt * 128, p.H + h, b);
+      tc::tma_load_4d(sV, &tm_qkv, kv_full, 0, jt * 128, 2 * p.H + h, b);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i & 1;
+        tc::mbar_wait(qd_empty(st), (((uint32_t)i >> 1) & 1u) ^ 1u);
+        tc::mbar_expect_tx(qd_full(st), 2 * TILE_BYTES);
+        tc::tma_load_4d(sQ + st * TILE_BYTES, &tm_qkv, qd_full(st), 0, i * 128, h, b);
+        tc::tma_load_4d(sdO + st * TILE_BYTES, &tm_do, qd_full(st), 0, i * 128, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================================ MMA issuer (one thread) =============================
+      const uint32_t idesc_dvk = tc::make_idesc_bf16(128, HD, 0, 1);
+      const uint32_t idesc_dq = tc::make_idesc_bf16(128, HD, 1, 1);
+      uint32_t acc_dvk = 0;
+      auto issue_sdp = [&](int i, int hh) {
+        const int st = i & 1;
+        const uint32_t idesc = tc::make_idesc_bf16(128, bwd_half_n(p.L, i, hh), 0, 0);
+        const uint32_t q_rows = sQ + st * TILE_BYTES + hh * 8192;
+        const uint32_t do_rows = sdO + st * TILE_BYTES + hh * 8192;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc::mma_f16_ss(tmem + hh * 64, tc::make_desc(sK + k * 32, 16, 1024),
+                         tc::make_desc(q_rows + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc::mma_f16_ss(tmem + DP_COL + hh * 64, tc::make_desc(sV + k * 32, 16, 1024),
+                         tc::make_desc(do_rows + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+        tc::mma_commit(sdp_full(hh));
+      };
+      auto issue_dvk = [&](int i, int hh, uint32_t acc) {
+        const int st = i & 1;
+        const int steps = bwd_half_n(p.L, i, hh) >> 4;
+        const uint32_t q_rows = sQ + st * TILE_BYTES + hh * 8192;
+        const uint32_t do_rows = sdO + st * TILE_BYTES + hh * 8192;
+        for (int s = 0; s < steps; ++s)
+          tc::mma_f16_ts(tmem + DV_COL, tmem + hh * 64 + s * 8, tc::make_desc(do_rows + s * 2048, 16384, 1024),
+                         idesc_dvk, (acc | (uint32_t)s) ? 1u : 0u);
+        for (int s = 0; s < steps; ++s)
+          tc::mma_f16_ts(tmem + DK_COL, tmem + DP_COL + hh * 64 + s * 8,
+                         tc::make_desc(q_rows + s * 2048, 16384, 1024), idesc_dvk, (acc | (uint32_t)s) ? 1u : 0u);
+      };
+      tc::mbar_wait(kv_full, 0);
+      tc::mbar_wait(qd_full(0), 0);
+      tc::fence_after_sync();
+      issue_sdp(0, 0);
+      issue_sdp(0, 1);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i & 1;
+        const uint32_t ph = (uint32_t)i & 1u;
+        tc::mbar_wait(pds_full(0), ph);
+        tc::fence_after_sync();
+        issue_dvk(i, 0, acc_dvk);
+        if (i + 1 < nq) {
+          tc::mbar_wait(qd_full(st ^ 1), ((uint32_t)(i + 1) >> 1) & 1u);
+          tc::fence_after_sync();
+          issue_sdp(i + 1, 0);
+        }
+        tc::mbar_wait(pds_full(1), ph);
+        tc::fence_after_sync();
+        issue_dvk(i, 1, 1u);
+        acc_dvk = 1;
+        tc::mma_commit(qd_empty(st));
+        tc::mbar_wait(dq_empty, ph ^ 1u);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          tc::mma_f16_ss(tmem + DQ_COL, tc::make_desc(sdS + s * 2048, 16384, 1024),
+                         tc::make_desc(sK + s * 2048, 16384, 1024), idesc_dq, s > 0 ? 1u : 0u);
+        tc::mma_commit(dq_done);
+        if (i + 1 < nq) issue_sdp(i + 1, 1);
+      }
+      tc::mma_commit(dvk_full);
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ================================== softmax warps =======================================
+    const int hh = (warp - 4) >> 2;             // query half handled by this warpgroup
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;           // key row (TMEM lane)
+    const int key = jt * 128 + row;
+    const bool key_ok = key < p.L;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    {
+      const int t256 = threadIdx.x - 128;
+      const float* lse_b = p.lse + ((size_t)b * p.H + h) * p.L;
+      const float* dl_b = p.delta + ((size_t)b * p.H + h) * p.L;
+      for (int i = t256; i < lpad; i += 256) {
+        const bool ok = i < p.L;
+        lse2s[i] = ok ? lse_b[i] * LOG2E : INFINITY;
+        dlts[i] = ok ? dl_b[i] : 0.f;
+        float g = 0.f;
+        if (p.u0 && ok) g = p.w * LOG2E * (p.gate ? p.gate[(size_t)b * p.L + i] : 1.f);
+        wgls[i] = g;
+      }
+      tc::named_bar_sync(1, 256);
+    }
+    const float u0k = (p.u0 && key_ok) ? p.u0[(size_t)b * p.L + key] : 0.f;
+    const float c1 = p.scale * LOG2E;
+    const uint32_t ds_row = sdS + hh * 16384 + row * 128;
+    const uint32_t swz = (uint32_t)(row & 7);
+    for (int i = 0; i < nq; ++i) {
+      const int n = bwd_half_n(p.L, i, hh);
+      tc::mbar_wait(sdp_full(hh), (uint32_t)i & 1u);
+      tc::fence_after_sync();
+      const int qbase = i * 128 + hh * 64;
+      for (int c16 = 0; c16 < (n >> 4); ++c16) {
+        uint32_t sv[16], dv[16];
+        tc::tmem_ld16(lane_base + hh * 64 + c16 * 16, sv);
+        tc::tmem_ld16(lane_base + DP_COL + hh * 64 + c16 * 16, dv);
+        float ls[16], dd[16], wg[16];
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const float4 a4 = *reinterpret_cast<const float4*>(lse2s + qbase + c16 * 16 + v4 * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(dlts + qbase + c16 * 16 + v4 * 4);
+          const float4 c4 = *reinterpret_cast<const float4*>(wgls + qbase + c16 * 16 + v4 * 4);
+          ls[v4 * 4] = a4.x; ls[v4 * 4 + 1] = a4.y; ls[v4 * 4 + 2] = a4.z; ls[v4 * 4 + 3] = a4.w;
+          dd[v4 * 4] = b4.x; dd[v4 * 4 + 1] = b4.y; dd[v4 * 4 + 2] = b4.z; dd[v4 * 4 + 3] = b4.w;
+          wg[v4 * 4] = c4.x; wg[v4 * 4 + 1] = c4.y; wg[v4 * 4 + 2] = c4.z; wg[v4 * 4 + 3] = c4.w;
+        }
+        tc::tmem_ld_wait();
+        uint32_t pp[8], dsp[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float pv[2], dsv[2];
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            const int c = 2 * e + x;
+            const float t = fmaf(__uint_as_float(sv[c]), c1, fmaf(wg[c], u0k, -ls[c]));
+            const float pe = key_ok ? tc::ex2(t) : 0.f;
+            pv[x] = pe;
+            dsv[x] = pe * (__uint_as_float(dv[c]) - dd[c]);
+          }
+          pp[e] = pack_bf16(pv[0], pv[1]);
+          dsp[e] = pack_bf16(dsv[0], dsv[1]);
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"r"(lane_base + hh * 64 + c16 * 8), "r"(pp[0]), "r"(pp[1]), "r"(pp[2]), "r"(pp[3]),
+                       "r"(pp[4]), "r"(pp[5]), "r"(pp[6]), "r"(pp[7]) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"r"(lane_base + DP_COL + hh * 64 + c16 * 8), "r"(dsp[0]), "r"(dsp[1]), "r"(dsp[2]),
+                       "r"(dsp[3]), "r"(dsp[4]), "r"(dsp[5]), "r"(dsp[6]), "r"(dsp[7]) : "memory");
+        if (c16 == 0 && i > 0) {   // the dQ MMA of the previous tile must have consumed sdS
+          tc::mbar_wait(dq_done, (uint32_t)(i - 1) & 1u);
+        }
+        // dS^T row (this key) for queries [c16*16, +16): two 16-byte chunks of the swizzled row
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + ((((uint32_t)(2 * c16)) ^ swz) << 4)),
+                     "r"(dsp[0]), "r"(dsp[1]), "r"(dsp[2]), "r"(dsp[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + ((((uint32_t)(2 * c16 + 1)) ^ swz) << 4)),
+                     "r"(dsp[4]), "r"(dsp[5]), "r"(dsp[6]), "r"(dsp[7]) : "memory");
+      }
+      tc::tmem_st_wait();
+      tc::fence_proxy_async();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(pds_full(hh));
+    }
+    // ---- final: dV (warpgroup 0) / dK (warpgroup 1) -> bf16 rows of dqkv ----
+    tc::mbar_wait(dvk_full, 0);
+    tc::fence_after_sync();
+    const int D3 = 3 * p.H * HD;
+    const float osc = hh == 0 ? 1.f : p.scale;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.dqkv) + ((size_t)b * p.L + (key_ok ? key : 0)) * D3 +
+                          (hh == 0 ? 2 * p.H + h : p.H + h) * HD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tc::tmem_ld32(lane_base + (hh == 0 ? DV_COL : DK_COL) + c * 32, o);
+      tc::tmem_ld_wait();
+      if (key_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * osc, __uint_as_float(o[8 * i + 1]) * osc);
+          v.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * osc, __uint_as_float(o[8 * i + 3]) * osc);
+          v.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * osc, __uint_as_float(o[8 * i + 5]) * osc);
+          v.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * osc, __uint_as_float(o[8 * i + 7]) * osc);
+          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = v;
+        }
+      }
+    }
+  } else if (warp >= 12) {
+    // ================================== dQ epilogue =========================================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;           // query row of the tile
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t srow = sdQ + row * 256;
+    const uint32_t swz = (uint32_t)(row & 15);
+    float* acc_base = p.dq_accum + ((size_t)(b * p.H + h) * p.q_tiles) * (128 * 64);
+    for (int i = 0; i < nq; ++i) {
+      tc::mbar_wait(dq_done, (uint32_t)i & 1u);
+      tc::fence_after_sync();
+      uint32_t o0[32], o1[32];
+      tc::tmem_ld32(lane_base + DQ_COL, o0);
+      tc::tmem_ld32(lane_base + DQ_COL + 32, o1);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(dq_empty);
+      // the previous tile's bulk reduce must have finished reading the staging buffer
+      if (threadIdx.x == 12 * 32) tc::bulk_wait_read<0>();
+      tc::named_bar_sync(2, 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((((uint32_t)c) ^ swz) << 4)),
+                     "r"(o0[4 * c]), "r"(o0[4 * c + 1]), "r"(o0[4 * c + 2]), "r"(o0[4 * c + 3]) : "memory");
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((((uint32_t)(c + 8)) ^ swz) << 4)),
+                     "r"(o1[4 * c]), "r"(o1[4 * c + 1]), "r"(o1[4 * c + 2]), "r"(o1[4 * c + 3]) : "memory");
+      tc::fence_proxy_async();
+      tc::named_bar_sync(2, 128);
+      if (threadIdx.x == 12 * 32) {
+        bulk_reduce_add_f32(acc_base + (size_t)i * (128 * 64), sdQ, 128 * 64 * 4);
+        tc::bulk_commit();
+      }
+    }
+    if (threadIdx.x == 12 * 32) tc::bulk_wait<0>();
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem, 512);
+  }
+}
+
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
+__global__ void __launch_bounds__(256)
+attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                      float* __restrict__ delta, int B, int H, int L) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, q, h)
+  const long long total = (long long)B * L * H;
+  if (idx >= total) return;
+  const int hh = (int)(idx % H);
+  const long long bq = idx / H;
+  const int q = (int)(bq % L);
+  const int b = (int)(bq / L);
+  const uint4* a = reinterpret_cast<const uint4*>(dout + (size_t)bq * H * HD + hh * HD);
+  const uint4* o = reinterpret_cast<const uint4*>(out + (size_t)bq * H * HD + hh * HD);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 x = a[i], y = o[i];
+    const __nv_bfloat162* xs = reinterpret_cast<const __nv_bfloat162*>(&x);
+    const __nv_bfloat162* ys = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fx = __bfloat1622float2(xs[k]), fy = __bfloat1622float2(ys[k]);
+      acc = fmaf(fx.x, fy.x, acc);
+      acc = fmaf(fx.y, fy.y, acc);
+    }
+  }
+  delta[((size_t)b * H + hh) * L + q] = acc;
+}
+
+// dq_accum [B,H,q_tiles,128,64] fp32 (16-byte chunks XOR-swizzled by row) -> dqkv[:, :, h*64 + d] * scale
+__global__ void __launch_bounds__(256)
+attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, int B, int H,
+                           int L, int q_tiles, float scale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, q, h, 8-column group)
+  const long long total = (long long)B * L * H * 8;
+  if (idx >= total) return;
+  const int g8 = (int)(idx & 7);
+  const int hh = (int)((idx >> 3) % H);
+  const long long bq = (idx >> 3) / H;
+  const int q = (int)(bq % L);
+  const int b = (int)(bq / L);
+  const int r = q & 127;
+  const float* rowp = acc + (((size_t)(b * H + hh) * q_tiles + (q >> 7)) * 128 + r) * 64;
+  const float4 lo = *reinterpret_cast<const float4*>(rowp + (((2 * g8) ^ (r & 15)) << 2));
+  const float4 hi = *reinterpret_cast<const float4*>(rowp + (((2 * g8 + 1) ^ (r & 15)) << 2));
+  uint4 v;
+  v.x = pack_bf16(lo.x * scale, lo.y * scale);
+  v.y = pack_bf16(lo.z * scale, lo.w * scale);
+  v.z = pack_bf16(hi.x * scale, hi.y * scale);
+  v.w = pack_bf16(hi.z * scale, hi.w * scale);
+  *reinterpret_cast<uint4*>(dqkv + (size_t)bq * 3 * H * HD + hh * HD + g8 * 8) = v;
+}
+
+int env_composed() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("S4_ATTN_COMPOSED");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
+}  // namespace
+
+bool s4_attention_tc_fwd_supported(int B, int H, int L, int hd, int dtype) {
+  if (env_composed()) return false;
+  return dtype == S4_BF16 && hd == HD && L >= 1 && B >= 1 && H >= 1 && (long long)B * H * ((L + BQ - 1) / BQ) < (1ll << 31);
+}
+
+bool s4_attention_tc_bwd_supported(int B, int H, int L, int hd, int dtype) {
+  return s4_attention_tc_fwd_supported(B, H, L, hd, dtype);
+}
+
+// workspace of the fused backward: delta [B,H,L] + dq_accum [B,H,q_tiles,128,64], fp32
+size_t s4_attention_tc_bwd_workspace(int B, int H, int L) {
+  const size_t qt = (size_t)(L + 127) / 128;
+  return ((size_t)B * H * L * 4 + 255) / 256 * 256 + (size_t)B * H * qt * 128 * 64 * 4;
+}
 
 int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, float w, void* out,
                         float* lse, int B, int H, int L, int hd, cudaStream_t st) {
-  s4_set_error("attention_tc_fwd: not available");
-  return S4_ERR_UNSUPPORTED;
+  if ((((uintptr_t)qkv) & 15) || (((uintptr_t)out) & 15)) {
+    s4_set_error("attention_tc_fwd: qkv/out must be 16-byte aligned");
+    return S4_ERR_ARG;
+  }
+  const int D = H * HD;
+  CUtensorMap tm;
+  const uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)(3 * H), (uint64_t)B};
+  const uint64_t str[3] = {(uint64_t)(3 * D), (uint64_t)HD, (uint64_t)L * 3 * D};
+  const uint32_t box[4] = {64, 128, 1, 1};
+  int rc = s4_make_tmap_bf16(&tm, qkv, dims, str, box);
+  if (rc) return rc;
+  FwdParams p{};
+  p.out = out; p.lse = lse; p.u0 = u0; p.gate = gate; p.w = w;
+  p.scale = 1.0f / sqrtf((float)hd);
+  p.B = B; p.H = H; p.L = L;
+  p.q_tiles = (L + BQ - 1) / BQ;
+  p.n_full = L / BKV;
+  p.rem = L % BKV;
+  p.tail_n = (p.rem + 15) & ~15;
+  const int n_tiles = p.n_full + (p.tail_n ? 1 : 0);
+  const size_t smem = 1024 + 5 * TILE_BYTES + 128 + (size_t)n_tiles * BKV * 4;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      s4_set_error("attention_tc_fwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return S4_ERR_CUDA;
+    }
+    smem_set = smem;
+  }
+  const double flops = 4.0 * B * H * (double)L * L * HD;
+  S4ProfScope prof("attn_fwd_tc", flops, 0, st);
+  attn_fwd_kernel<<<B * H * p.q_tiles, FWD_THREADS, smem, st>>>(tm, p);
+  return s4_check_launch("attn_fwd_tc");
 }
 
 int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, const float* lse,
                         const float* u0, const float* gate, float w, void* dqkv, void* ws,
                         size_t ws_bytes, int B, int H, int L, int hd, cudaStream_t st) {
-  s4_set_error("attention_tc_bwd: not available");
-  return S4_ERR_UNSUPPORTED;
+  if ((((uintptr_t)qkv) & 15) || (((uintptr_t)dout) & 15) || (((uintptr_t)out) & 15) || (((uintptr_t)dqkv) & 15) ||
+      (((uintptr_t)ws) & 255)) {
+    s4_set_error("attention_tc_bwd: pointers must be 16-byte (workspace 256-byte) aligned");
+    return S4_ERR_ARG;
+  }
+  if (ws_bytes < s4_attention_tc_bwd_workspace(B, H, L)) {
+    s4_set_error("attention_tc_bwd: workspace too small");
+    return S4_ERR_ARG;
+  }
+  const int D = H * HD;
+  const int q_tiles = (L + 127) / 128;
+  float* delta = (float*)ws;
+  const size_t delta_bytes = ((size_t)B * H * L * 4 + 255) / 256 * 256;
+  float* dq_accum = (float*)((char*)ws + delta_bytes);
+  const size_t acc_bytes = (size_t)B * H * q_tiles * 128 * 64 * 4;
+  CUtensorMap tq, tdo;
+  int rc;
+  {
+    const uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)(3 * H), (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)(3 * D), (uint64_t)HD, (uint64_t)L * 3 * D};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if ((rc = s4_make_tmap_bf16(&tq, qkv, dims, str, box))) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)D, (uint64_t)HD, (uint64_t)L * D};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if ((rc = s4_make_tmap_bf16(&tdo, dout, dims, str, box))) return rc;
+  }
+  BwdParams p{};
+  p.dqkv = dqkv; p.dq_accum = dq_accum; p.lse = lse; p.delta = delta; p.u0 = u0; p.gate = gate;
+  p.w = w; p.scale = 1.0f / sqrtf((float)hd);
+  p.B = B; p.H = H; p.L = L; p.q_tiles = q_tiles;
+  const size_t smem = 1024 + 10 * TILE_BYTES + 128 + (size_t)3 * q_tiles * 128 * 4;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      s4_set_error("attention_tc_bwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return S4_ERR_CUDA;
+    }
+    smem_set = smem;
+  }
+  S4ProfScope prof("attn_bwd_tc", 8.0 * B * H * (double)L * L * HD, 0, st);
+  cudaError_t e = cudaMemsetAsync(dq_accum, 0, acc_bytes, st);
+  if (e != cudaSuccess) {
+    s4_set_error("attention_tc_bwd: memset failed: %s", cudaGetErrorString(e));
+    return S4_ERR_CUDA;
+  }
+  {
+    const long long total = (long long)B * L * H;
+    attn_bwd_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, delta, B, H, L);
+    if ((rc = s4_check_launch("attn_bwd_delta"))) return rc;
+  }
+  attn_bwd_kernel<<<B * H * q_tiles, BWD_THREADS, smem, st>>>(tq, tdo, p);
+  if ((rc = s4_check_launch("attn_bwd_tc"))) return rc;
+  {
+    const long long total = (long long)B * L * H * 8;
+    attn_bwd_dq_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        dq_accum, (__nv_bfloat16*)dqkv, B, H, L, q_tiles, p.scale);
+    rc = s4_check_launch("attn_bwd_dq_convert");
+  }
+  return rc;
 }

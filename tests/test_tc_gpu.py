@@ -121,3 +121,89 @@ def test_tc_conv3x3_wgrad(B, H, W, Cin, Cout):
     dw = torch.zeros(Cout, Cin, 3, 3, device=DEV)
     L.call('s4_conv3x3_wgrad', x.data_ptr(), dy.data_ptr(), dw.data_ptr(), B, H, W, Cin, Cout, L.BF16, L.BACKEND_TC, st)
     assert rel(dw, wr.grad) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------ fused attention
+def _attn_ref(qkv, B, Lt, H, hd, u0, gate, w, dout=None):
+    """fp32 math on the same bf16 inputs: softmax(q k^T / sqrt(d) + w*gate[q]*u0[k]) v (vit.py:519-535)."""
+    import math
+    D = H * hd
+    qr = qkv.float().cpu().requires_grad_(True)
+    q, k, v = qr.view(B, Lt, 3 * D).split(D, dim=-1)
+    q = q.view(B, Lt, H, hd).transpose(1, 2) / math.sqrt(hd)
+    k = k.view(B, Lt, H, hd).transpose(1, 2)
+    v = v.view(B, Lt, H, hd).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    if u0 is not None:
+        gq = gate.cpu() if gate is not None else torch.ones_like(u0.cpu())
+        s = s + (w * gq.unsqueeze(-1) * u0.cpu().unsqueeze(1)).unsqueeze(1)
+    lse = torch.logsumexp(s, -1)
+    o = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * Lt, D)
+    grad = None
+    if dout is not None:
+        o.backward(dout.float().cpu())
+        grad = qr.grad
+    return o.detach(), lse.detach(), grad
+
+
+@pytest.mark.parametrize('B,H,Lt', [(2, 2, 65), (1, 3, 128), (2, 2, 257), (1, 12, 1025), (1, 2, 2305)])
+@pytest.mark.parametrize('pasa', [False, True])
+def test_tc_attention_fwd(B, H, Lt, pasa):
+    g = gen(11)
+    hd = 64
+    D = H * hd
+    qkv = (torch.randn(B * Lt, 3 * D, generator=g) * 0.7).to(DEV, BF)
+    u0 = gate = None
+    w = 0.0
+    if pasa:
+        u = (torch.rand(B, Lt - 1, generator=g) * 16).round() / 16
+        u0 = torch.cat([torch.zeros(B, 1), u], 1)
+        gate = (torch.rand(B, Lt, generator=g) > 0.5).float()
+        gate[:, 0] = 1.0
+        u0, gate, w = u0.to(DEV), gate.to(DEV), 5.0
+    assert ops.backend() == L.BACKEND_AUTO
+    out, lse = ops.attention_fwd(qkv, B, Lt, H, hd, u0, gate, w)
+    o_ref, lse_ref, _ = _attn_ref(qkv, B, Lt, H, hd, u0, gate, w)
+    assert rel(out.float(), o_ref) < 2e-2
+    assert torch.allclose(lse.cpu(), lse_ref, rtol=1e-3, atol=2e-3)
+
+
+def test_tc_attention_large_logits_lazy_rescale():
+    """Rows whose running max grows across key tiles by far more than the lazy-rescale threshold."""
+    g = gen(12)
+    B, H, Lt, hd = 1, 2, 513, 64
+    D = H * hd
+    qkv = torch.randn(B * Lt, 3 * D, generator=g)
+    ramp = torch.linspace(0.2, 6.0, Lt).view(Lt, 1)
+    qkv[:, D:2 * D] *= ramp                      # later keys produce ever larger logits
+    qkv = qkv.to(DEV, BF)
+    out, lse = ops.attention_fwd(qkv, B, Lt, H, hd, None, None, 0.0)
+    o_ref, lse_ref, _ = _attn_ref(qkv, B, Lt, H, hd, None, None, 0.0)
+    assert rel(out.float(), o_ref) < 2e-2
+    assert torch.allclose(lse.cpu(), lse_ref, rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize('B,H,Lt', [(2, 2, 65), (1, 3, 128), (2, 2, 257), (1, 4, 1025), (1, 1, 2305)])
+@pytest.mark.parametrize('pasa', [False, True])
+def test_tc_attention_bwd(B, H, Lt, pasa):
+    g = gen(13)
+    hd = 64
+    D = H * hd
+    qkv = (torch.randn(B * Lt, 3 * D, generator=g) * 0.7).to(DEV, BF)
+    dout = torch.randn(B * Lt, D, generator=g).to(DEV, BF)
+    u0 = gate = None
+    w = 0.0
+    if pasa:
+        u = (torch.rand(B, Lt - 1, generator=g) * 16).round() / 16
+        u0 = torch.cat([torch.zeros(B, 1), u], 1)
+        gate = (torch.rand(B, Lt, generator=g) > 0.5).float()
+        gate[:, 0] = 1.0
+        u0, gate, w = u0.to(DEV), gate.to(DEV), 5.0
+    out, lse = ops.attention_fwd(qkv, B, Lt, H, hd, u0, gate, w)
+    dqkv = ops.attention_bwd(dout, qkv, out, lse, B, Lt, H, hd, u0, gate, w)
+    _, _, g_ref = _attn_ref(qkv, B, Lt, H, hd, u0, gate, w, dout)
+    gq, gk, gv = dqkv.float().cpu().view(B * Lt, 3, D).unbind(1)
+    rq, rk, rv = g_ref.view(B * Lt, 3, D).unbind(1)
+    assert rel(gv, rv) < 2e-2, ('dV', rel(gv, rv))
+    assert rel(gk, rk) < 3e-2, ('dK', rel(gk, rk))
+    assert rel(gq, rq) < 3e-2, ('dQ', rel(gq, rq))
