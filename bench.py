@@ -352,7 +352,7 @@ def main():
                         d2h_bytes_per_step=4 * len(last)),
                gpu_launches=int(launches) * a.steps, gpu_launches_per_step=int(launches),
                clocks=clk, roofline=roofline,
-               kernels=sorted(kinds, key=lambda k: -k['ms_per_step'])[:12])
+               kernels=sorted(kinds, key=lambda k: -k["ms_per_step"])[:40])
     if world == 1 and not a.no_cpu_baseline:
         s_sup, s_unsup = 1, (1 if n_unsup else 0)
         csec, n, threads = cpu_reference_steps(a, s_sup, s_unsup, 1, 0, 40.0)

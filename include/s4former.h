@@ -193,6 +193,23 @@ int s4_upsample_logits_fwd(const float* z, float* logits, int B, int H, int W, i
 int s4_upsample_logits_bwd(const float* dlogits, float* dz, int B, int H, int W, int NC, int s,
                            cudaStream_t stream);
 
+/* bf16 fast path of the last stage's backward (C in {64,128,256,512}, NC <= 24; s4_cls_supported):
+ *   dz16 [B*H*W, 32] bf16 (classes >= NC zero) = bilinear_s^T(dlogits)
+ *   reduce: dw[NC,C] +=, dbias[NC] +=, dsum[C] += sum da, ddot[C] += sum da*xhat,
+ *           da = relu'(x*scale+shift) * (dz w)         (x is read once, nothing is written back)
+ *   apply : dy = gamma*invstd*(da - dsum/count - xhat*ddot/count), da recomputed on the fly
+ * (the SyncBN all-reduce of dsum/ddot happens between the two calls) */
+int s4_cls_supported(int C, int NC, int dtype);
+int s4_cls_upsample_bwd_padded(const float* dlogits, void* dz16, int B, int H, int W, int NC, int s,
+                               cudaStream_t stream);
+int s4_cls_bwd_reduce(const void* dz16, const void* x, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, const float* w, float* dw, float* dbias,
+                      float* dsum, float* ddot, long long rows, int C, int NC, cudaStream_t stream);
+int s4_cls_bwd_apply(const void* dz16, const void* x, const float* scale, const float* shift,
+                     const float* mean, const float* invstd, const float* gamma, const float* w,
+                     const float* dsum, const float* ddot, double count, void* dy, long long rows,
+                     int C, int NC, cudaStream_t stream);
+
 /* ---- pseudo labels and losses ------------------------------------------------------------------
  * s4_pseudo_label replaces encoder_decoder.py:888-901 (+ :541-542) and the patch unconfidence
  * of :547-555: hard = argmax or 255, conf = (max softmax > thr), u = mean_{patch}(1-conf).

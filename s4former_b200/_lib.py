@@ -69,6 +69,10 @@ _SPEC = {
     's4_bn_relu_conv1x1_bwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
     's4_upsample_logits_fwd': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     's4_upsample_logits_bwd': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    's4_cls_supported': (_I, [_I, _I, _I]),
+    's4_cls_upsample_bwd_padded': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    's4_cls_bwd_reduce': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
+    's4_cls_bwd_apply': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _P, _L, _I, _I, _P]),
     's4_pseudo_label': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     's4_ce_ncr_workspace': (_Z, [_I, _I, _I]),
     's4_ce_ncr': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P, _Z, _P]),

@@ -12,6 +12,20 @@
 //  * CUDA-core 3x3 convolutions here are the fp32 validation path; gemm_tc.cu holds the
 //    tcgen05 implicit-GEMM version.
 #include "common.cuh"
+
+// head_cls.cu: bf16 tensor-core kernels of the last stage
+bool s4_cls_tc_supported(int C, int NC, int dtype);
+int s4_cls_fwd_tc(const void* y, const float* scale, const float* shift, const float* w, const float* bias,
+                  float* z, long long rows, int C, int NC, cudaStream_t st);
+int s4_cls_bwd_reduce_tc(const void* dz16, const void* y, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, const float* w, float* dw, float* dbias,
+                         float* dsum, float* ddot, long long rows, int C, int NC, cudaStream_t st);
+int s4_cls_bwd_apply_tc(const void* dz16, const void* y, const float* scale, const float* shift,
+                        const float* mean, const float* invstd, const float* gamma, const float* w,
+                        const float* dsum, const float* ddot, double count, void* dy, long long rows,
+                        int C, int NC, cudaStream_t st);
+int s4_cls_upsample_fwd(const float* z, float* logits, int B, int H, int W, int NC, int s, cudaStream_t st);
+int s4_cls_upsample_bwd(const float* dlogits, void* dz16, int B, int H, int W, int NC, int s, cudaStream_t st);
 #include "gemm_params.h"
 
 // ------------------------------------------------------------------------------------------
@@ -568,6 +582,7 @@ extern "C" int s4_bn_relu_conv1x1_fwd(const void* x, const float* scale, const f
   S4ProfScope prof_("bn_relu_conv1x1_fwd", 0.0, 1, stream);
   S4_REQUIRE(NC >= 1 && NC <= MAXNC, "conv1x1: NC=%d not in [1,%d]", NC, MAXNC);
   if (rows == 0) return S4_OK;
+  if (s4_cls_tc_supported(C, NC, dtype)) return s4_cls_fwd_tc(x, scale, shift, w, bias, z, rows, C, NC, stream);
   const size_t smem = ((size_t)NC * C + 2 * C) * sizeof(float);
   S4_REQUIRE(smem <= 200 * 1024, "conv1x1: C*NC too large for shared memory");
   const int grid = (int)min(((size_t)rows + 7) / 8, (size_t)s4_num_sms() * 8);
@@ -715,6 +730,7 @@ extern "C" int s4_upsample_logits_fwd(const float* z, float* logits, int B, int 
   S4ProfScope prof_("upsample_logits_fwd", 0.0, 1, stream);
   const size_t total = (size_t)B * NC * H * s * W * s;
   if (total == 0) return S4_OK;
+  if ((size_t)2 * W * NC * 4 <= 160 * 1024) return s4_cls_upsample_fwd(z, logits, B, H, W, NC, s, stream);
   const int grid = (int)min((total + 255) / 256, (size_t)s4_num_sms() * 32);
   upsample_logits_fwd_kernel<<<grid, 256, 0, stream>>>(z, logits, B, H, W, NC, s);
   return s4_check_launch("upsample_logits_fwd");
@@ -728,4 +744,36 @@ extern "C" int s4_upsample_logits_bwd(const float* dlogits, float* dz, int B, in
   const int grid = (int)min((total + 255) / 256, (size_t)s4_num_sms() * 32);
   upsample_logits_bwd_kernel<<<grid, 256, 0, stream>>>(dlogits, dz, B, H, W, NC, s);
   return s4_check_launch("upsample_logits_bwd");
+}
+
+// ---- bf16 tensor-core backward of the last stage (head_cls.cu) ---------------------------------
+extern "C" int s4_cls_supported(int C, int NC, int dtype) { return s4_cls_tc_supported(C, NC, dtype) ? 1 : 0; }
+
+extern "C" int s4_cls_upsample_bwd_padded(const float* dlogits, void* dz16, int B, int H, int W, int NC,
+                                          int s, cudaStream_t stream) {
+  S4ProfScope prof_("cls_upsample_bwd", 0.0, 1, stream);
+  S4_REQUIRE(NC >= 1 && NC <= 32, "cls_upsample_bwd: NC=%d not in [1,32]", NC);
+  S4_REQUIRE((size_t)NC * W * s * 4 <= 200 * 1024, "cls_upsample_bwd: row too wide for shared memory");
+  if ((size_t)B * H * W == 0) return S4_OK;
+  return s4_cls_upsample_bwd(dlogits, dz16, B, H, W, NC, s, stream);
+}
+
+extern "C" int s4_cls_bwd_reduce(const void* dz16, const void* y, const float* scale, const float* shift,
+                                 const float* mean, const float* invstd, const float* w, float* dw,
+                                 float* dbias, float* dsum, float* ddot, long long rows, int C, int NC,
+                                 cudaStream_t stream) {
+  S4ProfScope prof_("cls_bwd_reduce", 0.0, 1, stream);
+  S4_REQUIRE(s4_cls_tc_supported(C, NC, S4_BF16), "cls_bwd_reduce: unsupported C=%d NC=%d", C, NC);
+  if (rows == 0) return S4_OK;
+  return s4_cls_bwd_reduce_tc(dz16, y, scale, shift, mean, invstd, w, dw, dbias, dsum, ddot, rows, C, NC, stream);
+}
+
+extern "C" int s4_cls_bwd_apply(const void* dz16, const void* y, const float* scale, const float* shift,
+                                const float* mean, const float* invstd, const float* gamma, const float* w,
+                                const float* dsum, const float* ddot, double count, void* dy,
+                                long long rows, int C, int NC, cudaStream_t stream) {
+  S4ProfScope prof_("cls_bwd_apply", 0.0, 1, stream);
+  S4_REQUIRE(s4_cls_tc_supported(C, NC, S4_BF16), "cls_bwd_apply: unsupported C=%d NC=%d", C, NC);
+  if (rows == 0) return S4_OK;
+  return s4_cls_bwd_apply_tc(dz16, y, scale, shift, mean, invstd, gamma, w, dsum, ddot, count, dy, rows, C, NC, stream);
 }

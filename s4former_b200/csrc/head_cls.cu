@@ -1,0 +1,597 @@
+// Last SETR-PUP stage, bf16 path: BatchNorm + ReLU + 1x1 `conv_seg` (decode_head.py:107,311-316
+// commuted in front of the final bilinear upsample) and its backward.
+//
+// These contractions are tiny in FLOPs (C x NC per pixel, NC = 19/21 classes) and bound by the
+// HBM traffic of the [pixels, C] conv output, so they are fused around that traffic instead of
+// being shaped into big tensor-core GEMMs: every kernel streams the conv output ONCE, applies
+// BN(+ReLU) in registers and runs the small contraction with warp-level bf16 MMAs
+// (mma.sync m16n8k16, fp32 accumulate).
+//
+//   cls_fwd          z[p, j]   = bias[j] + sum_c w[j,c] relu(y[p,c] scale[c] + shift[c])
+//   cls_bwd_reduce   dw[j,c]  += sum_p dz[p,j] act[p,c];  dbias[j] += sum_p dz[p,j]
+//                    dsum[c]  += sum_p da[p,c];           ddot[c]  += sum_p da[p,c] xhat[p,c]
+//                    with da = relu'(.) (dz w)  -- the two sums BatchNorm's backward needs
+//   cls_bwd_apply    dy[p,c]   = gamma invstd (da - dsum/n - xhat ddot/n)   (da recomputed)
+// plus the logits upsample pair (NHWC z <-> NCHW fp32 logits) with smem-staged rows.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool ok) {
+  const int sz = ok ? 16 : 0;   // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// forward: one warp per 16 pixel rows, all C channels.  The contraction index is permuted so
+// that each lane's A fragments are 8 CONSECUTIVE channels of its two rows (16-byte loads, four
+// lanes = 64 contiguous bytes per row): channel(step s, mma m, slot) = 32 s + 8 t + 4 m + slot.
+// ---------------------------------------------------------------------------------------------
+template <int STEPS, int NT>   // C = 32 * STEPS, NC <= 8 * NT
+__global__ void __launch_bounds__(256)
+cls_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+               const float* __restrict__ shift, const float* __restrict__ w,
+               const float* __restrict__ bias, float* __restrict__ z, long long rows, int NC) {
+  constexpr int C = 32 * STEPS;
+  extern __shared__ __align__(16) uint8_t smem[];
+  float2* ss = reinterpret_cast<float2*>(smem);                       // [C] (scale, shift)
+  uint4* bfr = reinterpret_cast<uint4*>(smem + C * sizeof(float2));   // [STEPS][NT][32]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) ss[i] = make_float2(scale[i], shift[i]);
+  for (int i = threadIdx.x; i < STEPS * NT * 32; i += blockDim.x) {
+    const int ln = i & 31, nt = (i >> 5) % NT, s = (i >> 5) / NT;
+    const int n = nt * 8 + (ln >> 2), ch = 32 * s + 8 * (ln & 3);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = n < NC ? w[(size_t)n * C + ch + e] : 0.f;
+    bfr[i] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long nblk = (rows + 15) / 16;
+  for (long long blk = warp0; blk < nblk; blk += nwarps) {
+    const long long ra = blk * 16 + g, rb = ra + 8;
+    const bool oka = ra < rows, okb = rb < rows;
+    uint4 xa[STEPS], xb[STEPS];
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      xa[s] = oka ? __ldg(reinterpret_cast<const uint4*>(y + ra * C + 32 * s + 8 * t)) : make_uint4(0, 0, 0, 0);
+      xb[s] = okb ? __ldg(reinterpret_cast<const uint4*>(y + rb * C + 32 * s + 8 * t)) : make_uint4(0, 0, 0, 0);
+    }
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      const float4* sp = reinterpret_cast<const float4*>(ss + 32 * s + 8 * t);
+      float sc[8], sh[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 f = sp[q];
+        sc[2 * q] = f.x; sh[2 * q] = f.y; sc[2 * q + 1] = f.z; sh[2 * q + 1] = f.w;
+      }
+      const uint32_t xw[4] = {xa[s].x, xa[s].y, xa[s].z, xa[s].w};
+      const uint32_t yw[4] = {xb[s].x, xb[s].y, xb[s].z, xb[s].w};
+      uint32_t pa[4], pb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a = unpack2(xw[q]), b = unpack2(yw[q]);
+        pa[q] = pack2(fmaxf(fmaf(a.x, sc[2 * q], sh[2 * q]), 0.f), fmaxf(fmaf(a.y, sc[2 * q + 1], sh[2 * q + 1]), 0.f));
+        pb[q] = pack2(fmaxf(fmaf(b.x, sc[2 * q], sh[2 * q]), 0.f), fmaxf(fmaf(b.y, sc[2 * q + 1], sh[2 * q + 1]), 0.f));
+      }
+      const uint32_t a1[4] = {pa[0], pb[0], pa[1], pb[1]};
+      const uint32_t a2[4] = {pa[2], pb[2], pa[3], pb[3]};
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint4 bf = bfr[(s * NT + nt) * 32 + lane];
+        mma_bf16_16816(acc[nt], a1, bf.x, bf.y);
+        mma_bf16_16816(acc[nt], a2, bf.z, bf.w);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int c0 = nt * 8 + 2 * t;
+      if (c0 < NC) {
+        const float b0 = __ldg(bias + c0);
+        if (oka) z[ra * NC + c0] = acc[nt][0] + b0;
+        if (okb) z[rb * NC + c0] = acc[nt][2] + b0;
+      }
+      if (c0 + 1 < NC) {
+        const float b1 = __ldg(bias + c0 + 1);
+        if (oka) z[ra * NC + c0 + 1] = acc[nt][1] + b1;
+        if (okb) z[rb * NC + c0 + 1] = acc[nt][3] + b1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, pass 2 (apply): one warp per 16 rows, channels in groups of 64.  Inside a group the
+// 8 n-tiles are interleaved so that lane t owns channels [8t, 8t+8) and [32+8t, 32+8t+8) of the
+// group (two 16-byte chunks per row, 64 contiguous bytes per row per load instruction):
+//   channel(nt, col j) = base(j/2) + 2 nt + (j & 1)   with base(t) = 8t for 2nt+e < 8 else 32+8t-8
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int grp_channel(int nt, int j) {
+  const int idx = 2 * nt + (j & 1), tt = j >> 1;
+  return idx < 8 ? 8 * tt + idx : 32 + 8 * tt + (idx - 8);
+}
+
+template <int GROUPS>   // C = 64 * GROUPS
+__global__ void __launch_bounds__(256)
+cls_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz16, const __nv_bfloat16* __restrict__ y,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const float* __restrict__ gamma, const float* __restrict__ w,
+                     const float* __restrict__ dsum, const float* __restrict__ ddot, float inv_n,
+                     __nv_bfloat16* __restrict__ dy, long long rows, int NC) {
+  constexpr int C = 64 * GROUPS;
+  extern __shared__ __align__(16) uint8_t smem[];
+  float4* t1 = reinterpret_cast<float4*>(smem);                       // [C] scale, shift, E, F
+  float* t2 = reinterpret_cast<float*>(smem + C * sizeof(float4));    // [C] A = gamma * invstd
+  uint2* bfr = reinterpret_cast<uint2*>(smem + C * (sizeof(float4) + sizeof(float)));   // [GROUPS][8][2][32]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float is = invstd[c];
+    const float E = is * ddot[c] * inv_n;                    // xhat*ddot/n = (y - mean) * E
+    const float F = dsum[c] * inv_n - mean[c] * E;
+    t1[c] = make_float4(scale[c], shift[c], E, F);
+    t2[c] = gamma[c] * is;
+  }
+  for (int i = threadIdx.x; i < GROUPS * 8 * 2 * 32; i += blockDim.x) {
+    const int ln = i & 31, ks = (i >> 5) & 1, nt = (i >> 6) & 7, gq = i >> 9;
+    const int ch = 64 * gq + grp_channel(nt, ln >> 2);
+    const int k = 16 * ks + 2 * (ln & 3);
+    auto wv = [&](int kk) { return kk < NC ? w[(size_t)kk * C + ch] : 0.f; };
+    bfr[i] = make_uint2(pack2(wv(k), wv(k + 1)), pack2(wv(k + 8), wv(k + 9)));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long nblk = (rows + 15) / 16;
+  for (long long blk = warp0; blk < nblk; blk += nwarps) {
+    const long long ra = blk * 16 + g, rb = ra + 8;
+    const bool oka = ra < rows, okb = rb < rows;
+    uint32_t a[2][4];
+    {
+      const uint32_t* pa = reinterpret_cast<const uint32_t*>(dz16 + ra * 32);
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(dz16 + rb * 32);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        a[ks][0] = oka ? __ldg(pa + 8 * ks + t) : 0u;
+        a[ks][1] = okb ? __ldg(pb + 8 * ks + t) : 0u;
+        a[ks][2] = oka ? __ldg(pa + 8 * ks + 4 + t) : 0u;
+        a[ks][3] = okb ? __ldg(pb + 8 * ks + 4 + t) : 0u;
+      }
+    }
+#pragma unroll 1
+    for (int gq = 0; gq < GROUPS; ++gq) {
+      const int cb = 64 * gq;
+      uint4 ya[2], yb[2];
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        ya[hc] = oka ? __ldg(reinterpret_cast<const uint4*>(y + ra * C + cb + 32 * hc + 8 * t)) : make_uint4(0, 0, 0, 0);
+        yb[hc] = okb ? __ldg(reinterpret_cast<const uint4*>(y + rb * C + cb + 32 * hc + 8 * t)) : make_uint4(0, 0, 0, 0);
+      }
+      float acc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+        const uint2 b0 = bfr[((gq * 8 + nt) * 2 + 0) * 32 + lane];
+        const uint2 b1 = bfr[((gq * 8 + nt) * 2 + 1) * 32 + lane];
+        mma_bf16_16816(acc[nt], a[0], b0.x, b0.y);
+        mma_bf16_16816(acc[nt], a[1], b1.x, b1.y);
+      }
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        const uint32_t wa[4] = {ya[hc].x, ya[hc].y, ya[hc].z, ya[hc].w};
+        const uint32_t wb[4] = {yb[hc].x, yb[hc].y, yb[hc].z, yb[hc].w};
+        uint32_t oa[4], ob[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {   // channels cb + 32 hc + 8 t + 2q (+1)  <->  n-tile 4 hc + q
+          const int nt = 4 * hc + q;
+          const int ch = cb + 32 * hc + 8 * t + 2 * q;
+          const float4 k0 = t1[ch], k1 = t1[ch + 1];
+          const float A0 = t2[ch], A1 = t2[ch + 1];
+          const float2 va = unpack2(wa[q]), vb = unpack2(wb[q]);
+          const float da00 = fmaf(va.x, k0.x, k0.y) > 0.f ? acc[nt][0] : 0.f;
+          const float da01 = fmaf(va.y, k1.x, k1.y) > 0.f ? acc[nt][1] : 0.f;
+          const float da10 = fmaf(vb.x, k0.x, k0.y) > 0.f ? acc[nt][2] : 0.f;
+          const float da11 = fmaf(vb.y, k1.x, k1.y) > 0.f ? acc[nt][3] : 0.f;
+          oa[q] = pack2(A0 * (da00 - fmaf(va.x, k0.z, k0.w)), A1 * (da01 - fmaf(va.y, k1.z, k1.w)));
+          ob[q] = pack2(A0 * (da10 - fmaf(vb.x, k0.z, k0.w)), A1 * (da11 - fmaf(vb.y, k1.z, k1.w)));
+        }
+        if (oka) *reinterpret_cast<uint4*>(dy + ra * C + cb + 32 * hc + 8 * t) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+        if (okb) *reinterpret_cast<uint4*>(dy + rb * C + cb + 32 * hc + 8 * t) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, pass 1 (reduce): block of C/64 warps, warp w owns channels [64w, 64w+64); the block
+// walks 32-row tiles staged in smem with cp.async (double buffered); fragments via ldmatrix.
+// ---------------------------------------------------------------------------------------------
+constexpr int RT = 32;   // rows per tile
+
+template <int WARPS>   // C = 64 * WARPS
+__global__ void __launch_bounds__(WARPS * 32)
+cls_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz16, const __nv_bfloat16* __restrict__ y,
+                      const float* __restrict__ scale, const float* __restrict__ shift,
+                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                      const float* __restrict__ w, float* __restrict__ dw, float* __restrict__ dbias,
+                      float* __restrict__ dsum, float* __restrict__ ddot, long long rows, int NC,
+                      long long tiles_per_block) {
+  constexpr int C = 64 * WARPS;
+  constexpr int YS = C * 2 + 16;    // row strides in bytes (padding keeps ldmatrix conflict free)
+  constexpr int ZS = 64 + 16;
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* ytile = smem;                       // [2][RT][YS]
+  uint8_t* ztile = smem + 2 * RT * YS;         // [2][RT][ZS]
+  float4* tab = reinterpret_cast<float4*>(smem + 2 * RT * (YS + ZS));   // [C] scale, shift, mean, invstd
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  for (int c = tid; c < C; c += blockDim.x) tab[c] = make_float4(scale[c], shift[c], mean[c], invstd[c]);
+
+  const long long tile0 = (long long)blockIdx.x * tiles_per_block;
+  const long long ntiles_all = (rows + RT - 1) / RT;
+  const long long tile1 = min(ntiles_all, tile0 + tiles_per_block);
+  auto load_tile = [&](long long tile, int buf) {
+    const long long r0 = tile * RT;
+    for (int i = tid; i < RT * (C / 8); i += WARPS * 32) {
+      const int r = i / (C / 8), ck = i % (C / 8);
+      const bool ok = r0 + r < rows;
+      cp_async16(smem_addr(ytile + (buf * RT + r) * YS + ck * 16), y + (ok ? (r0 + r) : 0) * C + ck * 8, ok);
+    }
+    for (int i = tid; i < RT * 4; i += WARPS * 32) {
+      const int r = i >> 2, ck = i & 3;
+      const bool ok = r0 + r < rows;
+      cp_async16(smem_addr(ztile + (buf * RT + r) * ZS + ck * 16), dz16 + (ok ? (r0 + r) : 0) * 32 + ck * 8, ok);
+    }
+    cp_async_commit();
+  };
+  // W fragments for g = dz @ W over this warp's channels: (k = class, n = channel)
+  uint32_t wf[8][2][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int ch = 64 * warp + 8 * nt + g, k = 16 * ks + 2 * t;
+      auto wv = [&](int kk) { return kk < NC ? w[(size_t)kk * C + ch] : 0.f; };
+      wf[nt][ks][0] = pack2(wv(k), wv(k + 1));
+      wf[nt][ks][1] = pack2(wv(k + 8), wv(k + 9));
+    }
+  // BN constants of the channels this lane sees in the dW B-fragments: channel 64w + 8nt + g
+  float bsc[8], bsh[8];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    bsc[nt] = scale[64 * warp + 8 * nt + g];
+    bsh[nt] = shift[64 * warp + 8 * nt + g];
+  }
+  float dwacc[2][8][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dwacc[m][nt][e] = 0.f;
+  float ssum[8][2], sdot[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { ssum[nt][0] = ssum[nt][1] = sdot[nt][0] = sdot[nt][1] = 0.f; }
+  float sbias = 0.f;
+
+  if (tile0 < tile1) load_tile(tile0, 0);
+  __syncthreads();   // tab visible
+  for (long long tile = tile0; tile < tile1; ++tile) {
+    const int buf = (int)((tile - tile0) & 1);
+    if (tile + 1 < tile1) {
+      load_tile(tile + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint8_t* yt = ytile + buf * RT * YS;
+    const uint8_t* zt = ztile + buf * RT * ZS;
+    if (warp == 0) {   // dbias: lane j sums class column j of the tile
+      const __nv_bfloat16* zc = reinterpret_cast<const __nv_bfloat16*>(zt) + lane;
+#pragma unroll 8
+      for (int r = 0; r < RT; ++r) sbias += __bfloat162float(zc[r * (ZS / 2)]);
+    }
+#pragma unroll
+    for (int sub = 0; sub < RT / 16; ++sub) {
+      const int r0 = sub * 16;
+      // ---- g = dz @ W  (A: rows x classes, straight ldmatrix) ----
+      uint32_t az[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        ldmatrix_x4(az[ks], smem_addr(zt + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ZS + (16 * ks + (lane >> 4) * 8) * 2));
+      // ---- dz^T fragments for dW (A: classes x rows, transposed ldmatrix) ----
+      uint32_t azt[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+        ldmatrix_x4_trans(azt[m], smem_addr(zt + (r0 + (lane & 7) + (lane >> 4) * 8) * ZS +
+                                            (16 * m + ((lane >> 3) & 1) * 8) * 2));
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        // act fragments of n-tiles 2np, 2np+1 (B: rows x channels, transposed ldmatrix) + BN + ReLU
+        uint32_t yb[4];
+        ldmatrix_x4_trans(yb, smem_addr(yt + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * YS +
+                                        (64 * warp + 16 * np + (lane >> 4) * 8) * 2));
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int nt = 2 * np + q;
+          uint32_t bact[2];
+#pragma unroll
+          for (int hk = 0; hk < 2; ++hk) {
+            const float2 v = unpack2(yb[2 * q + hk]);
+            bact[hk] = pack2(fmaxf(fmaf(v.x, bsc[nt], bsh[nt]), 0.f), fmaxf(fmaf(v.y, bsc[nt], bsh[nt]), 0.f));
+          }
+          mma_bf16_16816(dwacc[0][nt], azt[0], bact[0], bact[1]);
+          mma_bf16_16816(dwacc[1][nt], azt[1], bact[0], bact[1]);
+          // g for this n-tile and the BatchNorm-backward sums
+          float gacc[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16_16816(gacc, az[0], wf[nt][0][0], wf[nt][0][1]);
+          mma_bf16_16816(gacc, az[1], wf[nt][1][0], wf[nt][1][1]);
+          const int ch = 64 * warp + 8 * nt + 2 * t;
+          const float4 k0 = tab[ch], k1 = tab[ch + 1];
+          const float2 va = unpack2(*reinterpret_cast<const uint32_t*>(yt + (r0 + g) * YS + ch * 2));
+          const float2 vb = unpack2(*reinterpret_cast<const uint32_t*>(yt + (r0 + g + 8) * YS + ch * 2));
+          const float d00 = fmaf(va.x, k0.x, k0.y) > 0.f ? gacc[0] : 0.f;
+          const float d01 = fmaf(va.y, k1.x, k1.y) > 0.f ? gacc[1] : 0.f;
+          const float d10 = fmaf(vb.x, k0.x, k0.y) > 0.f ? gacc[2] : 0.f;
+          const float d11 = fmaf(vb.y, k1.x, k1.y) > 0.f ? gacc[3] : 0.f;
+          ssum[nt][0] += d00 + d10;
+          ssum[nt][1] += d01 + d11;
+          sdot[nt][0] += (d00 * (va.x - k0.z) + d10 * (vb.x - k0.z)) * k0.w;
+          sdot[nt][1] += (d01 * (va.y - k1.z) + d11 * (vb.y - k1.z)) * k1.w;
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with `buf` before it is refilled
+  }
+  // ---- flush: BatchNorm sums (reduce over the 8 row-lanes), dW, dbias ----
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float a = ssum[nt][e], b = sdot[nt][e];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (g == 0) {
+        const int ch = 64 * warp + 8 * nt + 2 * t + e;
+        atomicAdd(dsum + ch, a);
+        atomicAdd(ddot + ch, b);
+      }
+    }
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int ch = 64 * warp + 8 * nt + 2 * t;
+      const int j0 = 16 * m + g, j1 = j0 + 8;
+      if (j0 < NC) {
+        atomicAdd(dw + (size_t)j0 * C + ch, dwacc[m][nt][0]);
+        atomicAdd(dw + (size_t)j0 * C + ch + 1, dwacc[m][nt][1]);
+      }
+      if (j1 < NC) {
+        atomicAdd(dw + (size_t)j1 * C + ch, dwacc[m][nt][2]);
+        atomicAdd(dw + (size_t)j1 * C + ch + 1, dwacc[m][nt][3]);
+      }
+    }
+  if (warp == 0 && lane < NC) atomicAdd(dbias + lane, sbias);
+}
+
+// ---------------------------------------------------------------------------------------------
+// logits upsample (bilinear, align_corners=False, integer scale s): z [B,H,W,NC] fp32 ->
+// logits [B,NC,H*s,W*s] fp32 NCHW.  One block per (image, output row): the two source rows are
+// staged in smem, writes are contiguous along x.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bl_src(int o, int s, int n_in, int& i0, int& i1, float& l) {
+  float src = ((float)o + 0.5f) / (float)s - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  i1 = min(i0 + 1, n_in - 1);
+  l = src - (float)i0;
+}
+__device__ __forceinline__ float bl_w(int o, int i, int s, int n_in) {
+  int i0, i1;
+  float l;
+  bl_src(o, s, n_in, i0, i1, l);
+  return (i == i0 ? 1.f - l : 0.f) + (i == i1 ? l : 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+cls_upsample_fwd_kernel(const float* __restrict__ z, float* __restrict__ out, int H, int W, int NC, int s) {
+  extern __shared__ __align__(16) float zs[];   // [2][W*NC]
+  const int OH = H * s, OW = W * s;
+  const int oy = blockIdx.x % OH, b = blockIdx.x / OH;
+  int y0, y1;
+  float ly;
+  bl_src(oy, s, H, y0, y1, ly);
+  const int n = W * NC;
+  const float* r0 = z + ((size_t)b * H + y0) * n;
+  const float* r1 = z + ((size_t)b * H + y1) * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    zs[i] = __ldg(r0 + i);
+    zs[n + i] = __ldg(r1 + i);
+  }
+  __syncthreads();
+  float* ob = out + (size_t)b * NC * OH * OW + (size_t)oy * OW;
+  for (int i = threadIdx.x; i < NC * OW; i += blockDim.x) {
+    const int ox = i % OW, j = i / OW;
+    int x0, x1;
+    float lx;
+    bl_src(ox, s, W, x0, x1, lx);
+    const float top = (1.f - lx) * zs[x0 * NC + j] + lx * zs[x1 * NC + j];
+    const float bot = (1.f - lx) * zs[n + x0 * NC + j] + lx * zs[n + x1 * NC + j];
+    ob[(size_t)j * OH * OW + ox] = (1.f - ly) * top + ly * bot;
+  }
+}
+
+// transpose of the above into the padded bf16 layout the backward MMAs read: dz16 [B*H*W, 32].
+// One block per (image, source row): vertical taps straight from global (contiguous along x),
+// the per-class row of partial sums staged in smem, then the horizontal taps.
+__global__ void __launch_bounds__(256)
+cls_upsample_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restrict__ dz16, int H, int W,
+                        int NC, int s) {
+  extern __shared__ __align__(16) float ts[];   // [NC][OW]
+  const int OH = H * s, OW = W * s;
+  const int iy = blockIdx.x % H, b = blockIdx.x / H;
+  const int oy_lo = max(0, s * iy - s), oy_hi = min(OH, s * iy + 2 * s);
+  const float* db = dout + (size_t)b * NC * OH * OW;
+  for (int i = threadIdx.x; i < NC * OW; i += blockDim.x) {
+    const int ox = i % OW, j = i / OW;
+    const float* col = db + (size_t)j * OH * OW + ox;
+    float acc = 0.f;
+    for (int oy = oy_lo; oy < oy_hi; ++oy) {
+      const float wy = bl_w(oy, iy, s, H);
+      if (wy != 0.f) acc = fmaf(wy, __ldg(col + (size_t)oy * OW), acc);
+    }
+    ts[i] = acc;
+  }
+  __syncthreads();
+  __nv_bfloat16* orow = dz16 + ((size_t)b * H + iy) * W * 32;
+  for (int i = threadIdx.x; i < W * 32; i += blockDim.x) {
+    const int j = i & 31, ix = i >> 5;
+    float gsum = 0.f;
+    if (j < NC) {
+      const int ox_lo = max(0, s * ix - s), ox_hi = min(OW, s * ix + 2 * s);
+      for (int ox = ox_lo; ox < ox_hi; ++ox) {
+        const float wx = bl_w(ox, ix, s, W);
+        if (wx != 0.f) gsum = fmaf(wx, ts[j * OW + ox], gsum);
+      }
+    }
+    orow[i] = __float2bfloat16_rn(gsum);
+  }
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    s4_set_error("%s: cudaFuncSetAttribute(%zu) failed: %s", what, bytes, cudaGetErrorString(e));
+    return S4_ERR_CUDA;
+  }
+  return S4_OK;
+}
+
+}  // namespace
+
+bool s4_cls_tc_supported(int C, int NC, int dtype) {
+  return dtype == S4_BF16 && NC >= 1 && NC <= 24 && (C == 64 || C == 128 || C == 256 || C == 512);
+}
+
+int s4_cls_fwd_tc(const void* y, const float* scale, const float* shift, const float* w, const float* bias,
+                  float* z, long long rows, int C, int NC, cudaStream_t st) {
+  const size_t smem = (size_t)C * 8 + (size_t)(C / 32) * 3 * 32 * 16;
+  const int grid = (int)std::min<long long>((rows + 127) / 128, (long long)s4_num_sms() * 4);
+  int rc;
+#define S4_CLS_FWD(STEPS)                                                                         \
+  {                                                                                               \
+    if ((rc = set_smem(cls_fwd_kernel<STEPS, 3>, smem, "cls_fwd"))) return rc;                    \
+    cls_fwd_kernel<STEPS, 3><<<grid, 256, smem, st>>>((const __nv_bfloat16*)y, scale, shift, w,   \
+                                                      bias, z, rows, NC);                         \
+  }
+  if (C == 64) S4_CLS_FWD(2)
+  else if (C == 128) S4_CLS_FWD(4)
+  else if (C == 256) S4_CLS_FWD(8)
+  else S4_CLS_FWD(16)
+#undef S4_CLS_FWD
+  return s4_check_launch("cls_fwd");
+}
+
+int s4_cls_bwd_reduce_tc(const void* dz16, const void* y, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, const float* w, float* dw, float* dbias,
+                         float* dsum, float* ddot, long long rows, int C, int NC, cudaStream_t st) {
+  const int warps = C / 64;
+  const size_t smem = (size_t)2 * RT * ((size_t)C * 2 + 16 + 80) + (size_t)C * 16;
+  const long long ntiles = (rows + RT - 1) / RT;
+  const int per_sm = warps <= 2 ? 4 : (warps <= 4 ? 2 : 1);
+  long long blocks = std::min<long long>(ntiles, (long long)s4_num_sms() * per_sm);
+  const long long tpb = (ntiles + blocks - 1) / blocks;
+  blocks = (ntiles + tpb - 1) / tpb;
+  int rc;
+#define S4_CLS_RED(WARPS)                                                                          \
+  {                                                                                                \
+    if ((rc = set_smem(cls_bwd_reduce_kernel<WARPS>, smem, "cls_bwd_reduce"))) return rc;          \
+    cls_bwd_reduce_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, smem, st>>>(                      \
+        (const __nv_bfloat16*)dz16, (const __nv_bfloat16*)y, scale, shift, mean, invstd, w, dw,    \
+        dbias, dsum, ddot, rows, NC, tpb);                                                         \
+  }
+  if (warps == 1) S4_CLS_RED(1)
+  else if (warps == 2) S4_CLS_RED(2)
+  else if (warps == 4) S4_CLS_RED(4)
+  else S4_CLS_RED(8)
+#undef S4_CLS_RED
+  return s4_check_launch("cls_bwd_reduce");
+}
+
+int s4_cls_bwd_apply_tc(const void* dz16, const void* y, const float* scale, const float* shift,
+                        const float* mean, const float* invstd, const float* gamma, const float* w,
+                        const float* dsum, const float* ddot, double count, void* dy, long long rows,
+                        int C, int NC, cudaStream_t st) {
+  const size_t smem = (size_t)C * 20 + (size_t)(C / 64) * 8 * 2 * 32 * 8;
+  const int grid = (int)std::min<long long>((rows + 127) / 128, (long long)s4_num_sms() * 4);
+  const float inv_n = (float)(1.0 / count);
+  int rc;
+#define S4_CLS_APP(GROUPS)                                                                         \
+  {                                                                                                \
+    if ((rc = set_smem(cls_bwd_apply_kernel<GROUPS>, smem, "cls_bwd_apply"))) return rc;           \
+    cls_bwd_apply_kernel<GROUPS><<<grid, 256, smem, st>>>(                                         \
+        (const __nv_bfloat16*)dz16, (const __nv_bfloat16*)y, scale, shift, mean, invstd, gamma, w, \
+        dsum, ddot, inv_n, (__nv_bfloat16*)dy, rows, NC);                                          \
+  }
+  if (C == 64) S4_CLS_APP(1)
+  else if (C == 128) S4_CLS_APP(2)
+  else if (C == 256) S4_CLS_APP(4)
+  else S4_CLS_APP(8)
+#undef S4_CLS_APP
+  return s4_check_launch("cls_bwd_apply");
+}
+
+int s4_cls_upsample_fwd(const float* z, float* logits, int B, int H, int W, int NC, int s, cudaStream_t st) {
+  const size_t smem = (size_t)2 * W * NC * 4;
+  int rc;
+  if ((rc = set_smem(cls_upsample_fwd_kernel, smem, "cls_upsample_fwd"))) return rc;
+  cls_upsample_fwd_kernel<<<B * H * s, 256, smem, st>>>(z, logits, H, W, NC, s);
+  return s4_check_launch("cls_upsample_fwd");
+}
+
+int s4_cls_upsample_bwd(const float* dlogits, void* dz16, int B, int H, int W, int NC, int s, cudaStream_t st) {
+  const size_t smem = (size_t)NC * W * s * 4;
+  int rc;
+  if ((rc = set_smem(cls_upsample_bwd_kernel, smem, "cls_upsample_bwd"))) return rc;
+  cls_upsample_bwd_kernel<<<B * H, 256, smem, st>>>(dlogits, (__nv_bfloat16*)dz16, H, W, NC, s);
+  return s4_check_launch("cls_upsample_bwd");
+}

@@ -448,11 +448,25 @@ class ConvBNReLUUpFn(torch.autograd.Function):
         return dx, None, None, None, None, None, None, None
 
 
+def _conv_grads(stage, x, dyc, B, H, W, Cin, Cout, need_dx=True):
+    """conv3x3 weight gradient (accumulated into conv.weight.grad) and input gradient."""
+    conv = stage.conv
+    dt = _code(x.dtype)
+    L.call('s4_conv3x3_wgrad', _p(x), _p(dyc), _p(grad_buffer(conv.weight)), B, H, W, Cin, Cout, dt,
+           backend(), _st())
+    dx = None
+    if need_dx:
+        _, wd = conv_packed(conv.weight)
+        dx = torch.empty_like(x)
+        L.call('s4_conv3x3_dgrad', _p(dyc), _p(wd), _p(dx), B, H, W, Cin, Cout, dt, backend(), _st())
+    return dx
+
+
 def _conv_bn_backward(stage, x, y, dact, sums, mean, invstd, count, group_info, B, H, W, Cin, Cout,
                       need_dx=True):
     """Shared tail of the stage backward: BN backward (local dgamma/dbeta, global reduction of the
     two sums under SyncBN) -> conv wgrad / dgrad."""
-    bn, conv = stage.bn, stage.conv
+    bn = stage.bn
     dt = _code(x.dtype)
     grad_buffer(bn.bias).add_(sums[0])      # dbeta  = sum dact        (local, like torch SyncBN)
     grad_buffer(bn.weight).add_(sums[1])    # dgamma = sum dact * xhat
@@ -462,14 +476,7 @@ def _conv_bn_backward(stage, x, y, dact, sums, mean, invstd, count, group_info, 
     dyc = torch.empty_like(y)
     L.call('s4_bn_bwd_apply', _p(dact), _p(y), _p(bn.weight.detach()), _p(mean), _p(invstd),
            _p(gsums[0]), _p(gsums[1]), count, _p(dyc), B * H * W, Cout, dt, _st())
-    L.call('s4_conv3x3_wgrad', _p(x), _p(dyc), _p(grad_buffer(conv.weight)), B, H, W, Cin, Cout, dt,
-           backend(), _st())
-    dx = None
-    if need_dx:
-        _, wd = conv_packed(conv.weight)
-        dx = torch.empty_like(x)
-        L.call('s4_conv3x3_dgrad', _p(dyc), _p(wd), _p(dx), B, H, W, Cin, Cout, dt, backend(), _st())
-    return dx
+    return _conv_grads(stage, x, dyc, B, H, W, Cin, Cout, need_dx)
 
 
 class ConvBNReLUClsUpFn(torch.autograd.Function):
@@ -508,6 +515,29 @@ class ConvBNReLUClsUpFn(torch.autograd.Function):
         dt = _code(x.dtype)
         rows = B * H * W
         dlogits = dlogits.contiguous()
+        if L.load().s4_cls_supported(Cout, NC, dt):
+            # bf16 fast path: y is streamed twice (reduce, apply), the ReLU-masked gradient is
+            # never written to memory
+            bn = stage.bn
+            w2 = conv_seg.weight.detach().reshape(NC, Cout)
+            dz16 = torch.empty((rows, 32), dtype=torch.bfloat16, device=x.device)
+            L.call('s4_cls_upsample_bwd_padded', _p(dlogits), _p(dz16), B, H, W, NC, s, _st())
+            sums = torch.zeros((2, Cout), dtype=torch.float32, device=x.device)
+            L.call('s4_cls_bwd_reduce', _p(dz16), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(w2),
+                   _p(grad_buffer(conv_seg.weight)), _p(grad_buffer(conv_seg.bias)), _p(sums[0]), _p(sums[1]),
+                   rows, Cout, NC, _st())
+            grad_buffer(bn.bias).add_(sums[0])
+            grad_buffer(bn.weight).add_(sums[1])
+            gsums = sums
+            gi = ctx.group_info
+            if gi is not None and gi.get('world', 1) > 1:
+                gsums = _all_reduce_stats(sums.clone(), gi)
+            dyc = torch.empty_like(y)
+            L.call('s4_cls_bwd_apply', _p(dz16), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd),
+                   _p(bn.weight.detach()), _p(w2), _p(gsums[0]), _p(gsums[1]), ctx.count, _p(dyc), rows, Cout,
+                   NC, _st())
+            dx = _conv_grads(stage, x, dyc, B, H, W, Cin, Cout, need_dx=ctx.needs_input_grad[0])
+            return dx, None, None, None, None, None, None, None, None
         dz = torch.empty((rows, NC), dtype=torch.float32, device=x.device)
         L.call('s4_upsample_logits_bwd', _p(dlogits), _p(dz), B, H, W, NC, s, _st())
         dact = torch.empty_like(y)

@@ -207,3 +207,41 @@ def test_tc_attention_bwd(B, H, Lt, pasa):
     assert rel(gv, rv) < 2e-2, ('dV', rel(gv, rv))
     assert rel(gk, rk) < 3e-2, ('dK', rel(gk, rk))
     assert rel(gq, rq) < 3e-2, ('dQ', rel(gq, rq))
+
+
+# ------------------------------------------------------------------------------------------ last head stage (bf16)
+@pytest.mark.parametrize('B,H,W,Cin,Cout,NC,s', [(2, 16, 16, 64, 64, 5, 2), (1, 32, 32, 64, 256, 21, 2),
+                                                  (2, 8, 8, 64, 256, 19, 4), (1, 24, 24, 64, 128, 21, 2)])
+def test_cls_stage_bf16(B, H, W, Cin, Cout, NC, s):
+    """conv3x3 -> BN -> ReLU -> conv_seg -> bilinear: mma.sync kernels of head_cls.cu (forward,
+    reduce, apply) against fp32 autograd of the reference order (upsample THEN conv_seg)."""
+    from test_kernels_gpu import _Stage
+    g = gen(21)
+    stage = _Stage(Cin, Cout).to(DEV)
+    seg = torch.nn.Conv2d(Cout, NC, 1).to(DEV)
+    with torch.no_grad():
+        stage.bn.weight.copy_(1.0 + 0.2 * torch.randn(Cout, generator=g))
+        stage.bn.bias.copy_(0.2 * torch.randn(Cout, generator=g))
+        seg.weight.mul_(3.0)
+    ref, rseg = _Stage(Cin, Cout), torch.nn.Conv2d(Cout, NC, 1)
+    ref.load_state_dict({k: v.cpu() for k, v in stage.state_dict().items()})
+    rseg.load_state_dict({k: v.cpu() for k, v in seg.state_dict().items()})
+    x = torch.randn(B, H, W, Cin, generator=g)
+    xd = x.to(DEV, BF).reshape(B * H * W, Cin).requires_grad_(True)
+    assert L.load().s4_cls_supported(Cout, NC, L.BF16) == 1
+    out = ops.ConvBNReLUClsUpFn.apply(xd, stage, seg, B, H, W, s, True, None)
+    dout = torch.randn(B, NC, H * s, W * s, generator=g)
+    out.backward(dout.to(DEV))
+    xr = x.to(BF).float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yr = rseg(F.interpolate(F.relu(ref.bn(ref.conv(xr))), scale_factor=s, mode='bilinear', align_corners=False))
+    yr.backward(dout)
+    errs = dict(out=rel(out, yr), seg_w=rel(seg.weight.grad, rseg.weight.grad), seg_b=rel(seg.bias.grad, rseg.bias.grad),
+                bn_w=rel(stage.bn.weight.grad, ref.bn.weight.grad), bn_b=rel(stage.bn.bias.grad, ref.bn.bias.grad),
+                conv_w=rel(stage.conv.weight.grad, ref.conv.weight.grad),
+                dx=rel(xd.grad.float().view(B, H, W, Cin).permute(0, 3, 1, 2), xr.grad))
+    # forward / conv_seg gradients: plain bf16 accuracy.  Everything behind the BatchNorm backward
+    # carries the noise of the ReLU mask flipping where bf16 rounding of the conv output crosses
+    # zero (the reference keeps it in fp32), hence the wider gate there.
+    tol = dict(out=2e-2, seg_w=2e-2, seg_b=2e-2, bn_w=3e-2, bn_b=6e-2, conv_w=6e-2, dx=6e-2)
+    bad = {k: v for k, v in errs.items() if v > tol[k]}
+    assert not bad, (bad, errs)
