@@ -433,52 +433,70 @@ __device__ __forceinline__ float bl_w(int o, int i, int s, int n_in) {
 
 __global__ void __launch_bounds__(256)
 cls_upsample_fwd_kernel(const float* __restrict__ z, float* __restrict__ out, int H, int W, int NC, int s) {
-  extern __shared__ __align__(16) float zs[];   // [2][W*NC]
+  extern __shared__ __align__(16) float zs[];   // [2][W*NC] source rows, then [OW] (x0 | x1<<16) and [OW] lx
   const int OH = H * s, OW = W * s;
   const int oy = blockIdx.x % OH, b = blockIdx.x / OH;
   int y0, y1;
   float ly;
   bl_src(oy, s, H, y0, y1, ly);
   const int n = W * NC;
+  int* xi = reinterpret_cast<int*>(zs + 2 * n);
+  float* xl = zs + 2 * n + OW;
   const float* r0 = z + ((size_t)b * H + y0) * n;
   const float* r1 = z + ((size_t)b * H + y1) * n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    zs[i] = __ldg(r0 + i);
-    zs[n + i] = __ldg(r1 + i);
-  }
-  __syncthreads();
-  float* ob = out + (size_t)b * NC * OH * OW + (size_t)oy * OW;
-  for (int i = threadIdx.x; i < NC * OW; i += blockDim.x) {
-    const int ox = i % OW, j = i / OW;
+  // vertical blend once per source element: zs[i] = (1-ly) z[y0] + ly z[y1]
+  for (int i = threadIdx.x; i < n; i += blockDim.x) zs[i] = (1.f - ly) * __ldg(r0 + i) + ly * __ldg(r1 + i);
+  for (int ox = threadIdx.x; ox < OW; ox += blockDim.x) {
     int x0, x1;
     float lx;
     bl_src(ox, s, W, x0, x1, lx);
-    const float top = (1.f - lx) * zs[x0 * NC + j] + lx * zs[x1 * NC + j];
-    const float bot = (1.f - lx) * zs[n + x0 * NC + j] + lx * zs[n + x1 * NC + j];
-    ob[(size_t)j * OH * OW + ox] = (1.f - ly) * top + ly * bot;
+    xi[ox] = x0 | (x1 << 16);
+    xl[ox] = lx;
+  }
+  __syncthreads();
+  float* ob = out + (size_t)b * NC * OH * OW + (size_t)oy * OW;
+  for (int j = threadIdx.x / 32; j < NC; j += blockDim.x / 32) {     // one warp per class row
+    float* orow = ob + (size_t)j * OH * OW;
+    for (int ox = threadIdx.x & 31; ox < OW; ox += 32) {
+      const int pk = xi[ox];
+      const float lx = xl[ox];
+      const float v0 = zs[(pk & 0xffff) * NC + j], v1 = zs[(pk >> 16) * NC + j];
+      orow[ox] = (1.f - lx) * v0 + lx * v1;
+    }
   }
 }
 
 // transpose of the above into the padded bf16 layout the backward MMAs read: dz16 [B*H*W, 32].
-// One block per (image, source row): vertical taps straight from global (contiguous along x),
-// the per-class row of partial sums staged in smem, then the horizontal taps.
+// One block per (image, source row): vertical taps straight from global (contiguous along x,
+// weights precomputed per block), the per-class row of partial sums staged in smem, then the
+// horizontal taps from a per-block weight table.
 __global__ void __launch_bounds__(256)
 cls_upsample_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restrict__ dz16, int H, int W,
                         int NC, int s) {
-  extern __shared__ __align__(16) float ts[];   // [NC][OW]
+  extern __shared__ __align__(16) float ts[];   // [NC][OW] partial sums, [W][3s] horizontal weights, [3s] vertical
   const int OH = H * s, OW = W * s;
   const int iy = blockIdx.x % H, b = blockIdx.x / H;
+  const int taps = 3 * s;
+  float* wxs = ts + NC * OW;
+  float* wys = wxs + W * taps;
+  for (int i = threadIdx.x; i < W * taps; i += blockDim.x) {
+    const int ix = i / taps, ox = s * ix - s + i % taps;
+    wxs[i] = (ox >= 0 && ox < OW) ? bl_w(ox, ix, s, W) : 0.f;
+  }
+  if (threadIdx.x < taps) {
+    const int oy = s * iy - s + threadIdx.x;
+    wys[threadIdx.x] = (oy >= 0 && oy < OH) ? bl_w(oy, iy, s, H) : 0.f;
+  }
+  __syncthreads();
   const int oy_lo = max(0, s * iy - s), oy_hi = min(OH, s * iy + 2 * s);
   const float* db = dout + (size_t)b * NC * OH * OW;
-  for (int i = threadIdx.x; i < NC * OW; i += blockDim.x) {
-    const int ox = i % OW, j = i / OW;
-    const float* col = db + (size_t)j * OH * OW + ox;
-    float acc = 0.f;
-    for (int oy = oy_lo; oy < oy_hi; ++oy) {
-      const float wy = bl_w(oy, iy, s, H);
-      if (wy != 0.f) acc = fmaf(wy, __ldg(col + (size_t)oy * OW), acc);
+  for (int j = threadIdx.x / 32; j < NC; j += blockDim.x / 32) {
+    const float* plane = db + (size_t)j * OH * OW;
+    for (int ox = threadIdx.x & 31; ox < OW; ox += 32) {
+      float acc = 0.f;
+      for (int oy = oy_lo; oy < oy_hi; ++oy) acc = fmaf(wys[oy - (s * iy - s)], __ldg(plane + (size_t)oy * OW + ox), acc);
+      ts[j * OW + ox] = acc;
     }
-    ts[i] = acc;
   }
   __syncthreads();
   __nv_bfloat16* orow = dz16 + ((size_t)b * H + iy) * W * 32;
@@ -486,10 +504,10 @@ cls_upsample_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restric
     const int j = i & 31, ix = i >> 5;
     float gsum = 0.f;
     if (j < NC) {
-      const int ox_lo = max(0, s * ix - s), ox_hi = min(OW, s * ix + 2 * s);
-      for (int ox = ox_lo; ox < ox_hi; ++ox) {
-        const float wx = bl_w(ox, ix, s, W);
-        if (wx != 0.f) gsum = fmaf(wx, ts[j * OW + ox], gsum);
+      const int o0 = s * ix - s;
+      for (int tp = 0; tp < taps; ++tp) {
+        const int ox = o0 + tp;
+        if (ox >= 0 && ox < OW) gsum = fmaf(wxs[ix * taps + tp], ts[j * OW + ox], gsum);
       }
     }
     orow[i] = __float2bfloat16_rn(gsum);
@@ -581,7 +599,7 @@ int s4_cls_bwd_apply_tc(const void* dz16, const void* y, const float* scale, con
 }
 
 int s4_cls_upsample_fwd(const float* z, float* logits, int B, int H, int W, int NC, int s, cudaStream_t st) {
-  const size_t smem = (size_t)2 * W * NC * 4;
+  const size_t smem = (size_t)2 * W * NC * 4 + (size_t)2 * W * s * 4;
   int rc;
   if ((rc = set_smem(cls_upsample_fwd_kernel, smem, "cls_upsample_fwd"))) return rc;
   cls_upsample_fwd_kernel<<<B * H * s, 256, smem, st>>>(z, logits, H, W, NC, s);
@@ -589,7 +607,7 @@ int s4_cls_upsample_fwd(const float* z, float* logits, int B, int H, int W, int 
 }
 
 int s4_cls_upsample_bwd(const float* dlogits, void* dz16, int B, int H, int W, int NC, int s, cudaStream_t st) {
-  const size_t smem = (size_t)NC * W * s * 4;
+  const size_t smem = (size_t)NC * W * s * 4 + (size_t)W * 3 * s * 4 + (size_t)3 * s * 4;
   int rc;
   if ((rc = set_smem(cls_upsample_bwd_kernel, smem, "cls_upsample_bwd"))) return rc;
   cls_upsample_bwd_kernel<<<B * H, 256, smem, st>>>(dlogits, (__nv_bfloat16*)dz16, H, W, NC, s);

@@ -7,6 +7,16 @@
 
 #define LN_MAX_VPL 8  // vectors per lane: D <= 32 lanes * 8 vec * 4 (f32) = 1024
 
+// parameters of the columns a lane owns (vector k of the lane = columns (lane + 32k) * VN ...)
+template <int VN>
+__device__ __forceinline__ void load_cols(const float* __restrict__ p, int vi, float (&out)[VN]) {
+#pragma unroll
+  for (int q = 0; q < VN / 4; ++q) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(p + vi * VN) + q);
+    out[4 * q] = f.x; out[4 * q + 1] = f.y; out[4 * q + 2] = f.z; out[4 * q + 3] = f.w;
+  }
+}
+
 template <typename T, int VPL>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const T* __restrict__ x, const int* __restrict__ row_map,
@@ -14,59 +24,73 @@ ln_fwd_kernel(const T* __restrict__ x, const int* __restrict__ row_map,
               float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int D,
               float eps) {
   constexpr int VN = Vec16<T>::N;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const int src = row_map ? row_map[warp] : warp;
-  const T* xr = x + (size_t)src * D;
   const int nvec = D / VN;
-  Vec16<T> v[VPL];
-  float sum = 0.f;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float gm[VPL][VN], bt[VPL][VN];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int vi = lane + k * 32;
     if (vi < nvec) {
-      v[k].load(xr + vi * VN);
-#pragma unroll
-      for (int e = 0; e < VN; ++e) sum += v[k].get(e);
+      load_cols<VN>(gamma, vi, gm[k]);
+      load_cols<VN>(beta, vi, bt[k]);
     }
   }
-  const float mean = warp_sum(sum) / (float)D;
-  float sq = 0.f;
+  const float inv_d = 1.f / (float)D;
+  for (int row = warp0; row < rows; row += nwarps) {
+    const int src = row_map ? row_map[row] : row;
+    const T* xr = x + (size_t)src * D;
+    Vec16<T> v[VPL];
+    float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int vi = lane + k * 32;
-    if (vi < nvec) {
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) v[k].load(xr + vi * VN);
+    }
 #pragma unroll
-      for (int e = 0; e < VN; ++e) {
-        const float d = v[k].get(e) - mean;
-        sq += d * d;
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
+#pragma unroll
+        for (int e = 0; e < VN; ++e) sum += v[k].get(e);
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
-  if (lane == 0) {
-    if (mean_out) mean_out[warp] = mean;
-    if (rstd_out) rstd_out[warp] = rstd;
-  }
-  T* yr = y + (size_t)warp * D;
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int vi = lane + k * 32;
-    if (vi < nvec) {
-      Vec16<T> o;
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
 #pragma unroll
-      for (int e = 0; e < VN; ++e) {
-        const int c = vi * VN + e;
-        o.set(e, (v[k].get(e) - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c));
+        for (int e = 0; e < VN; ++e) {
+          const float d = v[k].get(e) - mean;
+          sq = fmaf(d, d, sq);
+        }
       }
-      o.store(yr + vi * VN);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    T* yr = y + (size_t)row * D;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
+        Vec16<T> o;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) o.set(e, fmaf((v[k].get(e) - mean) * rstd, gm[k][e], bt[k][e]));
+        o.store(yr + vi * VN);
+      }
     }
   }
 }
 
-// dx (written at the mapped source row of a pre-zeroed buffer when row_map != null),
-// dgamma/dbeta accumulated with atomics (buffers must be zero-initialised or hold a running sum).
+// dx (written at the mapped source row of a pre-zeroed buffer when row_map != null).
+// dgamma/dbeta: every warp keeps register partials over its rows, the block folds them through
+// shared memory (plain stores, one slab per warp) and issues ONE global atomic per column.
 template <typename T, int VPL>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __restrict__ row_map,
@@ -74,78 +98,89 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
               const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D) {
   constexpr int VN = Vec16<T>::N;
-  extern __shared__ float sh[];  // [2][D]
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
+  extern __shared__ float sh[];  // [warps][2][D]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const int nvec = D / VN;
+  float gm[VPL][VN];
   float ag[VPL][VN], ab[VPL][VN];
 #pragma unroll
-  for (int k = 0; k < VPL; ++k)
+  for (int k = 0; k < VPL; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) load_cols<VN>(gamma, vi, gm[k]);
 #pragma unroll
     for (int e = 0; e < VN; ++e) { ag[k][e] = 0.f; ab[k][e] = 0.f; }
-  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+  }
+  const float inv_d = 1.f / (float)D;
+  for (int row = blockIdx.x * wpb + wib; row < rows; row += gridDim.x * wpb) {
     const int src = row_map ? row_map[row] : row;
     const T* xr = x + (size_t)src * D;
     const T* gr = dy + (size_t)row * D;
     const float mu = mean[row], rs = rstd[row];
-    Vec16<T> xv[VPL], gv[VPL];
-    float s1 = 0.f, s2 = 0.f;
+    Vec16<T> xv[VPL], gv[VPL], rv[VPL];
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int vi = lane + k * 32;
       if (vi < nvec) {
         xv[k].load(xr + vi * VN);
         gv[k].load(gr + vi * VN);
+        if (dres) rv[k].load(dres + (size_t)src * D + vi * VN);
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
 #pragma unroll
         for (int e = 0; e < VN; ++e) {
           const float xh = (xv[k].get(e) - mu) * rs;
           const float go = gv[k].get(e);
-          const float g = go * __ldg(gamma + vi * VN + e);
+          const float g = go * gm[k][e];
           s1 += g;
-          s2 += g * xh;
-          ag[k][e] += go * xh;
+          s2 = fmaf(g, xh, s2);
+          ag[k][e] = fmaf(go, xh, ag[k][e]);
           ab[k][e] += go;
         }
       }
     }
-    s1 = warp_sum(s1) / (float)D;
-    s2 = warp_sum(s2) / (float)D;
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
     T* dr = dx + (size_t)src * D;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int vi = lane + k * 32;
       if (vi < nvec) {
-        Vec16<T> o, rv;
-        if (dres) rv.load(dres + (size_t)src * D + vi * VN);
+        Vec16<T> o;
 #pragma unroll
         for (int e = 0; e < VN; ++e) {
           const float xh = (xv[k].get(e) - mu) * rs;
-          const float g = gv[k].get(e) * __ldg(gamma + vi * VN + e);
+          const float g = gv[k].get(e) * gm[k][e];
           float val = rs * (g - s1 - xh * s2);
-          if (dres) val += rv.get(e);
+          if (dres) val += rv[k].get(e);
           o.set(e, val);
         }
         o.store(dr + vi * VN);
       }
     }
   }
+  float* mine = sh + (size_t)wib * 2 * D;
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int vi = lane + k * 32;
     if (vi < nvec) {
 #pragma unroll
       for (int e = 0; e < VN; ++e) {
-        atomicAdd(&sh[vi * VN + e], ag[k][e]);
-        atomicAdd(&sh[D + vi * VN + e], ab[k][e]);
+        mine[vi * VN + e] = ag[k][e];
+        mine[D + vi * VN + e] = ab[k][e];
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    atomicAdd(dgamma + i, sh[i]);
-    atomicAdd(dbeta + i, sh[D + i]);
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
+    float acc = 0.f;
+    for (int w2 = 0; w2 < wpb; ++w2) acc += sh[(size_t)w2 * 2 * D + i];
+    atomicAdd((i < D ? dgamma : dbeta - D) + i, acc);
   }
 }
 
@@ -166,7 +201,9 @@ extern "C" int s4_layernorm_fwd(const void* x, const int* row_map, const float* 
   const int vn = dtype == S4_BF16 ? 8 : 4;
   S4_REQUIRE(D % vn == 0 && D / vn <= 32 * LN_MAX_VPL, "layernorm: unsupported D=%d", D);
   if (rows == 0) return S4_OK;
-  const int blocks = (rows + 7) / 8;
+  int blocks = (rows + 7) / 8;
+  const int fcap = s4_num_sms() * 8;
+  if (blocks > fcap) blocks = fcap;
   const int vpl = (D / vn + 31) / 32;
   if (dtype == S4_BF16) {
     LN_DISPATCH_VPL(vpl, (ln_fwd_kernel<__nv_bfloat16, VPL><<<blocks, 256, 0, stream>>>(
@@ -187,9 +224,19 @@ extern "C" int s4_layernorm_bwd(const void* dy, const void* x, const int* row_ma
   S4_REQUIRE(D % vn == 0 && D / vn <= 32 * LN_MAX_VPL, "layernorm: unsupported D=%d", D);
   if (rows == 0) return S4_OK;
   int blocks = (rows + 7) / 8;
-  const int cap = s4_num_sms() * 4;
+  const int cap = s4_num_sms() * 2;
   if (blocks > cap) blocks = cap;
-  const size_t smem = 2 * (size_t)D * sizeof(float);
+  const size_t smem = 8 * 2 * (size_t)D * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      attr_done = true;
+    }
+  }
   const int vpl = (D / vn + 31) / 32;
   if (dtype == S4_BF16) {
     LN_DISPATCH_VPL(vpl, (ln_bwd_kernel<__nv_bfloat16, VPL><<<blocks, 256, smem, stream>>>(
