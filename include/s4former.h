@@ -87,6 +87,11 @@ typedef struct S4GemmParams {
 int s4_gemm(const S4GemmParams* p, cudaStream_t stream);
 /* 1 if s4_gemm would run this problem on the tcgen05 path */
 int s4_gemm_uses_tc(const S4GemmParams* p);
+/* Tile policy of the tcgen05 path: 0 = single-CTA tiles only, 1 = cost model (default; also the
+ * S4_TC_PAIR environment variable), 2 = CTA-pair (cta_group::2, 256-row) tiles whenever the
+ * problem allows them.  Returns the previous mode.  A tuning / test knob: results are the same
+ * GEMM in every mode. */
+int s4_set_tc_pair_mode(int mode);
 
 /* ---- LayerNorm (+ row gather) ----------------------------------------------------------------
  * Replaces: ln1/ln2 (vit.py:119-120, eps 1e-6); head LayerNorm with the feature tap

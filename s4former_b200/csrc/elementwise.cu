@@ -135,11 +135,100 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ sum,
   if (sumsq) atomicAdd(sumsq + c, q);
 }
 
+// Vectorised version (cols % (16 B of T) == 0): a block owns a 32-vector column slab and a strip
+// of rows; each of its 8 warps walks every 8th row of the strip with 16-byte loads, 4 rows in
+// flight per thread; the warps fold through shared memory and the block issues one fp32 atomic
+// per column.  SQ selects the sum-of-squares output at compile time.
+template <typename T, bool SQ>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ sum, float* __restrict__ sumsq,
+                  size_t rows, int cols, int rows_per_blk) {
+  constexpr int VN = Vec16<T>::N;
+  __shared__ float sh[8][2][32 * VN + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + lane) * VN;
+  const bool col_ok = c0 < cols;
+  const size_t r0 = (size_t)blockIdx.y * rows_per_blk;
+  const size_t r1 = min(rows, r0 + rows_per_blk);
+  float s[VN], q[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) { s[e] = 0.f; q[e] = 0.f; }
+  if (col_ok) {
+    const T* xp = x + c0;
+    size_t r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      Vec16<T> v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u].load(xp + (r + 8 * u) * cols);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          const float f = v[u].get(e);
+          s[e] += f;
+          if (SQ) q[e] = fmaf(f, f, q[e]);
+        }
+    }
+    for (; r < r1; r += 8) {
+      Vec16<T> v;
+      v.load(xp + r * cols);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        const float f = v.get(e);
+        s[e] += f;
+        if (SQ) q[e] = fmaf(f, f, q[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    sh[warp][0][lane * VN + e] = s[e];
+    if (SQ) sh[warp][1][lane * VN + e] = q[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * VN; i += 256) {
+    const int c = blockIdx.x * 32 * VN + i;
+    if (c >= cols) continue;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += sh[w][0][i];
+      if (SQ) b += sh[w][1][i];
+    }
+    atomicAdd(sum + c, a);
+    if (SQ) atomicAdd(sumsq + c, b);
+  }
+}
+
+template <typename T>
+static void colsum_vec_launch(const void* x, float* sum, float* sumsq, long long rows, int cols,
+                              cudaStream_t stream) {
+  constexpr int VN = Vec16<T>::N;
+  const int gx = (cols + 32 * VN - 1) / (32 * VN);
+  int gy = (s4_num_sms() * 6 + gx - 1) / gx;
+  const long long max_gy = (rows + 31) / 32;          // at least 32 rows (4 per warp) per block
+  if ((long long)gy > max_gy) gy = (int)max_gy;
+  if (gy < 1) gy = 1;
+  const int rpb = (int)((rows + gy - 1) / gy);
+  gy = (int)((rows + rpb - 1) / rpb);
+  dim3 grid(gx, gy);
+  if (sumsq)
+    colsum_vec_kernel<T, true><<<grid, 256, 0, stream>>>((const T*)x, sum, sumsq, (size_t)rows, cols, rpb);
+  else
+    colsum_vec_kernel<T, false><<<grid, 256, 0, stream>>>((const T*)x, sum, nullptr, (size_t)rows, cols, rpb);
+}
+
 // sum / sumsq are ACCUMULATED (+=): zero them first when a fresh sum is wanted.
 extern "C" int s4_colsum(const void* x, float* sum, float* sumsq, long long rows, int cols,
                          int dtype, cudaStream_t stream) {
   S4ProfScope prof_("colsum", 0.0, 1, stream);
   if (rows == 0 || cols == 0) return S4_OK;
+  const int vn = dtype == S4_BF16 ? 8 : 4;
+  if (cols % vn == 0 && (((uintptr_t)x) & 15) == 0) {
+    if (dtype == S4_BF16) colsum_vec_launch<__nv_bfloat16>(x, sum, sumsq, rows, cols, stream);
+    else colsum_vec_launch<float>(x, sum, sumsq, rows, cols, stream);
+    return s4_check_launch("colsum");
+  }
   const int bx = 128;
   const int gx = (cols + bx - 1) / bx;
   int gy = (s4_num_sms() * 8 + gx - 1) / gx;

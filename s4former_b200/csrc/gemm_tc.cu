@@ -1,6 +1,13 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a: the tensor-core path behind s4_gemm, s4_conv3x3_* .
 //
-// One persistent, warp-specialised kernel (grid = #SMs, 1 CTA/SM):
+// One persistent, warp-specialised kernel (grid = #SMs, 1 CTA/SM), in two flavours:
+//   CT = 1  every CTA owns a 128 x BN tile (tcgen05.mma.cta_group::1)
+//   CT = 2  a CTA PAIR (cluster of 2 = one TPC) owns a 256 x BN tile: each CTA stages its own 128
+//           rows of A and HALF of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 for
+//           both, each CTA drains its own 128 x BN accumulator.  The L2 -> SM operand traffic per
+//           MMA cycle drops from (16 + BN/8) KB to (16 + BN/16) KB per k-block, which is what
+//           bounds these GEMMs (the fabric delivers ~43 B/clk/SM with all SMs pulling; profiles/).
+// Roles per CTA:
 //   warp 0      TMA producer   (cp.async.bulk.tensor.4d, 128B swizzle, mbarrier complete_tx)
 //   warp 1      MMA issuer     (one lane issues tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
 //   warp 2      TMEM allocator (2 accumulator stages of BN fp32 columns)
@@ -60,13 +67,20 @@ constexpr int EPI_WARP_BYTES = 8192;     // per epilogue warp: OUT[2] + X[2] box
 constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_WARP_BYTES;
 constexpr int BAR_BYTES = 1024;
 
-template <int BN>
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+template <int BN, int CT>
 struct Cfg {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int BN_CTA = BN / CT;                 // B rows staged by one CTA
+  static constexpr int B_STAGE_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
-  static constexpr int TMEM_COLS = BN == 256 ? 512 : (BN == 128 ? 256 : 128);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES + EPI_BYTES;
+  static constexpr int FIXED_BYTES = 1024 /*align*/ + BAR_BYTES + EPI_BYTES;
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr int TMEM_COLS = 2 * BN > 256 ? 512 : (2 * BN > 128 ? 256 : 128);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
+  static_assert(STAGES >= 3, "pipeline too shallow");
+  static_assert(BN % (64 * CT) == 0 || (BN % (16 * CT) == 0), "tile width");
 };
 
 __device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float* v) {
@@ -94,7 +108,8 @@ struct TileCoord {
   int m0, n0, z1, z2, kb0, kb1;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int BN) {
+// p.tiles_m counts CTA-GROUP tiles (128*CT rows); `rank` is the CTA's rank in its pair
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int BN, int CT, int rank) {
   TileCoord t;
   const int split = tile % p.splits;
   int r = tile / p.splits;
@@ -102,7 +117,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
   r /= p.tiles_n;
   const int mt = r % p.tiles_m;
   const int z = r / p.tiles_m;
-  t.m0 = mt * BM;
+  t.m0 = (mt * CT + rank) * BM;
   t.n0 = nt * BN;
   t.z1 = z / p.nb2;
   t.z2 = z % p.nb2;
@@ -111,12 +126,16 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
   return t;
 }
 
-template <int BN>
+template <int BN, int CT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
                const TcParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CT>;
+  constexpr bool PAIR = CT == 2;
+  const int rank = PAIR ? (int)tc::cluster_ctarank() : 0;
+  const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = tc::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;            // 1024-B aligned stage ring
@@ -149,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(tfull_bar(s), 1);
-      tc::mbar_init(tempty_bar(s), NUM_EPI_WARPS);
+      tc::mbar_init(tempty_bar(s), NUM_EPI_WARPS * CT);   // leader: both CTAs' epilogue warps
     }
     for (int w = 0; w < NUM_EPI_WARPS; ++w) {
       tc::mbar_init(xbar(w, 0), 1);
@@ -157,9 +176,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc::fence_barrier_init();
   }
-  if (warp == 2) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR) tc::tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    else tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
   tc::fence_before_sync();
-  __syncthreads();
+  if (PAIR) tc::cluster_sync();     // peer barriers initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -173,18 +196,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       const uint32_t a_bytes = (p.a_mode == OP_CONV_K) ? (uint32_t)(p.cTW * p.cTH * BK * 2)
                                                         : (uint32_t)A_STAGE_BYTES;
-      const uint32_t tx_bytes = a_bytes + (uint32_t)C::B_STAGE_BYTES;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, BN);
+      // pair mode: the leader's barrier counts the bytes landing in BOTH CTAs
+      const uint32_t tx_bytes = (a_bytes + (uint32_t)C::B_STAGE_BYTES) * CT;
+      auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+        if (PAIR) tc::tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
+        else tc::tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+      };
+      const int nb_off = rank * C::BN_CTA;          // this CTA's slice of the B tile
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const TileCoord t = decode_tile(p, tile, BN, CT, rank);
         if (p.a_mode == OP_KMAJOR && p.b_mode == OP_KMAJOR) {
           // ---- plain GEMM, both operands K-major (forward / dgrad linear layers) ----
           int k0 = t.kb0 * BK;
           for (int kb = t.kb0; kb < t.kb1; ++kb, k0 += BK) {
             tc::mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = base + stage * C::STAGE_BYTES;
-            tc::mbar_expect_tx(full_bar(stage), tx_bytes);
-            tc::tma_load_4d(sa, &tmA, full_bar(stage), k0, t.m0, t.z2, t.z1);
-            tc::tma_load_4d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), k0, t.n0, t.z2, t.z1);
+            if (rank == 0) tc::mbar_expect_tx(full_bar(stage), tx_bytes);
+            load(sa, &tmA, full_bar(stage), k0, t.m0, t.z2, t.z1);
+            load(sa + A_STAGE_BYTES, &tmB, full_bar(stage), k0, t.n0 + nb_off, t.z2, t.z1);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
           }
           continue;
@@ -221,16 +250,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
-          tc::mbar_expect_tx(full_bar(stage), tx_bytes);
+          if (rank == 0) tc::mbar_expect_tx(full_bar(stage), tx_bytes);
           // ---- A ----
           if (p.a_mode == OP_KMAJOR) {
-            tc::tma_load_4d(sa, &tmA, full_bar(stage), k0, t.m0, t.z2, t.z1);
+            load(sa, &tmA, full_bar(stage), k0, t.m0, t.z2, t.z1);
           } else if (p.a_mode == OP_MNMAJOR) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
-              tc::tma_load_4d(sa + j * (BK * 128), &tmA, full_bar(stage), t.m0 + 64 * j, k0, az2, az1);
+              load(sa + j * (BK * 128), &tmA, full_bar(stage), t.m0 + 64 * j, k0, az2, az1);
           } else {  // OP_CONV_K: k-block = (tap, 64-channel chunk)
-            tc::tma_load_4d(sa, &tmA, full_bar(stage), cblk * 64, cx0 + tx, cy0 + ty, cb);
+            load(sa, &tmA, full_bar(stage), cblk * 64, cx0 + tx, cy0 + ty, cb);
             if (++cblk == p.cblocks) {
               cblk = 0;
               if (++tx == 2) { tx = -1; ++ty; }
@@ -238,16 +267,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           // ---- B ----
           if (p.b_mode == OP_KMAJOR) {
-            tc::tma_load_4d(sb, &tmB, full_bar(stage), k0, t.n0, t.z2, t.z1);
+            load(sb, &tmB, full_bar(stage), k0, t.n0 + nb_off, t.z2, t.z1);
           } else if (p.b_mode == OP_MNMAJOR) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tc::tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(stage), t.n0 + 64 * j, k0, t.z2, t.z1);
+            for (int j = 0; j < C::BN_CTA / 64; ++j)
+              load(sb + j * (BK * 128), &tmB, full_bar(stage), t.n0 + nb_off + 64 * j, k0, t.z2, t.z1);
           } else {  // OP_CONV_MN (wgrad)
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tc::tma_load_4d(sb + j * (BK * 128), &tmB, full_bar(stage), t.n0 + 64 * j, wx + wdx,
-                              wy + wdy, wb);
+            for (int j = 0; j < C::BN_CTA / 64; ++j)
+              load(sb + j * (BK * 128), &tmB, full_bar(stage), t.n0 + nb_off + 64 * j, wx + wdx,
+                   wy + wdy, wb);
             wx += p.cTW;                      // cTW x cTH = 64 pixels per k-block
             if (wx >= p.cW) {
               wx = 0;
@@ -264,10 +293,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ONE thread runs the whole loop (tcgen05.mma / commit are single-thread instructions): no
     // per-k-block elect / warp sync, descriptors are built from precomputed constants with one
     // add per MMA, so the issue loop is far shorter than the MMAs it feeds.
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       const int a_mn = (p.a_mode == OP_MNMAJOR) ? 1 : 0;
       const int b_mn = (p.b_mode == OP_MNMAJOR || p.b_mode == OP_CONV_MN) ? 1 : 0;
-      const uint32_t idesc = tc::make_idesc_bf16(BM, BN, a_mn, b_mn);
+      const uint32_t idesc = tc::make_idesc_bf16(BM * CT, BN, a_mn, b_mn);
+      auto commit = [&](uint32_t bar) {
+        if (PAIR) tc::mma_commit_pair(bar);
+        else tc::mma_commit(bar);
+      };
       // descriptor = [hi: SBO 1024 B | version 1 | SWIZZLE_128B] [lo: LBO << 16 | addr >> 4]
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_lo_fixed = (a_mn ? (uint32_t)((BK * 128) >> 4) : 1u) << 16;
@@ -278,8 +311,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, BN);
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const TileCoord t = decode_tile(p, tile, BN, CT, rank);
         tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -294,11 +327,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * a_kstep);
             const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * b_kstep);
-            tc::mma_f16_ss(d_tmem, ad, bd, idesc, accum);
+            if (PAIR) tc::mma_f16_ss_pair(d_tmem, ad, bd, idesc, accum);
+            else tc::mma_f16_ss(d_tmem, ad, bd, idesc, accum);
             accum = 1;
           }
-          tc::mma_commit(empty_bar(stage));               // frees the smem slot when MMAs retire
-          if (kb == t.kb1 - 1) tc::mma_commit(tfull_bar(acc));   // accumulator ready
+          commit(empty_bar(stage));                       // frees the smem slot when MMAs retire
+          if (kb == t.kb1 - 1) commit(tfull_bar(acc));    // accumulator ready
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -326,8 +360,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int xi = 0, si = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile, BN);
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const TileCoord t = decode_tile(p, tile, BN, CT, rank);
       const int c_begin = half * CH_PER_WARP;
       const int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
       const int row0 = (t.m0 / BM) * p.row_pitch + quad * 32;
@@ -450,7 +484,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (PAIR) tc::mbar_arrive_leader(tempty_bar(acc));
+        else tc::mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tc::bulk_wait<0>();
@@ -463,8 +500,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile, BN);
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const TileCoord t = decode_tile(p, tile, BN, CT, rank);
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::fence_after_sync();
       const int row_in_tile = quad * 32 + lane;
@@ -563,16 +600,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (PAIR) tc::mbar_arrive_leader(tempty_bar(acc));
+        else tc::mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tc::fence_before_sync();
-  __syncthreads();
+  if (PAIR) tc::cluster_sync();     // no CTA leaves while its peer may still read / signal it
+  else __syncthreads();
   if (warp == 2) {
     tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (PAIR) tc::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -598,13 +640,14 @@ EncodeFn get_encode_fn() {
   return fn;
 }
 
-template <int BN>
+// p.tiles_m already counts CTA-group tiles (pairs for CT = 2)
+template <int BN, int CT>
 int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const CUtensorMap& txm,
               const TcParams& p, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) {
       s4_set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -613,16 +656,41 @@ int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
     attr_set = true;
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.nb * p.splits;
-  const int grid = (int)std::min<long long>(total, s4_num_sms());
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tcm, txm, p);
+  const int groups = (int)std::min<long long>(total, s4_num_sms() / CT);
+  if (CT == 1) {
+    gemm_tc_kernel<BN, CT><<<groups, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tcm, txm, p);
+    return s4_check_launch("gemm_tc");
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CT);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CT;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CT>, ta, tb, tcm, txm, p);
+  if (e != cudaSuccess) {
+    s4_set_error("gemm_tc: cluster launch failed: %s", cudaGetErrorString(e));
+    return S4_ERR_CUDA;
+  }
   return s4_check_launch("gemm_tc");
 }
 
-int launch_any(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm,
+int launch_any(int BN, int CT, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm,
                const CUtensorMap& txm, const TcParams& p, cudaStream_t stream) {
-  if (BN == 256) return launch_bn<256>(ta, tb, tcm, txm, p, stream);
-  if (BN == 128) return launch_bn<128>(ta, tb, tcm, txm, p, stream);
-  return launch_bn<64>(ta, tb, tcm, txm, p, stream);
+  if (CT == 2) {
+    if (BN == 256) return launch_bn<256, 2>(ta, tb, tcm, txm, p, stream);
+    if (BN == 192) return launch_bn<192, 2>(ta, tb, tcm, txm, p, stream);
+    return launch_bn<128, 2>(ta, tb, tcm, txm, p, stream);
+  }
+  if (BN == 256) return launch_bn<256, 1>(ta, tb, tcm, txm, p, stream);
+  if (BN == 128) return launch_bn<128, 1>(ta, tb, tcm, txm, p, stream);
+  return launch_bn<64, 1>(ta, tb, tcm, txm, p, stream);
 }
 
 // Tensor maps of the TMA-staged epilogue: C (and the one extra [M,N] operand) as
@@ -645,24 +713,59 @@ int make_epilogue_maps(CUtensorMap* tcm, CUtensorMap* txm, void* c, const void* 
   return rc;
 }
 
-int pick_bn(int M, int N, int nb, int splits) {
-  if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  const long long tm = (M + BM - 1) / BM;
+int g_pair_mode = -1;
+int env_pair_mode() {   // S4_TC_PAIR: 0 = never, 1 = cost model (default), 2 = whenever legal
+  if (g_pair_mode < 0) {
+    const char* e = getenv("S4_TC_PAIR");
+    g_pair_mode = e ? atoi(e) : 1;
+    if (g_pair_mode < 0 || g_pair_mode > 2) g_pair_mode = 1;
+  }
+  return g_pair_mode;
+}
+
+// Tile configuration by a small cost model.  A k-block of a CTA costs
+//   max( MMA time = 2*BN clk , operand bytes / ~43 B/clk )
+// (the second term is the measured L2 -> SM delivery rate with every SM pulling; it, not the tensor
+// pipe, bounds the 128-row tiles), a tile costs kb k-blocks plus a fixed bubble, and the launch costs
+// ceil(tiles / CTA groups) tiles.  b_chunked: B is staged as 64-wide MN boxes (wgrad), so a CTA's
+// share of the tile must be a multiple of 64 columns.
+struct TileCfg { int BN, CT; };
+
+TileCfg pick_cfg(long long m_tiles, int N, int kb, int nb, int splits, bool b_chunked, bool allow_pair) {
   const int sms = s4_num_sms();
-  auto eff = [&](int bn) {
-    const long long tiles = tm * ((N + bn - 1) / bn) * nb * splits;
-    const long long waves = (tiles + sms - 1) / sms;
-    // useful work / occupied tile slots (accounts for the N tail too)
-    return (double)((double)tm * N * nb * splits) / ((double)waves * sms * bn);
-  };
-  const double e256 = eff(256), e128 = eff(128);
-  return e256 >= 0.97 * e128 ? 256 : 128;
+  const double feed = 43.0;
+  TileCfg best{N <= 64 ? 64 : (N <= 128 ? 128 : 256), 1};
+  double best_cost = 1e30;
+  const int mode = env_pair_mode();
+  struct Cand { int BN, CT; };
+  const Cand cands[] = {{256, 1}, {128, 1}, {64, 1}, {256, 2}, {192, 2}, {128, 2}};
+  for (const Cand& c : cands) {
+    if (c.CT == 2 && (!allow_pair || mode == 0)) continue;
+    if (c.CT == 1 && mode == 2 && allow_pair && N > 64) continue;
+    if (c.BN == 64 && N > 64) continue;
+    if (c.BN == 128 && c.CT == 1 && N <= 64) continue;
+    if (c.BN >= 192 && N <= 128) continue;
+    if (c.CT == 2 && b_chunked && (c.BN / 2) % 64) continue;
+    const long long tiles = ((m_tiles + c.CT - 1) / c.CT) * ((N + c.BN - 1) / c.BN) * nb * splits;
+    const long long groups = sms / c.CT;
+    const long long waves = (tiles + groups - 1) / groups;
+    const double bytes = 16384.0 + (double)(c.BN / c.CT) * 128.0;
+    const double per_kb = std::max(2.0 * c.BN, bytes / feed);
+    const double cost = (double)waves * (kb * per_kb + 500.0) * (c.CT == 2 ? 1.02 : 1.0);
+    if (cost < best_cost) { best_cost = cost; best = TileCfg{c.BN, c.CT}; }
+  }
+  return best;
 }
 
 bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 }  // namespace
+
+extern "C" int s4_set_tc_pair_mode(int mode) {
+  const int prev = env_pair_mode();
+  if (mode >= 0 && mode <= 2) g_pair_mode = mode;
+  return prev;
+}
 
 int s4_make_tmap_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4],
                       const uint64_t strides_elems[3], const uint32_t box[4]) {
@@ -750,7 +853,8 @@ int s4_gemm_tc_launch(const S4GemmParams& g, cudaStream_t stream) {
   if (splits > kblocks) splits = kblocks;
   int kb_per = (kblocks + splits - 1) / splits;
   splits = (kblocks + kb_per - 1) / kb_per;
-  const int BN = pick_bn(g.M, g.N, nb, splits);
+  const TileCfg tcfg = pick_cfg((g.M + BM - 1) / BM, g.N, kb_per, nb, splits, b_mn, true);
+  const int BN = tcfg.BN, CT = tcfg.CT;
 
   CUtensorMap ta, tb;
   int rc;
@@ -768,11 +872,11 @@ int s4_gemm_tc_launch(const S4GemmParams& g, cudaStream_t stream) {
     const uint64_t inner = b_mn ? g.N : g.K, outer = b_mn ? g.K : g.N;
     const uint64_t dims[4] = {inner, outer, (uint64_t)g.nb2, (uint64_t)g.nb1};
     uint64_t s2[3] = {ld, g.nb2 > 1 ? (uint64_t)g.b_b2 : ld * 8, g.nb1 > 1 ? (uint64_t)g.b_b1 : ld * 8};
-    const uint32_t box[4] = {64, b_mn ? (uint32_t)BK : (uint32_t)BN, 1, 1};
+    const uint32_t box[4] = {64, b_mn ? (uint32_t)BK : (uint32_t)(BN / CT), 1, 1};
     if ((rc = s4_make_tmap_bf16(&tb, g.b, dims, s2, box))) return rc;
   }
   TcParams p{};
-  p.tiles_m = (g.M + BM - 1) / BM;
+  p.tiles_m = ((g.M + BM - 1) / BM + CT - 1) / CT;
   p.tiles_n = (g.N + BN - 1) / BN;
   p.nb = nb; p.nb2 = g.nb2; p.splits = splits;
   p.M = g.M; p.N = g.N;
@@ -797,7 +901,7 @@ int s4_gemm_tc_launch(const S4GemmParams& g, cudaStream_t stream) {
     p.accumulate = need_add ? 1 : 0;
   }
   S4ProfScope prof("gemm_tc", 2.0 * g.M * g.N * (double)g.K * nb, 0, stream);
-  return launch_any(BN, ta, tb, tcm, txm, p, stream);
+  return launch_any(BN, CT, ta, tb, tcm, txm, p, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -834,7 +938,10 @@ int s4_conv3x3_tc(const void* x, const void* w_packed, void* y, int B, int H, in
   }
   const int K = 9 * Cin;
   const int tiles_m = B * (H / TH) * (W / TW);
-  const int BN = pick_bn(tiles_m * BM, Cout, 1, 1);
+  // every CTA streams the same weight k-blocks in step (the L2 serves them once per wave), so the
+  // single-CTA tile is not feed-bound here: pairs are not used
+  const TileCfg tcfg = pick_cfg(tiles_m, Cout, 9 * (Cin / 64), 1, 1, false, false);
+  const int BN = tcfg.BN;
   CUtensorMap ta, tb;
   int rc;
   {
@@ -871,7 +978,7 @@ int s4_conv3x3_tc(const void* x, const void* w_packed, void* y, int B, int H, in
     p.tma_epi = 1;
   }
   S4ProfScope prof("conv3x3_tc", 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 0, stream);
-  return launch_any(BN, ta, tb, tcm, txm, p, stream);
+  return launch_any(BN, 1, ta, tb, tcm, txm, p, stream);
 }
 
 // dw[co][ci][tap] += sum_pix dy[pix][co] * x[pix+tap][ci]   (split over pixels, fp32 atomics)
@@ -889,6 +996,8 @@ int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, 
   const int TWk = W >= 64 ? 64 : W, THk = 64 / TWk;
   const int kblocks = (int)(P / 64);
   const int BN = Cin >= 256 ? 256 : (Cin >= 128 ? 128 : 64);
+  // CTA pairs: both 128-row halves of dy^T share the x window, each CTA stages half of it
+  const int CT = (env_pair_mode() != 0 && BN >= 128 && Cout % 256 == 0) ? 2 : 1;
   CUtensorMap ta, tb;
   int rc;
   {
@@ -905,7 +1014,7 @@ int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, 
     if ((rc = s4_make_tmap_bf16(&tb, x, dims, str, box))) return rc;
   }
   TcParams p{};
-  p.tiles_m = (Cout + BM - 1) / BM;
+  p.tiles_m = ((Cout + BM - 1) / BM + CT - 1) / CT;
   p.tiles_n = (Cin + BN - 1) / BN;
   p.nb = 9; p.nb2 = 9;
   const int base_tiles = p.tiles_m * p.tiles_n * 9;
@@ -924,5 +1033,5 @@ int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, 
   p.c_sm = (long long)Cin * 9; p.c_sn = 9; p.c_b1 = 0; p.c_b2 = 1;   // z2 = tap
   p.alpha = 1.f; p.c_f32 = 1; p.atomic = 1; p.accumulate = 1;
   S4ProfScope prof("conv3x3_wgrad_tc", 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 0, stream);
-  return launch_any(BN, ta, tb, ta, ta, p, stream);
+  return launch_any(BN, CT, ta, tb, ta, ta, p, stream);
 }

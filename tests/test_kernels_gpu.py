@@ -39,6 +39,24 @@ def test_library_loads_on_gpu():
     assert torch.cuda.get_device_capability(0)[0] == 10
 
 
+# ------------------------------------------------------------------------------------------ colsum
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-5), (torch.bfloat16, 1e-5)])
+@pytest.mark.parametrize('rows,cols', [(1, 8), (77, 768), (8200, 2304), (1000, 256), (33, 21), (4099, 3072)])
+def test_colsum_and_sumsq(dtype, tol, rows, cols):
+    """bias gradients / BatchNorm statistics: column sums (accumulating) of a row-major matrix."""
+    g = gen(3)
+    x = torch.randn(rows, cols, generator=g).to(DEV, dtype)
+    s = torch.full((cols,), 0.5, device=DEV)
+    q = torch.zeros(cols, device=DEV)
+    L.call('s4_colsum', x.data_ptr(), s.data_ptr(), q.data_ptr(), rows, cols, ops._code(dtype), ops._st())
+    xf = x.double()
+    assert rel(s, xf.sum(0) + 0.5) < tol
+    assert rel(q, (xf * xf).sum(0)) < tol
+    s2 = torch.zeros(cols, device=DEV)
+    L.call('s4_colsum', x.data_ptr(), s2.data_ptr(), None, rows, cols, ops._code(dtype), ops._st())
+    assert rel(s2, xf.sum(0)) < tol
+
+
 # ------------------------------------------------------------------------------------------ LN
 @pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
 @pytest.mark.parametrize('D', [128, 768])

@@ -30,6 +30,43 @@ def test_tc_is_selected():
     assert L.load().s4_gemm_uses_tc(ctypes.byref(g)) == 1
 
 
+@pytest.fixture(params=[1, 2], ids=['costmodel', 'pairs'])
+def pair_mode(request):
+    """Runs a test under the default tile policy and with CTA-pair (cta_group::2) tiles forced."""
+    prev = L.load().s4_set_tc_pair_mode(request.param)
+    yield request.param
+    L.load().s4_set_tc_pair_mode(prev)
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 256, 128), (300, 200, 72), (1025, 768, 768),
+                                   (2050, 2304, 768), (520, 3072, 768), (8200, 768, 3072), (130, 192, 4096)])
+def test_tc_gemm_kmajor_pairs(M, N, K):
+    prev = L.load().s4_set_tc_pair_mode(2)
+    try:
+        _gemm_case(M, N, K, BF, L.BACKEND_TC)
+        _gemm_case(M, N, K, BF, L.BACKEND_TC, bias=True, res=True)
+    finally:
+        L.load().s4_set_tc_pair_mode(prev)
+
+
+def test_tc_gemm_pairs_layouts_and_splitk():
+    prev = L.load().s4_set_tc_pair_mode(2)
+    try:
+        _gemm_case(300, 256, 128, BF, L.BACKEND_TC, bias=True, act=True)
+        _gemm_case(300, 256, 128, BF, L.BACKEND_TC, aux=True)
+        _gemm_case(260, 136, 192, BF, L.BACKEND_TC, c32=True, accumulate=True, alpha=0.5)
+        _gemm_case(200, 136, 136, BF, L.BACKEND_TC, batch=(2, 3))
+        _gemm_case(256, 128, 128, BF, L.BACKEND_TC, b_mn=True)
+        _gemm_case(300, 256, 200, BF, L.BACKEND_TC, b_mn=True)
+        _gemm_case(256, 128, 128, BF, L.BACKEND_TC, a_mn=True)
+        _gemm_case(200, 192, 264, BF, L.BACKEND_TC, a_mn=True)
+        _gemm_case(768, 768, 2048, BF, L.BACKEND_TC, a_mn=True, b_mn=True, c32=True, accumulate=True, split_k=8)
+        _gemm_case(3072, 768, 8200, BF, L.BACKEND_TC, a_mn=True, b_mn=True, c32=True, accumulate=True, split_k=6)
+        _gemm_case(136, 200, 1000, BF, L.BACKEND_TC, a_mn=True, b_mn=True, c32=True, accumulate=True, split_k=4)
+    finally:
+        L.load().s4_set_tc_pair_mode(prev)
+
+
 @pytest.mark.parametrize('M,N,K', [(128, 64, 64), (128, 128, 64), (128, 256, 128), (300, 200, 72),
                                    (1025, 768, 768), (2050, 2304, 768), (520, 3072, 768)])
 def test_tc_gemm_kmajor(M, N, K):
@@ -116,7 +153,7 @@ def test_tc_conv3x3_fwd_dgrad(B, H, W, Cin, Cout):
 
 
 @pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 32, 32, 128, 64), (1, 64, 64, 64, 256), (2, 128, 128, 256, 256)])
-def test_tc_conv3x3_wgrad(B, H, W, Cin, Cout):
+def test_tc_conv3x3_wgrad(B, H, W, Cin, Cout, pair_mode):
     x, dy, wf, wd, xr, wr, yr, st = _conv_case(B, H, W, Cin, Cout)
     dw = torch.zeros(Cout, Cin, 3, 3, device=DEV)
     L.call('s4_conv3x3_wgrad', x.data_ptr(), dy.data_ptr(), dw.data_ptr(), B, H, W, Cin, Cout, L.BF16, L.BACKEND_TC, st)

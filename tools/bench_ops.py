@@ -60,6 +60,35 @@ if what == 'fc1':
     w = torch.randn(4 * D, D, device=dev).to(BF)
     bias = torch.randn(4 * D, device=dev)
     timeit(lambda: ops.linear_fwd(a, w, bias), 2.0 * M * 4 * D * D, 'fc1 fwd bias')
+if what == 'kslope':
+    # one full wave of tiles, K swept: slope = steady-state time per k-block, intercept = fixed cost
+    lib = L.load()
+    Ms = 148 * 128
+    for mode in (0, 2):
+        lib.s4_set_tc_pair_mode(mode)
+        for N in (256, 512):
+            for K in (768, 1536, 3072, 6144):
+                a = torch.randn(Ms, K, device=dev).to(BF)
+                w = torch.randn(N, K, device=dev).to(BF)
+                timeit(lambda: ops.linear_fwd(a, w, None), 2.0 * Ms * N * K,
+                       f'[pair mode {mode}] M={Ms} N={N} K={K} kb={K // 64}')
+    lib.s4_set_tc_pair_mode(1)
+if what == 'gemm_modes':
+    lib = L.load()
+    for N, K, nm in ((3 * D, D, 'qkv'), (D, D, 'out_proj'), (4 * D, D, 'fc1'), (D, 4 * D, 'fc2')):
+        a = torch.randn(M, K, device=dev).to(BF)
+        w = torch.randn(N, K, device=dev).to(BF)
+        bias = torch.randn(N, device=dev)
+        dy = torch.randn(M, N, device=dev).to(BF)
+        wt = w.t().contiguous()
+        wp = torch.nn.Parameter(torch.randn(N, K, device=dev))
+        fl = 2.0 * M * N * K
+        for mode in (0, 1, 2):
+            lib.s4_set_tc_pair_mode(mode)
+            timeit(lambda: ops.linear_fwd(a, w, bias), fl, f'[pair mode {mode}] {nm} fwd bias')
+            timeit(lambda: ops.linear_dgrad(dy, wt), fl, f'[pair mode {mode}] {nm} dgrad')
+            timeit(lambda: ops.linear_wgrad(dy, a, wp, None), fl, f'[pair mode {mode}] {nm} wgrad')
+    lib.s4_set_tc_pair_mode(1)
 if what in ('gemm', 'all'):
     x = torch.randn(M, D, device=dev).to(BF)
     for N, K, nm in ((3 * D, D, 'qkv'), (D, D, 'out_proj'), (4 * D, D, 'fc1'), (D, 4 * D, 'fc2')):
