@@ -184,9 +184,13 @@ class VisionTransformer(nn.Module):
 
     def forward(self, inputs, no_pos_embed=False, avg_pos_emd=False, duplicate_pos_emd=False,
                 use_fdrop=False, attn_mask=None, attn_mask_weight=0.0, adaptive_attn_mask=False,
-                topk_idx=None):
+                topk_idx=None, attn_mask_rows=None):
         """vit.py:479-570.  Returns NCHW-shaped feature maps (channels-last views of the token
-        matrix, no copy); each carries ``_s4_tokens = (x2d, B, L)`` for the fused head."""
+        matrix, no copy); each carries ``_s4_tokens = (x2d, B, L)`` for the fused head.
+
+        ``attn_mask_rows=(b0, b1)``: ``attn_mask`` covers only images ``[b0, b1)`` of the batch
+        (the segmentor runs its student passes as ONE batch; the other images get a zero bias
+        row, which the attention kernels treat as "no bias")."""
         if no_pos_embed or avg_pos_emd or duplicate_pos_emd or use_fdrop:
             raise NotImplementedError('pos-embed ablations / fdrop are off in every shipped config')
         B = inputs.shape[0]
@@ -200,6 +204,16 @@ class VisionTransformer(nn.Module):
         u0 = gate = None
         if attn_mask is not None:
             u0, gate = self.pasa_bias_vectors(attn_mask, adaptive_attn_mask, topk_idx)
+            if attn_mask_rows is not None:
+                b0, b1 = attn_mask_rows
+                assert b1 - b0 == u0.shape[0] and 0 <= b0 and b1 <= B
+                u0_all = torch.zeros((B, L), dtype=u0.dtype, device=u0.device)
+                u0_all[b0:b1] = u0
+                u0 = u0_all
+                if gate is not None:
+                    gate_all = torch.ones((B, L), dtype=gate.dtype, device=gate.device)
+                    gate_all[b0:b1] = gate
+                    gate = gate_all
         outs = []
         for i, layer in enumerate(self.layers):
             x = layer(x, B, L, u0, gate, attn_mask_weight if u0 is not None else 0.0)

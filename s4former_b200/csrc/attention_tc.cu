@@ -162,11 +162,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     const bool q_ok = q < p.L;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
     const int t128 = threadIdx.x - 128;
-    const bool has_bias = p.u0 != nullptr;
+    bool has_bias = p.u0 != nullptr;
     if (has_bias) {
+      // an all-zero u0 row means "no bias for this image" (the batched student pass mixes biased
+      // and unbiased images): detect it while staging the row and take the cheaper path
       const float* ub = p.u0 + (size_t)b * p.L;
-      for (int i = t128; i < n_tiles * BKV; i += 128) u0s[i] = (i < p.L) ? ub[i] : 0.f;
-      tc::named_bar_sync(1, 128);
+      uint32_t nz = 0;
+      for (int i = t128; i < n_tiles * BKV; i += 128) {
+        const float v = (i < p.L) ? ub[i] : 0.f;
+        u0s[i] = v;
+        nz |= (v != 0.f) ? 1u : 0u;
+      }
+      uint32_t any;
+      asm volatile(
+          "{\n"
+          ".reg .pred p, q;\n"
+          "setp.ne.u32 q, %1, 0;\n"
+          "bar.red.or.pred p, 1, 128, q;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(any)
+          : "r"(nz)
+          : "memory");
+      has_bias = any != 0;
     }
     const float c1 = p.scale * LOG2E;
     float wgl = 0.f;

@@ -77,13 +77,14 @@ class SETRUPHead(BaseDecodeHead):
             nn.init.constant_(uc[0].bn.bias, 0.)
 
     # -- row map: dst token row -> src row of the backbone's [B*L, D] matrix ------------------
-    def _row_map(self, B, g, has_cls, device, PatchMix_N, PatchMixIndex):
+    def _row_map(self, B, g, has_cls, device, PatchMix_N, PatchMixIndex, b0=0):
         """Feature tap (+1 skips the cls row, vit.py:556-562) and, when PatchMix_N != 0, the
-        inverse block permutation of decode_head.py:186-212: out_block[perm[p]] = in_block[p]."""
+        inverse block permutation of decode_head.py:186-212: out_block[perm[p]] = in_block[p].
+        ``b0``: index of this group's first image in the backbone's token matrix."""
         Ls = g * g + (1 if has_cls else 0)
-        off = 1 if has_cls else 0
+        off = (1 if has_cls else 0) + b0 * Ls
         if PatchMix_N == 0:
-            key = (B, g, has_cls, str(device))
+            key = (B, g, has_cls, str(device), b0)
             m = self._row_maps.get(key)
             if m is None:
                 pos = torch.arange(g * g, dtype=torch.int64)
@@ -117,8 +118,10 @@ class SETRUPHead(BaseDecodeHead):
             raise NotImplementedError('return_last_feat is a visualisation path')
         x = self._transform_inputs(x)
         tok = getattr(x, '_s4_tokens', None)
+        b0 = 0
         if tok is not None:
-            x2d, B, L = tok
+            x2d, B, L = tok[:3]
+            b0 = tok[3] if len(tok) > 3 else 0
             g = int(math.isqrt(L - 1))
             has_cls = True
         else:   # a foreign NCHW tensor: flatten to tokens (copy) in the compute dtype
@@ -127,7 +130,7 @@ class SETRUPHead(BaseDecodeHead):
             g = h
             x2d = ops.cast(x.permute(0, 2, 3, 1).reshape(B * h * w, Cc).contiguous(), ops.compute_dtype())
             has_cls = False
-        row_map = self._row_map(B, g, has_cls, x2d.device, PatchMix_N, PatchMixIndex)
+        row_map = self._row_map(B, g, has_cls, x2d.device, PatchMix_N, PatchMixIndex, b0)
         Ltok = g * g + 1
         y = ops.HeadLNFn.apply(x2d, self, row_map, B, Ltok)
         H = W = g

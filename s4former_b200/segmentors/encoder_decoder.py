@@ -96,6 +96,10 @@ class EncoderDecoder(BaseSegmentor):
         self.attn_mask_seperate_head = attn_mask_seperate_head
         self._ema_tables = {}
         self._topk_override = None   # parity tests may inject the PASA top-k index set
+        # Run the three student backbone passes of the S4Former step (labeled, PASA, CutMix +
+        # PatchShuffle) as ONE batched pass (see _forward_train_batched).  False keeps the
+        # reference's pass-by-pass order.
+        self.batch_student_passes = True
 
     # ------------------------------------------------------------------ construction (:164-246)
     def _init_ema_model(self, pretrained, backbone_ema, decode_head_ema):
@@ -176,6 +180,10 @@ class EncoderDecoder(BaseSegmentor):
                 self.update_ema_variables(self.backbone, self.backbone_ema, self.momentum_backbone)
                 self.update_ema_variables(self.decode_head, self.decode_head_ema, self.momentum_head)
 
+        if self._can_batch_student_passes(data_groups, current_iter):
+            self.losses.update(self._forward_train_batched(data_groups))
+            return self.losses
+
         sup_imgs = sup_gts = None
         if 'sup' in data_groups:
             sup_imgs = data_groups['sup']['img']
@@ -200,6 +208,86 @@ class EncoderDecoder(BaseSegmentor):
             else:
                 self.losses.update(unsup_loss)
         return self.losses
+
+    # ------------------------------------------------------------------ batched student passes
+    def _can_batch_student_passes(self, data_groups, current_iter):
+        return (self.batch_student_passes and self.ema and self.attn_mask_seperate_head
+                and self.use_PatchShuffle_w_Cutmix and not self.use_CutMix
+                and 'sup' in data_groups and 'unsup_student' in data_groups
+                and 'unsup_teacher' in data_groups and self.unsup_weight != 0
+                and (self.iter_unsup_start == 0 or current_iter > self.iter_unsup_start)
+                and data_groups['sup']['img'].shape[1:] == data_groups['unsup_student']['img'].shape[1:])
+
+    @staticmethod
+    def _feature_group(feats, b0, nb):
+        """Images [b0, b0+nb) of a batched backbone output, as the per-pass tuple the heads take."""
+        outs = []
+        for f in feats:
+            x2d, _, L = f._s4_tokens[:3]
+            g = f[b0:b0 + nb]
+            g._s4_tokens = (x2d, nb, L, b0)
+            outs.append(g)
+        return tuple(outs)
+
+    def _forward_train_batched(self, data_groups):
+        """The S4Former-full step (forward_train :426-512 + foward_unsup_train :516-687) with the
+        three student backbone passes run as one batch [labeled | PASA | CutMix+PatchShuffle].
+
+        The passes share weights and are independent of each other (the teacher is the only
+        producer the unlabeled passes wait for), so batching them changes no value: same loss
+        keys, same head / SyncBN invocation order (statistics stay per pass), same host RNG call
+        order.  It cuts the kernel launches of the backbone by 3x and triples the rows of every
+        GEMM (M = 24 x 1025 instead of 3 launches of 8 x 1025)."""
+        sup = data_groups['sup']
+        teacher_data, student_data = data_groups['unsup_teacher'], data_groups['unsup_student']
+        sup_imgs, sup_gts = sup['img'], sup['gt_semantic_seg']
+        loss_unsup = {}
+        # ---- teacher (:519-542) ----
+        tnames = [meta['filename'] for meta in teacher_data['img_metas']]
+        snames = [meta['filename'] for meta in student_data['img_metas']]
+        tidx = [tnames.index(name) for name in snames]
+        with torch.no_grad():
+            self.set_eval(self.ema)
+            timg = teacher_data['img']
+            if tidx != list(range(len(tidx))):
+                timg = timg[torch.tensor(tidx, device=timg.device)]
+            tmetas = [teacher_data['img_metas'][idx] for idx in tidx]
+            teacher_info = self.extract_teacher_info_ema(timg, tmetas)
+            self.set_train(self.ema)
+        student_info = self.extract_student_info(**student_data)
+        attn_mask = self._patch_unconfidence(teacher_info, student_info)
+        # the PASA pass sees the un-mixed images / labels / metas (:547-567)
+        pasa_student = dict(student_info, img_metas=[dict(m) for m in student_info['img_metas']])
+        pasa_teacher = dict(teacher_info)
+        # ---- strong augmentation of the third pass (:633-638); host RNG order as the reference ----
+        if np.random.uniform(0, 1) < self.strong_aug_prob:
+            teacher_info, student_info = generate_unsup_cutmix_data(
+                teacher_info, student_info, ratio=self.cutout_area, patchwise=False)
+        student_info, teacher_info = generate_unsup_patchmix_data(
+            student_info, teacher_info, PatchMix_N=self.PatchMix_N, patchmix_ratio=self.patchmix_ratio)
+        # ---- one backbone pass ----
+        ns, nu = sup_imgs.shape[0], student_info['img'].shape[0]
+        imgs = torch.cat([sup_imgs, pasa_student['img'], student_info['img']], 0)
+        feats = self.backbone(imgs, attn_mask=attn_mask, attn_mask_weight=self.attn_mask_weight,
+                              adaptive_attn_mask=self.adaptive_attn_mask, topk_idx=self._topk_override,
+                              attn_mask_rows=(ns, ns + nu))
+        # ---- heads and losses, in the reference's order ----
+        losses = dict()
+        labeled_features = self._feature_group(feats, 0, ns)
+        loss_decode_sup = self._decode_head_forward_train(labeled_features, sup['img_metas'], sup_gts)
+        if self.with_auxiliary_head:
+            losses.update(self._auxiliary_head_forward_train(labeled_features, sup['img_metas'], sup_gts))
+        losses.update(loss_decode_sup)
+        pasa_student['backbone_feature'] = self._feature_group(feats, ns, nu)
+        loss_unsup['loss_seg_unsup_attn_mask'] = \
+            self.compute_pseudo_loss(pasa_student, pasa_teacher, want_ncr=False)['loss_seg_unsup'] * 0.5
+        student_info['backbone_feature'] = self._feature_group(feats, ns + nu, nu)
+        mixed = self.compute_pseudo_loss(student_info, teacher_info)
+        if self.negative_class_ranking:
+            loss_unsup['loss_ncr_unsup'] = mixed['loss_ncr_unsup'] * 0.5
+        loss_unsup['loss_seg_unsup'] = mixed['loss_seg_unsup'] * self.fdrop_loss_weight
+        losses.update(weighted_loss(loss_unsup, weight=self.unsup_weight))
+        return losses
 
     # ------------------------------------------------------------------ unsup branch (:516-687)
     def foward_unsup_train(self, teacher_data, student_data, sup_imgs, sup_gts):

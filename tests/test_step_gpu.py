@@ -27,10 +27,11 @@ def _build(variant):
     return m.to(DEV).train(), sd
 
 
-def _run(variant, dtype, topk=None):
+def _run(variant, dtype, topk=None, batched=True):
     ops.set_compute_dtype(dtype)
     try:
         m, sd = _build(variant)
+        m.batch_student_passes = batched
         img, gt, metas = gc.tiny_batch(variant)
         O.seed_host_rng(1999)
         m._topk_override = topk
@@ -94,6 +95,44 @@ def test_train_step_fp32_vs_reference_golden(golden_dir, variant):
         sm = [mm for mm in metas if mm['tag'] == 'unsup_student']
         for mm, p in zip(sm, G['perms']):
             assert torch.equal(torch.as_tensor(mm['PatchMixIndex']), torch.as_tensor(p))
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_batched_student_passes_equal_pass_by_pass(golden_dir, dtype, tol):
+    """The S4Former-full step runs its three student backbone passes as one batch; the
+    reference's pass-by-pass order (batch_student_passes=False) must give the same losses,
+    gradients, BN running statistics and PatchShuffle permutations.  The fp32 pass-by-pass run is
+    also held to the reference goldens."""
+    topk = _reference_topk('ours')
+    ma, la, _, metas_a = _run('ours', dtype, topk=topk, batched=True)
+    mb, lb, _, metas_b = _run('ours', dtype, topk=topk, batched=False)
+    assert list(la) == list(lb)
+    for k in la:
+        a, b = float(la[k]), float(lb[k])
+        assert abs(a - b) <= tol * abs(b) + 1e-6, (k, a, b)
+    na, nb = dict(ma.named_parameters()), dict(mb.named_parameters())
+    bad = []
+    for k, pb in nb.items():
+        if pb.grad is None:
+            assert na[k].grad is None, k
+            continue
+        r = float((na[k].grad - pb.grad).norm() / (pb.grad.norm() + 1e-12))
+        if r > (1e-4 if dtype == torch.float32 else 6e-2):
+            bad.append((k, r))
+    assert not bad, bad
+    sa, sb = ma.state_dict(), mb.state_dict()
+    for k in sb:
+        if 'running_' in k:
+            assert torch.allclose(sa[k], sb[k], rtol=1e-3 if dtype == torch.float32 else 3e-2, atol=1e-4), k
+    for x, y in zip(metas_a, metas_b):
+        if 'PatchMixIndex' in y:
+            assert torch.equal(torch.as_tensor(x['PatchMixIndex']), torch.as_tensor(y['PatchMixIndex']))
+    if dtype == torch.float32:
+        G = _golden(golden_dir, 'ours')
+        for k, v in G['losses'].items():
+            assert abs(float(lb[k]) - float(v)) <= 1e-3 * abs(float(v)) + 1e-6, k
+        for k, g in G['grads'].items():
+            assert float((nb[k].grad.cpu() - g).norm() / (g.norm() + 1e-12)) < 1e-3, k
 
 
 @pytest.mark.parametrize('variant', ['sup', 'ours'])
