@@ -230,6 +230,13 @@ int s4_ce_ncr(const float* logits_s, const float* logits_t, const long long* lab
               float* loss_out, const float* grad_scale, int B, int C, int H, int W,
               float ce_weight, float ncr_weight, int ignore_index, void* workspace,
               size_t ws_bytes, cudaStream_t stream);
+/* Gradient fix-up for a dlogits produced together with the losses (unit upstream gradients):
+ * applies the real upstream gradients grad_scale = (g_ce, g_ncr), read on the device -- nothing is
+ * touched when they are (1, 1), a rescale when equal, a recompute from the logits when they
+ * differ.  No host synchronisation. */
+int s4_ce_ncr_grad_fixup(const float* logits_s, const float* logits_t, const long long* label,
+                         float* dlogits, const float* grad_scale, int B, int C, int H, int W,
+                         float ce_weight, float ncr_weight, int ignore_index, cudaStream_t stream);
 int s4_scale_by_scalar(float* y, const float* scale_dev, size_t n, cudaStream_t stream);
 
 /* ---- augmentation (host RNG, device gathers) --------------------------------------------------

@@ -78,6 +78,7 @@ _SPEC = {
     's4_ce_ncr_workspace': (_Z, [_I, _I, _I]),
     's4_ce_ncr': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P, _Z, _P]),
     's4_scale_by_scalar': (_I, [_P, _P, _Z, _P]),
+    's4_ce_ncr_grad_fixup': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P]),
     's4_cutmix': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     's4_patchshuffle': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     's4_chunk_elems': (_I, []),

@@ -11,6 +11,8 @@
 //    (268 MB/img fp32) never exists; a 21-channel map is upsampled instead.
 //  * CUDA-core 3x3 convolutions here are the fp32 validation path; gemm_tc.cu holds the
 //    tcgen05 implicit-GEMM version.
+#include <algorithm>
+
 #include "common.cuh"
 
 // head_cls.cu: bf16 tensor-core kernels of the last stage
@@ -367,6 +369,83 @@ bn_relu_upsample_fwd_kernel(const T* __restrict__ x, const float* __restrict__ s
   }
 }
 
+// Block-structured version (the hot one): a thread owns (input pixel, 16-byte channel vector).
+// It loads the 3x3 clamped neighbourhood once, applies BN + ReLU once per loaded element and emits
+// the S x S output pixels that interpolate inside it.  With clamped neighbour coordinates the
+// border cases need no special weights: a clamped row/column is a copy of the centre one, so the
+// interior weights reproduce ATen's clamped source index.  32-bit index math only; a warp covers
+// one pixel's 512 contiguous bytes (C = 256, bf16) in every load and store.
+template <typename T, int S>
+__global__ void __launch_bounds__(256)
+bn_relu_upsample_fwd_blk_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                                const float* __restrict__ shift, T* __restrict__ out, int B, int H,
+                                int W, int C) {
+  constexpr int VN = Vec16<T>::N;
+  const int cv = C / VN, ppb = 256 / cv;
+  const int v = threadIdx.x % cv, pl = threadIdx.x / cv;
+  float sc[VN], sh[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) { sc[e] = __ldg(scale + v * VN + e); sh[e] = __ldg(shift + v * VN + e); }
+  const int xg = (W + ppb - 1) / ppb;
+  const int n_items = B * H * xg;
+  const int OW = W * S;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int xgi = item % xg;
+    const int r = item / xg;
+    const int iy = r % H, b = r / H;
+    const int ix = xgi * ppb + pl;
+    if (ix >= W) continue;
+    const int ys[3] = {max(iy - 1, 0), iy, min(iy + 1, H - 1)};
+    const int xs[3] = {max(ix - 1, 0), ix, min(ix + 1, W - 1)};
+    const T* base = x + (size_t)b * H * W * C + (size_t)v * VN;
+    float a[3][3][VN];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        Vec16<T> t;
+        t.load(base + ((size_t)ys[j] * W + xs[i]) * C);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) a[j][i][e] = fmaxf(fmaf(t.get(e), sc[e], sh[e]), 0.f);
+      }
+    T* obase = out + (((size_t)b * H * S + (size_t)iy * S) * OW + (size_t)ix * S) * C + (size_t)v * VN;
+#pragma unroll
+    for (int ry = 0; ry < S; ++ry) {
+      // source row = iy + (ry + 0.5)/S - 0.5: rows (iy-1, iy) for the upper half, (iy, iy+1) below
+      const int j0 = ry < S / 2 ? 0 : 1;
+      const float ly = (ry + 0.5f) / S - 0.5f + (ry < S / 2 ? 1.f : 0.f);
+#pragma unroll
+      for (int rx = 0; rx < S; ++rx) {
+        const int i0 = rx < S / 2 ? 0 : 1;
+        const float lx = (rx + 0.5f) / S - 0.5f + (rx < S / 2 ? 1.f : 0.f);
+        Vec16<T> o;
+#pragma unroll
+        for (int e = 0; e < VN; ++e)
+          o.set(e, (1.f - ly) * ((1.f - lx) * a[j0][i0][e] + lx * a[j0][i0 + 1][e]) +
+                       ly * ((1.f - lx) * a[j0 + 1][i0][e] + lx * a[j0 + 1][i0 + 1][e]));
+        o.store(obase + ((size_t)ry * OW + rx) * C);
+      }
+    }
+  }
+}
+
+template <typename T>
+static bool bn_relu_upsample_fwd_blk(const void* x, const float* scale, const float* shift, void* out,
+                                     int B, int H, int W, int C, int s, cudaStream_t stream) {
+  constexpr int VN = Vec16<T>::N;
+  const int cv = C / VN;
+  if ((s != 2 && s != 4) || cv > 256 || 256 % cv) return false;
+  const int ppb = 256 / cv;
+  const long long items = (long long)B * H * ((W + ppb - 1) / ppb);
+  if (items >= (1ll << 31) || (long long)B * H * W * s * s >= (1ll << 31)) return false;
+  const int grid = (int)std::min<long long>(items, (long long)s4_num_sms() * 16);
+  if (s == 2)
+    bn_relu_upsample_fwd_blk_kernel<T, 2><<<grid, 256, 0, stream>>>((const T*)x, scale, shift, (T*)out, B, H, W, C);
+  else
+    bn_relu_upsample_fwd_blk_kernel<T, 4><<<grid, 256, 0, stream>>>((const T*)x, scale, shift, (T*)out, B, H, W, C);
+  return true;
+}
+
 extern "C" int s4_bn_relu_upsample_fwd(const void* x, const float* scale, const float* shift,
                                        void* out, int B, int H, int W, int C, int s, int dtype,
                                        cudaStream_t stream) {
@@ -375,6 +454,10 @@ extern "C" int s4_bn_relu_upsample_fwd(const void* x, const float* scale, const 
   S4_REQUIRE(C % vn == 0 && s >= 1, "bn_relu_upsample: C=%d must be a multiple of %d", C, vn);
   const size_t total = (size_t)B * H * s * W * s * (C / vn);
   if (total == 0) return S4_OK;
+  const bool done = dtype == S4_BF16
+                        ? bn_relu_upsample_fwd_blk<__nv_bfloat16>(x, scale, shift, out, B, H, W, C, s, stream)
+                        : bn_relu_upsample_fwd_blk<float>(x, scale, shift, out, B, H, W, C, s, stream);
+  if (done) return s4_check_launch("bn_relu_upsample_fwd");
   const int grid = (int)min((total + 255) / 256, (size_t)s4_num_sms() * 32);
   if (dtype == S4_BF16)
     bn_relu_upsample_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
@@ -461,6 +544,116 @@ bn_relu_upsample_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x,
   }
 }
 
+// Block-structured backward: a thread owns (input pixel, channel vector).  Exactly 2S x 2S output
+// pixels carry weight for an input pixel (rows S*iy - S/2 .. S*iy + 3S/2 - 1); their weights are
+// evaluated once per thread (2 * 2S calls of bilinear_w, which knows ATen's border clamping) and
+// all 16-byte loads of a row are independent.  The per-channel BatchNorm-backward sums stay in
+// registers across a thread's pixels and are folded once per block.
+template <typename T, int S>
+__global__ void __launch_bounds__(256)
+bn_relu_upsample_bwd_blk_kernel(const T* __restrict__ dout, const T* __restrict__ x,
+                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                T* __restrict__ dact, float* __restrict__ dsum,
+                                float* __restrict__ ddot, int B, int H, int W, int C) {
+  constexpr int VN = Vec16<T>::N;
+  constexpr int NT = 2 * S;
+  extern __shared__ float sh[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int cv = C / VN, ppb = 256 / cv;
+  const int v = threadIdx.x % cv, pl = threadIdx.x / cv;
+  float sc[VN], sf[VN], mu[VN], is[VN], as[VN], ad[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    const int c = v * VN + e;
+    sc[e] = __ldg(scale + c); sf[e] = __ldg(shift + c); mu[e] = __ldg(mean + c); is[e] = __ldg(invstd + c);
+    as[e] = 0.f; ad[e] = 0.f;
+  }
+  const int xg = (W + ppb - 1) / ppb;
+  const int n_items = B * H * xg;
+  const int OH = H * S, OW = W * S;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int xgi = item % xg;
+    const int r = item / xg;
+    const int iy = r % H, b = r / H;
+    const int ix = xgi * ppb + pl;
+    if (ix >= W) continue;
+    const int oy0 = S * iy - S / 2, ox0 = S * ix - S / 2;
+    float wy[NT], wx[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int oy = oy0 + t, ox = ox0 + t;
+      wy[t] = (oy >= 0 && oy < OH) ? bilinear_w(oy, iy, S, H) : 0.f;
+      wx[t] = (ox >= 0 && ox < OW) ? bilinear_w(ox, ix, S, W) : 0.f;
+    }
+    float g[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) g[e] = 0.f;
+    const T* dbase = dout + (size_t)b * OH * OW * C + (size_t)v * VN;
+#pragma unroll
+    for (int ty = 0; ty < NT; ++ty) {
+      const int oy = min(max(oy0 + ty, 0), OH - 1);      // zero weight where clamped
+      Vec16<T> d[NT];
+#pragma unroll
+      for (int tx = 0; tx < NT; ++tx) {
+        const int ox = min(max(ox0 + tx, 0), OW - 1);
+        d[tx].load(dbase + ((size_t)oy * OW + ox) * C);
+      }
+#pragma unroll
+      for (int tx = 0; tx < NT; ++tx) {
+        const float wgt = wy[ty] * wx[tx];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) g[e] = fmaf(wgt, d[tx].get(e), g[e]);
+      }
+    }
+    const size_t pix = ((size_t)b * H + iy) * W + ix;
+    Vec16<T> xv, o;
+    xv.load(x + pix * C + (size_t)v * VN);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const float xe = xv.get(e);
+      const float da = fmaf(xe, sc[e], sf[e]) > 0.f ? g[e] : 0.f;
+      o.set(e, da);
+      as[e] += da;
+      ad[e] = fmaf(da, (xe - mu[e]) * is[e], ad[e]);
+    }
+    o.store(dact + pix * C + (size_t)v * VN);
+  }
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    atomicAdd(&sh[v * VN + e], as[e]);
+    atomicAdd(&sh[C + v * VN + e], ad[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dsum + i, sh[i]);
+    atomicAdd(ddot + i, sh[C + i]);
+  }
+}
+
+template <typename T>
+static bool bn_relu_upsample_bwd_blk(const void* dout, const void* x, const float* scale,
+                                     const float* shift, const float* mean, const float* invstd,
+                                     void* dact, float* dsum, float* ddot, int B, int H, int W, int C,
+                                     int s, cudaStream_t stream) {
+  constexpr int VN = Vec16<T>::N;
+  const int cv = C / VN;
+  if ((s != 2 && s != 4) || cv > 256 || 256 % cv) return false;
+  const int ppb = 256 / cv;
+  const long long items = (long long)B * H * ((W + ppb - 1) / ppb);
+  if (items >= (1ll << 31) || (long long)B * H * W * s * s >= (1ll << 31)) return false;
+  const int grid = (int)std::min<long long>(items, (long long)s4_num_sms() * 8);
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  if (s == 2)
+    bn_relu_upsample_bwd_blk_kernel<T, 2><<<grid, 256, smem, stream>>>(
+        (const T*)dout, (const T*)x, scale, shift, mean, invstd, (T*)dact, dsum, ddot, B, H, W, C);
+  else
+    bn_relu_upsample_bwd_blk_kernel<T, 4><<<grid, 256, smem, stream>>>(
+        (const T*)dout, (const T*)x, scale, shift, mean, invstd, (T*)dact, dsum, ddot, B, H, W, C);
+  return true;
+}
+
 extern "C" int s4_bn_relu_upsample_bwd(const void* dout, const void* x, const float* scale,
                                        const float* shift, const float* mean, const float* invstd,
                                        void* dact, float* dsum, float* ddot, int B, int H, int W,
@@ -470,6 +663,11 @@ extern "C" int s4_bn_relu_upsample_bwd(const void* dout, const void* x, const fl
   S4_REQUIRE(C % vn == 0 && s >= 1, "bn_relu_upsample_bwd: C=%d must be a multiple of %d", C, vn);
   const size_t total = (size_t)B * H * W * (C / vn);
   if (total == 0) return S4_OK;
+  const bool done =
+      dtype == S4_BF16
+          ? bn_relu_upsample_bwd_blk<__nv_bfloat16>(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, s, stream)
+          : bn_relu_upsample_bwd_blk<float>(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, s, stream);
+  if (done) return s4_check_launch("bn_relu_upsample_bwd");
   const int grid = (int)min((total + 255) / 256, (size_t)s4_num_sms() * 16);
   const size_t smem = 2 * (size_t)C * sizeof(float);
   if (dtype == S4_BF16)
@@ -483,7 +681,9 @@ extern "C" int s4_bn_relu_upsample_bwd(const void* dout, const void* x, const fl
   return s4_check_launch("bn_relu_upsample_bwd");
 }
 
-// dy = gamma*invstd*(dact - dsum/n - xhat*ddot/n)
+// dy = gamma*invstd*(dact - dsum/n - xhat*ddot/n) = A*dact + Bc*x + Cc with per-channel constants
+// kept in registers (the grid stride is a multiple of the vectors per row, so a thread keeps its
+// channel vector)
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dact, const T* __restrict__ x,
@@ -494,20 +694,29 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, const T* __restrict__ x,
   constexpr int VN = Vec16<T>::N;
   const int cv = C / VN;
   const size_t total = rows * cv;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int v = (int)(i % cv);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool fixed = stride % cv == 0;
+  float A[VN], Bc[VN], Cc[VN];
+  auto coeffs = [&](int v) {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const int c = v * VN + e;
+      const float is = __ldg(invstd + c), a = __ldg(gamma + c) * is;
+      const float k = is * __ldg(ddot + c) * inv_n;          // xhat*ddot/n = (x - mean) * k
+      A[e] = a;
+      Bc[e] = -a * k;
+      Cc[e] = a * (__ldg(mean + c) * k - __ldg(dsum + c) * inv_n);
+    }
+  };
+  if (fixed) coeffs((int)(i0 % cv));
+  for (size_t i = i0; i < total; i += stride) {
+    if (!fixed) coeffs((int)(i % cv));
     Vec16<T> d, xv, o;
     d.load(dact + i * VN);
     xv.load(x + i * VN);
 #pragma unroll
-    for (int e = 0; e < VN; ++e) {
-      const int c = v * VN + e;
-      const float is = __ldg(invstd + c);
-      const float xh = (xv.get(e) - __ldg(mean + c)) * is;
-      o.set(e, __ldg(gamma + c) * is *
-                   (d.get(e) - __ldg(dsum + c) * inv_n - xh * __ldg(ddot + c) * inv_n));
-    }
+    for (int e = 0; e < VN; ++e) o.set(e, fmaf(A[e], d.get(e), fmaf(Bc[e], xv.get(e), Cc[e])));
     o.store(dy + i * VN);
   }
 }

@@ -467,36 +467,55 @@ cls_upsample_fwd_kernel(const float* __restrict__ z, float* __restrict__ out, in
 }
 
 // transpose of the above into the padded bf16 layout the backward MMAs read: dz16 [B*H*W, 32].
-// One block per (image, source row): vertical taps straight from global (contiguous along x,
-// weights precomputed per block), the per-class row of partial sums staged in smem, then the
-// horizontal taps from a per-block weight table.
+// One block per (image, source row).  Exactly 2S output rows / columns carry weight for a source
+// row / column (S*i - S/2 .. S*i + 3S/2 - 1).  Phase 1 streams the 2S output rows of every class
+// with independent 16-byte loads (all taps of an item in flight) into a per-class row of vertical
+// partial sums in smem; phase 2 applies the 2S horizontal taps from a per-block weight table.
+template <int S>
 __global__ void __launch_bounds__(256)
 cls_upsample_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restrict__ dz16, int H, int W,
-                        int NC, int s) {
-  extern __shared__ __align__(16) float ts[];   // [NC][OW] partial sums, [W][3s] horizontal weights, [3s] vertical
-  const int OH = H * s, OW = W * s;
+                        int NC) {
+  constexpr int NT = 2 * S;
+  extern __shared__ __align__(16) float ts[];   // [NC][OW + 4] partial sums, [W][NT] horizontal weights, [NT] vertical
+  const int OH = H * S, OW = W * S;
+  const int TS = OW + 4;                        // row pitch: phase 2 reads a column across classes
   const int iy = blockIdx.x % H, b = blockIdx.x / H;
-  const int taps = 3 * s;
-  float* wxs = ts + NC * OW;
-  float* wys = wxs + W * taps;
-  for (int i = threadIdx.x; i < W * taps; i += blockDim.x) {
-    const int ix = i / taps, ox = s * ix - s + i % taps;
-    wxs[i] = (ox >= 0 && ox < OW) ? bl_w(ox, ix, s, W) : 0.f;
+  float* wxs = ts + NC * TS;
+  float* wys = wxs + W * NT;
+  for (int i = threadIdx.x; i < W * NT; i += blockDim.x) {
+    const int ix = i / NT, ox = S * ix - S / 2 + i % NT;
+    wxs[i] = (ox >= 0 && ox < OW) ? bl_w(ox, ix, S, W) : 0.f;
   }
-  if (threadIdx.x < taps) {
-    const int oy = s * iy - s + threadIdx.x;
-    wys[threadIdx.x] = (oy >= 0 && oy < OH) ? bl_w(oy, iy, s, H) : 0.f;
+  const int oy0 = S * iy - S / 2;
+  if (threadIdx.x < NT) {
+    const int oy = oy0 + threadIdx.x;
+    wys[threadIdx.x] = (oy >= 0 && oy < OH) ? bl_w(oy, iy, S, H) : 0.f;
   }
   __syncthreads();
-  const int oy_lo = max(0, s * iy - s), oy_hi = min(OH, s * iy + 2 * s);
+  float wy[NT];
+  size_t roff[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    wy[t] = wys[t];
+    roff[t] = (size_t)min(max(oy0 + t, 0), OH - 1) * OW;      // clamped rows carry zero weight
+  }
   const float* db = dout + (size_t)b * NC * OH * OW;
-  for (int j = threadIdx.x / 32; j < NC; j += blockDim.x / 32) {
-    const float* plane = db + (size_t)j * OH * OW;
-    for (int ox = threadIdx.x & 31; ox < OW; ox += 32) {
-      float acc = 0.f;
-      for (int oy = oy_lo; oy < oy_hi; ++oy) acc = fmaf(wys[oy - (s * iy - s)], __ldg(plane + (size_t)oy * OW + ox), acc);
-      ts[j * OW + ox] = acc;
+  const int ow4 = OW / 4;
+  for (int i = threadIdx.x; i < NC * ow4; i += blockDim.x) {
+    const int j = i / ow4, o4 = i % ow4;
+    const float* plane = db + (size_t)j * OH * OW + o4 * 4;
+    float4 d[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) d[t] = __ldg(reinterpret_cast<const float4*>(plane + roff[t]));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      acc.x = fmaf(wy[t], d[t].x, acc.x);
+      acc.y = fmaf(wy[t], d[t].y, acc.y);
+      acc.z = fmaf(wy[t], d[t].z, acc.z);
+      acc.w = fmaf(wy[t], d[t].w, acc.w);
     }
+    *reinterpret_cast<float4*>(ts + j * TS + o4 * 4) = acc;
   }
   __syncthreads();
   __nv_bfloat16* orow = dz16 + ((size_t)b * H + iy) * W * 32;
@@ -504,10 +523,11 @@ cls_upsample_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restric
     const int j = i & 31, ix = i >> 5;
     float gsum = 0.f;
     if (j < NC) {
-      const int o0 = s * ix - s;
-      for (int tp = 0; tp < taps; ++tp) {
-        const int ox = o0 + tp;
-        if (ox >= 0 && ox < OW) gsum = fmaf(wxs[ix * taps + tp], ts[j * OW + ox], gsum);
+      const int o0 = S * ix - S / 2;
+#pragma unroll
+      for (int tp = 0; tp < NT; ++tp) {
+        const int ox = min(max(o0 + tp, 0), OW - 1);
+        gsum = fmaf(wxs[ix * NT + tp], ts[j * TS + ox], gsum);
       }
     }
     orow[i] = __float2bfloat16_rn(gsum);
@@ -607,9 +627,22 @@ int s4_cls_upsample_fwd(const float* z, float* logits, int B, int H, int W, int 
 }
 
 int s4_cls_upsample_bwd(const float* dlogits, void* dz16, int B, int H, int W, int NC, int s, cudaStream_t st) {
-  const size_t smem = (size_t)NC * W * s * 4 + (size_t)W * 3 * s * 4 + (size_t)3 * s * 4;
+  if (s != 2 && s != 4) {
+    s4_set_error("cls_upsample_bwd: scale %d not supported (2 or 4)", s);
+    return S4_ERR_UNSUPPORTED;
+  }
+  if ((((uintptr_t)dlogits) & 15) != 0) {
+    s4_set_error("cls_upsample_bwd: dlogits must be 16-byte aligned");
+    return S4_ERR_ARG;
+  }
+  const size_t smem = (size_t)NC * (W * s + 4) * 4 + (size_t)W * 2 * s * 4 + (size_t)2 * s * 4;
   int rc;
-  if ((rc = set_smem(cls_upsample_bwd_kernel, smem, "cls_upsample_bwd"))) return rc;
-  cls_upsample_bwd_kernel<<<B * H, 256, smem, st>>>(dlogits, (__nv_bfloat16*)dz16, H, W, NC, s);
+  if (s == 2) {
+    if ((rc = set_smem(cls_upsample_bwd_kernel<2>, smem, "cls_upsample_bwd"))) return rc;
+    cls_upsample_bwd_kernel<2><<<B * H, 256, smem, st>>>(dlogits, (__nv_bfloat16*)dz16, H, W, NC);
+  } else {
+    if ((rc = set_smem(cls_upsample_bwd_kernel<4>, smem, "cls_upsample_bwd"))) return rc;
+    cls_upsample_bwd_kernel<4><<<B * H, 256, smem, st>>>(dlogits, (__nv_bfloat16*)dz16, H, W, NC);
+  }
   return s4_check_launch("cls_upsample_bwd");
 }

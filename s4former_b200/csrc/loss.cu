@@ -74,7 +74,15 @@ extern "C" int s4_pseudo_label(const float* logits, long long* hard, long long* 
 // ------------------------------------------------------------------------------------------
 // masked CE + NCR, forward + gradient in one pass
 // ------------------------------------------------------------------------------------------
-// partial[blk*3 + {0,1,2}] = sum nll, sum ncr distance, #valid for that block
+// partial[blk*3 + {0,1,2}] = sum nll, sum ncr distance, #valid for that block.
+// One pixel per thread, the C class planes are read with coalesced 128-byte warps and all C loads
+// of a pixel are in flight together.  exp / log / divide use the fast intrinsics (ex2.approx,
+// lg2.approx, rcp.approx: ~1e-6 relative, far inside the 1e-3 loss gate); the bit-exactness
+// contract (softmax-max > threshold) lives in pseudo_label_kernel, not here.
+// WRITE_DZ: also emit d(loss)/dz_s; HAS_T: NCR term against the teacher logits.
+// SKIP_IF_EQUAL: gradient fix-up launch -- returns at once unless gscale[0] != gscale[1]
+// (see s4_ce_ncr_grad_fixup).
+template <bool WRITE_DZ, bool HAS_T, bool SKIP_IF_EQUAL>
 __global__ void __launch_bounds__(256)
 ce_ncr_kernel(const float* __restrict__ zs, const float* __restrict__ zt,
               const long long* __restrict__ label, float* __restrict__ dz,
@@ -82,80 +90,114 @@ ce_ncr_kernel(const float* __restrict__ zs, const float* __restrict__ zt,
               float ncr_scale, int ignore_index, const float* __restrict__ gscale) {
   __shared__ float red[32];
   if (gscale) {   // upstream gradients of (loss_ce, loss_ncr), device resident: no host sync
-    ce_scale *= gscale[0];
-    ncr_scale *= gscale[1];
+    const float g0 = gscale[0], g1 = gscale[1];
+    if (SKIP_IF_EQUAL && g0 == g1) return;
+    ce_scale *= g0;
+    ncr_scale *= g1;
   }
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   float nll = 0.f, dist = 0.f, nvalid = 0.f;
   if (pix < npix) {
     const size_t b = pix / plane, r = pix % plane;
     const float* sp = zs + b * C * plane + r;
-    float* gp = dz ? dz + b * C * plane + r : nullptr;
     const long long y = label[pix];
     const bool valid = (y != ignore_index) && y >= 0 && y < C;
-    float v[S4_MAXC], g[S4_MAXC];
-    float m = -INFINITY;
+    const int yi = valid ? (int)y : -1;
+    float v[S4_MAXC], t[S4_MAXC];
+    float m = -INFINITY;      // max over all classes
+    float ms = -INFINITY;     // max over the negative classes (c != label)
 #pragma unroll
     for (int c = 0; c < S4_MAXC; ++c)
-      if (c < C) { v[c] = __ldg(sp + c * plane); m = fmaxf(m, v[c]); g[c] = 0.f; }
-    if (valid) {
-      float s = 0.f;
-#pragma unroll
-      for (int c = 0; c < S4_MAXC; ++c)
-        if (c < C) s += expf(v[c] - m);
-      const float logs = logf(s);
-      const float inv = 1.f / s;
-      nvalid = 1.f;
+      if (c < C) {
+        v[c] = __ldg(sp + c * plane);
+        m = fmaxf(m, v[c]);
+        if (c != yi) ms = fmaxf(ms, v[c]);
+      }
+    float mt = -INFINITY;
+    if (HAS_T) {
+      const float* tp = zt + b * C * plane + r;
 #pragma unroll
       for (int c = 0; c < S4_MAXC; ++c)
         if (c < C) {
-          if (c == (int)y) nll = -(v[c] - m - logs);
-          g[c] = ce_scale * (expf(v[c] - m) * inv - (c == (int)y ? 1.f : 0.f));
+          t[c] = __ldg(tp + c * plane);
+          if (c != yi) mt = fmaxf(mt, t[c]);
         }
-      if (zt != nullptr) {
-        // softmax over the C-1 negative classes, student and teacher
-        const float* tp = zt + b * C * plane + r;
-        float t[S4_MAXC];
-        float ms = -INFINITY, mt = -INFINITY;
+    }
+    float* gp = WRITE_DZ ? dz + b * C * plane + r : nullptr;
+    if (valid) {
+      nvalid = 1.f;
+      if (!HAS_T) {
+        float vy = 0.f, s = 0.f;
 #pragma unroll
         for (int c = 0; c < S4_MAXC; ++c)
           if (c < C) {
-            t[c] = __ldg(tp + c * plane);
-            if (c != (int)y) { ms = fmaxf(ms, v[c]); mt = fmaxf(mt, t[c]); }
+            if (c == yi) vy = v[c];
+            v[c] = __expf(v[c] - m);
+            s += v[c];
           }
-        float ss = 0.f, st = 0.f;
+        nll = m + __logf(s) - vy;
+        if (WRITE_DZ) {
+          const float k = ce_scale * __fdividef(1.f, s);
+#pragma unroll
+          for (int c = 0; c < S4_MAXC; ++c)
+            if (c < C) gp[c * plane] = fmaf(v[c], k, c == yi ? -ce_scale : 0.f);
+        }
+      } else {
+        // negatives are exponentiated against THEIR max (f_c = exp(v_c - ms), the NCR softmax of
+        // the C-1 negative classes is f_c / F exactly as the reference forms it); the CE softmax
+        // over all classes follows from s = F exp(ms - m) + exp(v_y - m) with both exponents <= 0.
+        float vy = 0.f, F = 0.f, st = 0.f;
 #pragma unroll
         for (int c = 0; c < S4_MAXC; ++c)
-          if (c < C && c != (int)y) { ss += expf(v[c] - ms); st += expf(t[c] - mt); }
-        const float is = 1.f / ss, it = 1.f / st;
+          if (c < C) {
+            if (c == yi) {
+              vy = v[c];
+            } else {
+              v[c] = __expf(v[c] - ms);
+              F += v[c];
+              t[c] = __expf(t[c] - mt);
+              st += t[c];
+            }
+          }
+        const float a = __expf(ms - m), ey = __expf(vy - m);
+        const float s = fmaf(F, a, ey);
+        nll = m + __logf(s) - vy;
+        const float inv = __fdividef(1.f, s);
+        const float iF = __fdividef(1.f, F), it = __fdividef(1.f, st);
         float sq = 0.f;
+        // t[c] <- d_c = p_c - q_c + eps   (torch PairwiseDistance eps, inside the norm)
 #pragma unroll
         for (int c = 0; c < S4_MAXC; ++c)
-          if (c < C && c != (int)y) {
-            const float p = expf(v[c] - ms) * is;
-            const float q = expf(t[c] - mt) * it;
-            const float d = p - q + 1e-6f;     // torch PairwiseDistance eps, inside the norm
-            sq += d * d;
-            v[c] = p;                          // reuse registers: v <- p, t <- d
+          if (c < C && c != yi) {
+            const float d = fmaf(v[c], iF, fmaf(-t[c], it, 1e-6f));
+            sq = fmaf(d, d, sq);
             t[c] = d;
           }
         dist = sqrtf(sq);
-        const float ir = 1.f / dist;
-        float dot = 0.f;
+        if (WRITE_DZ) {
+          const float ir = __fdividef(1.f, dist);
+          float dot = 0.f;
 #pragma unroll
-        for (int c = 0; c < S4_MAXC; ++c)
-          if (c < C && c != (int)y) dot += t[c] * ir * v[c];
+          for (int c = 0; c < S4_MAXC; ++c)
+            if (c < C && c != yi) dot = fmaf(t[c] * ir, v[c] * iF, dot);
+          const float k = ce_scale * inv * a;
 #pragma unroll
-        for (int c = 0; c < S4_MAXC; ++c)
-          if (c < C && c != (int)y) g[c] += ncr_scale * v[c] * (t[c] * ir - dot);
+          for (int c = 0; c < S4_MAXC; ++c)
+            if (c < C) {
+              float g;
+              if (c == yi) g = ce_scale * (ey * inv - 1.f);
+              else g = fmaf(ncr_scale * (v[c] * iF), fmaf(t[c], ir, -dot), v[c] * k);
+              gp[c * plane] = g;
+            }
+        }
       }
-    }
-    if (gp) {
+    } else if (WRITE_DZ) {
 #pragma unroll
       for (int c = 0; c < S4_MAXC; ++c)
-        if (c < C) gp[c * plane] = g[c];
+        if (c < C) gp[c * plane] = 0.f;
     }
   }
+  if (SKIP_IF_EQUAL) return;      // fix-up launches do not touch the loss partials
   const float a = block_sum(nll, red);
   const float bsum = block_sum(dist, red);
   const float cnt = block_sum(nvalid, red);
@@ -201,7 +243,8 @@ extern "C" size_t s4_ce_ncr_workspace(int B, int H, int W) {
 // loss_out[0] = ce_weight/P * sum_valid nll ; loss_out[1] = ncr_weight/P * sum_valid dist ;
 // loss_out[2] = number of valid pixels (loss_out may be null: gradient-only call).
 // dlogits (may be null) receives g0*d(loss0)/dz_s + g1*d(loss1)/dz_s with (g0,g1) = grad_scale
-// (device pointer to two floats, or null for (1,1)).
+// (device pointer to two floats, or null for (1,1)).  Losses and gradient may be requested in the
+// same call: the forward of a training step does, so the logits are streamed once.
 extern "C" int s4_ce_ncr(const float* logits_s, const float* logits_t, const long long* label,
                          float* dlogits, float* loss_out, const float* grad_scale, int B, int C,
                          int H, int W, float ce_weight, float ncr_weight, int ignore_index,
@@ -213,14 +256,66 @@ extern "C" int s4_ce_ncr(const float* logits_s, const float* logits_t, const lon
   S4_REQUIRE(ws_bytes >= s4_ce_ncr_workspace(B, H, W), "ce_ncr: workspace too small");
   const int nblk = (int)((npix + 255) / 256);
   const float P = (float)npix;
-  ce_ncr_kernel<<<nblk, 256, 0, stream>>>(logits_s, logits_t, label, dlogits, (float*)workspace, C,
-                                          (size_t)H * W, npix, ce_weight / P, ncr_weight / P,
-                                          ignore_index, grad_scale);
+  const size_t plane = (size_t)H * W;
+  const float cs = ce_weight / P, ns = ncr_weight / P;
+  float* part = (float*)workspace;
+  const bool has_t = logits_t != nullptr && ncr_weight != 0.f;
+#define S4_CE(WD, HT)                                                                               \
+  ce_ncr_kernel<WD, HT, false><<<nblk, 256, 0, stream>>>(logits_s, logits_t, label, dlogits, part, C, \
+                                                         plane, npix, cs, ns, ignore_index, grad_scale)
+  if (dlogits) {
+    if (has_t) S4_CE(true, true); else S4_CE(true, false);
+  } else {
+    if (has_t) S4_CE(false, true); else S4_CE(false, false);
+  }
+#undef S4_CE
   if (loss_out) s4_count_launches(1);
   if (loss_out)
-    ce_ncr_finalize_kernel<<<1, 256, 0, stream>>>((const float*)workspace, nblk, loss_out,
-                                                  ce_weight / P, ncr_weight / P);
+    ce_ncr_finalize_kernel<<<1, 256, 0, stream>>>((const float*)workspace, nblk, loss_out, cs, ns);
   return s4_check_launch("ce_ncr");
+}
+
+// dlogits *= g when the two upstream gradients are equal (the common case: the step's total loss
+// is a plain sum, g = (1, 1), and nothing is touched); recomputed from the logits when they differ.
+// Everything is decided on the device from grad_scale: no host synchronisation.
+__global__ void ce_ncr_rescale_kernel(float* __restrict__ y, const float* __restrict__ gscale,
+                                      int use_second, size_t n4, size_t n) {
+  const float s = gscale[0];
+  if (use_second && gscale[1] != s) return;     // the recompute launch handles it
+  if (s == 1.f) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float4* y4 = reinterpret_cast<float4*>(y);
+  for (size_t k = i; k < n4; k += stride) {
+    float4 v = y4[k];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    y4[k] = v;
+  }
+  for (size_t k = n4 * 4 + i; k < n; k += stride) y[k] *= s;
+}
+
+extern "C" int s4_ce_ncr_grad_fixup(const float* logits_s, const float* logits_t,
+                                    const long long* label, float* dlogits, const float* grad_scale,
+                                    int B, int C, int H, int W, float ce_weight, float ncr_weight,
+                                    int ignore_index, cudaStream_t stream) {
+  S4ProfScope prof_("ce_ncr_fixup", 0.0, 1, stream);
+  S4_REQUIRE(C >= 1 && C <= S4_MAXC, "ce_ncr: C=%d not in [1,%d]", C, S4_MAXC);
+  S4_REQUIRE(grad_scale != nullptr && dlogits != nullptr, "ce_ncr_grad_fixup: null argument");
+  const size_t npix = (size_t)B * H * W;
+  if (npix == 0) return S4_OK;
+  const bool has_t = logits_t != nullptr && ncr_weight != 0.f;
+  const size_t n = npix * C;
+  const int grid = s4_num_sms() * 8;
+  ce_ncr_rescale_kernel<<<grid, 256, 0, stream>>>(dlogits, grad_scale, has_t ? 1 : 0, n / 4, n);
+  if (has_t) {
+    s4_count_launches(1);
+    const int nblk = (int)((npix + 255) / 256);
+    const float P = (float)npix;
+    ce_ncr_kernel<true, true, true><<<nblk, 256, 0, stream>>>(
+        logits_s, logits_t, label, dlogits, nullptr, C, (size_t)H * W, npix, ce_weight / P,
+        ncr_weight / P, ignore_index, grad_scale);
+  }
+  return s4_check_launch("ce_ncr_grad_fixup");
 }
 
 // y[i] *= *scale   (upstream gradient of a scalar loss applied to a saved gradient)

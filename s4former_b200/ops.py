@@ -555,7 +555,11 @@ class ConvBNReLUClsUpFn(torch.autograd.Function):
 # losses / pseudo labels / augmentation / EMA
 # ----------------------------------------------------------------------------------------------
 class CeNcrFn(torch.autograd.Function):
-    """(loss_ce, loss_ncr) = (w_ce/P * sum_valid nll, w_ncr/P * sum_valid ||p_s - p_t + eps||)."""
+    """(loss_ce, loss_ncr) = (w_ce/P * sum_valid nll, w_ncr/P * sum_valid ||p_s - p_t + eps||).
+
+    When the student logits require grad the forward launch also writes d(loss)/dz_s for unit
+    upstream gradients (the logits are streamed once per step instead of twice); backward applies
+    the real upstream gradients on the device (``s4_ce_ncr_grad_fixup``: a no-op for (1, 1))."""
 
     @staticmethod
     def forward(ctx, logits_s, logits_t, label, ce_w, ncr_w, ignore_index):
@@ -569,9 +573,11 @@ class CeNcrFn(torch.autograd.Function):
         out = torch.empty(3, dtype=torch.float32, device=logits_s.device)
         nbytes = L.load().s4_ce_ncr_workspace(B, H, W)
         ws = workspace(nbytes, logits_s.device, 'loss')
-        L.call('s4_ce_ncr', _p(logits_s), _p(logits_t), _p(label), None, _p(out), None, B, Cc, H, W,
+        dz = torch.empty_like(logits_s) if ctx.needs_input_grad[0] else None
+        L.call('s4_ce_ncr', _p(logits_s), _p(logits_t), _p(label), _p(dz), _p(out), None, B, Cc, H, W,
                float(ce_w), float(ncr_w), int(ignore_index), _p(ws), nbytes, _st())
         ctx.args = (float(ce_w), float(ncr_w), int(ignore_index))
+        ctx.dz = dz
         ctx.save_for_backward(logits_s, logits_t, label)
         return out[0], out[1], out[2]
 
@@ -581,13 +587,14 @@ class CeNcrFn(torch.autograd.Function):
         ce_w, ncr_w, ignore_index = ctx.args
         B, Cc, H, W = logits_s.shape
         dev = logits_s.device
+        dz = ctx.dz
+        if dz is None:
+            raise RuntimeError('CeNcrFn.backward called twice (the saved gradient buffer is consumed)')
+        ctx.dz = None
         gs = torch.stack([g_ce if g_ce is not None else torch.zeros((), device=dev),
                           g_ncr if g_ncr is not None else torch.zeros((), device=dev)]).float().contiguous()
-        dz = torch.empty_like(logits_s)
-        nbytes = L.load().s4_ce_ncr_workspace(B, H, W)
-        ws = workspace(nbytes, dev, 'loss')
-        L.call('s4_ce_ncr', _p(logits_s), _p(logits_t), _p(label), _p(dz), None, _p(gs), B, Cc, H, W,
-               ce_w, ncr_w, ignore_index, _p(ws), nbytes, _st())
+        L.call('s4_ce_ncr_grad_fixup', _p(logits_s), _p(logits_t), _p(label), _p(dz), _p(gs), B, Cc, H, W,
+               ce_w, ncr_w, ignore_index, _st())
         return dz, None, None, None, None, None
 
 

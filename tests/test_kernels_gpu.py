@@ -265,6 +265,47 @@ def test_conv_bn_relu_upsample_stage_fp32(s):
         ops.set_compute_dtype(torch.bfloat16)
 
 
+@pytest.mark.parametrize('dtype,tol', [(torch.bfloat16, 1e-2), (torch.float32, 1e-5)])
+@pytest.mark.parametrize('B,H,W,C,s', [(2, 16, 16, 256, 2), (1, 8, 24, 256, 4), (2, 5, 7, 64, 2), (1, 32, 32, 128, 2)])
+def test_bn_relu_upsample_kernels(dtype, tol, B, H, W, C, s):
+    """fused BN + ReLU + bilinear (and its transpose with the BatchNorm-backward sums) against
+    F.interpolate on the same inputs, incl. non-square maps and every border case."""
+    g = gen(9)
+    x = torch.randn(B, H, W, C, generator=g).to(DEV, dtype)
+    scale = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(C, generator=g) * 0.3).to(DEV)
+    mean = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    invstd = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    dout = torch.randn(B, H * s, W * s, C, generator=g).to(DEV, dtype)
+    st = ops._st()
+    dt = ops._code(dtype)
+    out = torch.empty(B, H * s, W * s, C, device=DEV, dtype=dtype)
+    L.call('s4_bn_relu_upsample_fwd', x.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(),
+           B, H, W, C, s, dt, st)
+    a = (x.float() * scale + shift).permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.interpolate(F.relu(a), scale_factor=s, mode='bilinear', align_corners=False)
+    assert rel(out.float().permute(0, 3, 1, 2), ref) < tol
+    ref.backward(dout.float().permute(0, 3, 1, 2))
+    dact = torch.empty_like(x)
+    sums = torch.zeros(2, C, device=DEV)
+    L.call('s4_bn_relu_upsample_bwd', dout.data_ptr(), x.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+           mean.data_ptr(), invstd.data_ptr(), dact.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(),
+           B, H, W, C, s, dt, st)
+    da_ref = a.grad.permute(0, 2, 3, 1)
+    assert rel(dact.float(), da_ref) < tol
+    xhat = (x.float() - mean) * invstd
+    assert rel(sums[0], da_ref.sum((0, 1, 2))) < max(tol, 1e-4)
+    assert rel(sums[1], (da_ref * xhat).sum((0, 1, 2))) < max(tol, 1e-4)
+    # BatchNorm backward apply on the same tensors
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    n = float(B * H * W)
+    dy = torch.empty_like(x)
+    L.call('s4_bn_bwd_apply', dact.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+           sums[0].data_ptr(), sums[1].data_ptr(), n, dy.data_ptr(), B * H * W, C, dt, st)
+    want = gamma * invstd * (dact.float() - sums[0] / n - xhat * sums[1] / n)
+    assert rel(dy.float(), want) < tol
+
+
 def test_conv_bn_relu_cls_upsample_stage_fp32():
     ops.set_compute_dtype(torch.float32)
     try:
@@ -331,6 +372,45 @@ def test_ce_ncr_golden_and_grad(golden_dir):
     assert rel(zs.grad, zr.grad) < 1e-4
     w = ops.cross_entropy(G['z_s'].to(DEV), hard, 0.4, 255)
     assert abs(float(w) - float(G['ce_w04'])) < 1e-5 * abs(float(G['ce_w04']))
+
+
+@pytest.mark.parametrize('g_ce,g_ncr,with_t', [(1.0, 1.0, True), (0.5, 0.5, True), (2.0, 0.25, True),
+                                               (1.0, 0.0, False), (0.4, 0.0, False)])
+def test_ce_ncr_fused_gradient_paths(golden_dir, g_ce, g_ncr, with_t):
+    """The forward launch also emits the gradient for unit upstream gradients; backward leaves it
+    alone (1,1), rescales it (equal) or recomputes it (different) -- all decided on the device."""
+    G = torch.load(os.path.join(golden_dir, 'loss_pseudo.pt'), weights_only=False)
+    zs = G['z_s'].to(DEV).requires_grad_(True)
+    hard = G['hard'].to(DEV)
+    zt = G['z_t'].to(DEV) if with_t else None
+    ce, ncr, _ = ops.CeNcrFn.apply(zs, zt, hard, 1.0, 1.0 if with_t else 0.0, 255)
+    (g_ce * ce + g_ncr * ncr).backward()
+    zr = G['z_s'].clone().requires_grad_(True)
+    lo = g_ce * O.cross_entropy_mean_all(zr, G['hard'])
+    if with_t:
+        lo = lo + g_ncr * O.ncr_unsup_only(zr, G['z_t'], G['hard'])
+    lo.backward()
+    assert rel(zs.grad, zr.grad) < 1e-4
+
+
+def test_ce_ncr_extreme_logits():
+    """label far above / far below the other classes: no overflow, no 0/0 in the NCR softmax."""
+    g = gen(11)
+    z = torch.randn(1, 21, 16, 32, generator=g)
+    zt = torch.randn(1, 21, 16, 32, generator=g)
+    y = torch.randint(0, 21, (1, 16, 32), generator=g)
+    z.scatter_(1, y[:, None], 150.0)           # the label dominates
+    z[:, :, 8:] = z[:, :, 8:] - 300.0 * torch.nn.functional.one_hot(y[:, 8:], 21).permute(0, 3, 1, 2)
+    zs = z.to(DEV).requires_grad_(True)
+    ce, ncr, _ = ops.CeNcrFn.apply(zs, zt.to(DEV), y.to(DEV), 1.0, 1.0, 255)
+    (ce + ncr).backward()
+    zr = z.clone().requires_grad_(True)
+    lo_ce, lo_ncr = O.cross_entropy_mean_all(zr, y), O.ncr_unsup_only(zr, zt, y)
+    (lo_ce + lo_ncr).backward()
+    assert torch.isfinite(zs.grad).all()
+    assert abs(float(ce) - float(lo_ce)) < 1e-4 * abs(float(lo_ce))
+    assert abs(float(ncr) - float(lo_ncr)) < 1e-4 * abs(float(lo_ncr)) + 1e-7
+    assert rel(zs.grad, zr.grad) < 1e-3
 
 
 def test_ce_known_answers_gpu():
