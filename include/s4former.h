@@ -81,7 +81,8 @@ typedef struct S4GemmParams {
   int c_dtype;         /* dtype of C */
   int backend;         /* S4_BACKEND_* */
   int split_k;         /* tcgen05 path: >1 splits K over CTAs and accumulates atomically
-                          into a float32 C (requires accumulate=1, c_dtype=f32, no epilogue) */
+                          into a float32 C (requires accumulate=1, c_dtype=f32, no epilogue);
+                          <0 lets the library pick the split count (same requirements) */
 } S4GemmParams;
 
 int s4_gemm(const S4GemmParams* p, cudaStream_t stream);
@@ -250,9 +251,11 @@ int s4_patchshuffle(const float* img, const long long* perm_dev, float* out, int
  * encoder_decoder.py:1044-1066 (t = m*t + (1-m)*s over all parameters and BN running stats) and
  * the SGD-momentum step mmcv's OptimizerHook drives.  Tables live in device memory. */
 int s4_chunk_elems(void);
-int s4_ema_multi_tensor(void* const* dst_ptrs, void* const* src_ptrs, const long long* sizes,
-                        const int* chunk_tensor, const long long* chunk_off, int n_chunks,
-                        float momentum, float one_minus_momentum, cudaStream_t stream);
+/* bf16_shadow (table of device pointers, entries or the table itself may be NULL): a bfloat16
+ * copy of dst refreshed in the same pass (the tensor-core kernels read weights from it). */
+int s4_ema_multi_tensor(void* const* dst_ptrs, void* const* src_ptrs, void* const* bf16_shadow,
+                        const long long* sizes, const int* chunk_tensor, const long long* chunk_off,
+                        int n_chunks, float momentum, float one_minus_momentum, cudaStream_t stream);
 int s4_sgd_multi_tensor(void* const* params, void* const* grads, void* const* bufs,
                         void* const* bf16_shadow, const long long* sizes, const float* lrs,
                         const int* chunk_tensor, const long long* chunk_off, int n_chunks,

@@ -332,14 +332,15 @@ struct S4TensorTable {
 #define S4_CHUNK 16384
 
 __global__ void __launch_bounds__(256)
-ema_multi_kernel(S4TensorTable t, float momentum, float one_minus) {
+ema_multi_kernel(S4TensorTable t, void* const* shadow, float momentum, float one_minus) {
   const int ti = t.chunk_tensor[blockIdx.x];
   const long long off = t.chunk_off[blockIdx.x];
   const long long n = min((long long)S4_CHUNK, t.size[ti] - off);
   float* dst = (float*)t.a[ti] + off;
   const float* src = (const float*)t.b[ti] + off;
+  __nv_bfloat16* sh = (shadow && shadow[ti]) ? (__nv_bfloat16*)shadow[ti] + off : nullptr;
   // chunk offsets are multiples of S4_CHUNK, tensor bases are 16B aligned (torch allocator)
-  const bool vec = ((((uintptr_t)dst) | ((uintptr_t)src)) & 15) == 0;
+  const bool vec = ((((uintptr_t)dst) | ((uintptr_t)src)) & 15) == 0 && (((uintptr_t)sh) & 7) == 0;
   if (vec) {
     const long long n4 = n / 4;
     for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
@@ -350,23 +351,35 @@ ema_multi_kernel(S4TensorTable t, float momentum, float one_minus) {
       d.z = fmaf(s.z, one_minus, d.z * momentum);
       d.w = fmaf(s.w, one_minus, d.w * momentum);
       reinterpret_cast<float4*>(dst)[i] = d;
+      if (sh) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(d.x, d.y), b = __floats2bfloat162_rn(d.z, d.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&a);
+        o.y = *reinterpret_cast<uint32_t*>(&b);
+        reinterpret_cast<uint2*>(sh)[i] = o;
+      }
     }
-    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x)
+    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
       dst[i] = fmaf(src[i], one_minus, dst[i] * momentum);
+      if (sh) sh[i] = __float2bfloat16_rn(dst[i]);
+    }
   } else {
-    for (long long i = threadIdx.x; i < n; i += blockDim.x)
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
       dst[i] = fmaf(src[i], one_minus, dst[i] * momentum);
+      if (sh) sh[i] = __float2bfloat16_rn(dst[i]);
+    }
   }
 }
 
 extern "C" int s4_ema_multi_tensor(void* const* dst_ptrs, void* const* src_ptrs,
-                                   const long long* sizes, const int* chunk_tensor,
-                                   const long long* chunk_off, int n_chunks, float momentum,
-                                   float one_minus_momentum, cudaStream_t stream) {
+                                   void* const* bf16_shadow, const long long* sizes,
+                                   const int* chunk_tensor, const long long* chunk_off,
+                                   int n_chunks, float momentum, float one_minus_momentum,
+                                   cudaStream_t stream) {
   S4ProfScope prof_("ema_multi_tensor", 0.0, 1, stream);
   if (n_chunks == 0) return S4_OK;
   S4TensorTable t{dst_ptrs, src_ptrs, nullptr, sizes, nullptr, chunk_tensor, chunk_off};
-  ema_multi_kernel<<<n_chunks, 256, 0, stream>>>(t, momentum, one_minus_momentum);
+  ema_multi_kernel<<<n_chunks, 256, 0, stream>>>(t, bf16_shadow, momentum, one_minus_momentum);
   return s4_check_launch("ema_multi_tensor");
 }
 
@@ -383,13 +396,36 @@ sgd_multi_kernel(S4TensorTable t, void* const* shadow, float mu, float wd, int f
   float* buf = (float*)t.c[ti] + off;
   __nv_bfloat16* sh = (shadow && shadow[ti]) ? (__nv_bfloat16*)shadow[ti] + off : nullptr;
   const float lr = t.scalar[ti];
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    float gi = g[i];
-    float pi = p[i];
+  auto upd = [&](float gi, float& pi, float& bi) {
     if (wd != 0.f) gi = fmaf(wd, pi, gi);
-    const float b = first_step ? gi : fmaf(mu, buf[i], gi);
-    buf[i] = b;
-    pi = fmaf(-lr, b, pi);
+    bi = first_step ? gi : fmaf(mu, bi, gi);
+    pi = fmaf(-lr, bi, pi);
+  };
+  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)buf)) & 15) == 0 && (((uintptr_t)sh) & 7) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 bv = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(buf)[i];
+    upd(gv.x, pv.x, bv.x);
+    upd(gv.y, pv.y, bv.y);
+    upd(gv.z, pv.z, bv.z);
+    upd(gv.w, pv.w, bv.w);
+    reinterpret_cast<float4*>(buf)[i] = bv;
+    reinterpret_cast<float4*>(p)[i] = pv;
+    if (sh) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(pv.x, pv.y), b = __floats2bfloat162_rn(pv.z, pv.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(sh)[i] = o;
+    }
+  }
+  for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+    float pi = p[i];
+    float bi = first_step ? 0.f : buf[i];
+    upd(g[i], pi, bi);
+    buf[i] = bi;
     p[i] = pi;
     if (sh) sh[i] = __float2bfloat16_rn(pi);
   }

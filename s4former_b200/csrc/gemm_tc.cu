@@ -729,12 +729,15 @@ int env_pair_mode() {   // S4_TC_PAIR: 0 = never, 1 = cost model (default), 2 = 
 // pipe, bounds the 128-row tiles), a tile costs kb k-blocks plus a fixed bubble, and the launch costs
 // ceil(tiles / CTA groups) tiles.  b_chunked: B is staged as 64-wide MN boxes (wgrad), so a CTA's
 // share of the tile must be a multiple of 64 columns.
-struct TileCfg { int BN, CT; };
+struct TileCfg { int BN, CT, splits; };
 
-TileCfg pick_cfg(long long m_tiles, int N, int kb, int nb, int splits, bool b_chunked, bool allow_pair) {
+// kblocks: k-blocks of the whole reduction.  splits > 0: fixed by the caller; splits == 0: chosen
+// here too (split-K weight gradients) -- a split count whose work items fill whole waves of CTA
+// groups beats "as many as possible" (e.g. 9 taps x 33 splits on 74 pairs is 4.01 waves).
+TileCfg pick_cfg(long long m_tiles, int N, int kblocks, int nb, int splits, bool b_chunked, bool allow_pair) {
   const int sms = s4_num_sms();
   const double feed = 43.0;
-  TileCfg best{N <= 64 ? 64 : (N <= 128 ? 128 : 256), 1};
+  TileCfg best{N <= 64 ? 64 : (N <= 128 ? 128 : 256), 1, splits > 0 ? splits : 1};
   double best_cost = 1e30;
   const int mode = env_pair_mode();
   struct Cand { int BN, CT; };
@@ -746,13 +749,22 @@ TileCfg pick_cfg(long long m_tiles, int N, int kb, int nb, int splits, bool b_ch
     if (c.BN == 128 && c.CT == 1 && N <= 64) continue;
     if (c.BN >= 192 && N <= 128) continue;
     if (c.CT == 2 && b_chunked && (c.BN / 2) % 64) continue;
-    const long long tiles = ((m_tiles + c.CT - 1) / c.CT) * ((N + c.BN - 1) / c.BN) * nb * splits;
+    const long long base = ((m_tiles + c.CT - 1) / c.CT) * ((N + c.BN - 1) / c.BN) * nb;
     const long long groups = sms / c.CT;
-    const long long waves = (tiles + groups - 1) / groups;
     const double bytes = 16384.0 + (double)(c.BN / c.CT) * 128.0;
     const double per_kb = std::max(2.0 * c.BN, bytes / feed);
-    const double cost = (double)waves * (kb * per_kb + 500.0) * (c.CT == 2 ? 1.02 : 1.0);
-    if (cost < best_cost) { best_cost = cost; best = TileCfg{c.BN, c.CT}; }
+    const int s_lo = splits > 0 ? splits : 1;
+    const int s_hi = splits > 0 ? splits : std::min(kblocks, 96);
+    for (int sp = s_lo; sp <= s_hi; ++sp) {
+      const int kb_per = (kblocks + sp - 1) / sp;
+      const int sp_eff = (kblocks + kb_per - 1) / kb_per;
+      const long long tiles = base * sp_eff;
+      const long long waves = (tiles + groups - 1) / groups;
+      // every extra split adds one fp32 reduce-add pass of the tile through L2
+      const double cost = (double)waves * (kb_per * per_kb + 500.0 + (sp_eff > 1 ? 700.0 : 0.0)) *
+                          (c.CT == 2 ? 1.02 : 1.0);
+      if (cost < best_cost) { best_cost = cost; best = TileCfg{c.BN, c.CT, sp_eff}; }
+    }
   }
   return best;
 }
@@ -838,8 +850,8 @@ bool s4_gemm_tc_supported(const S4GemmParams& p) {
   if ((p.aux && !aligned16(p.aux)) || (p.res && !aligned16(p.res)) || (p.pre && !aligned16(p.pre)))
     return false;
   if ((p.aux || p.res || p.pre) && p.c_sm % 8) return false;
-  if (p.split_k > 1 && !(p.accumulate && p.c_dtype == S4_F32 && !p.bias && !p.aux && !p.res &&
-                         !p.pre && p.act == S4_ACT_NONE))
+  if ((p.split_k > 1 || p.split_k < 0) && !(p.accumulate && p.c_dtype == S4_F32 && !p.bias && !p.aux &&
+                                            !p.res && !p.pre && p.act == S4_ACT_NONE))
     return false;
   if ((long long)p.nb1 * p.nb2 > 65535) return false;
   return true;
@@ -849,12 +861,15 @@ int s4_gemm_tc_launch(const S4GemmParams& g, cudaStream_t stream) {
   const bool a_mn = g.a_sk != 1, b_mn = g.b_sk != 1;
   const int nb = g.nb1 * g.nb2;
   const int kblocks = (g.K + BK - 1) / BK;
+  // split_k: > 1 fixed, 0 / 1 none, < 0 chosen by the cost model (split-K capable problems only)
   int splits = g.split_k > 1 ? g.split_k : 1;
   if (splits > kblocks) splits = kblocks;
+  const bool auto_split = g.split_k < 0;
+  const TileCfg tcfg = pick_cfg((g.M + BM - 1) / BM, g.N, kblocks, nb, auto_split ? 0 : splits, b_mn, true);
+  const int BN = tcfg.BN, CT = tcfg.CT;
+  splits = tcfg.splits;
   int kb_per = (kblocks + splits - 1) / splits;
   splits = (kblocks + kb_per - 1) / kb_per;
-  const TileCfg tcfg = pick_cfg((g.M + BM - 1) / BM, g.N, kb_per, nb, splits, b_mn, true);
-  const int BN = tcfg.BN, CT = tcfg.CT;
 
   CUtensorMap ta, tb;
   int rc;
@@ -1017,8 +1032,12 @@ int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, 
   p.tiles_m = ((Cout + BM - 1) / BM + CT - 1) / CT;
   p.tiles_n = (Cin + BN - 1) / BN;
   p.nb = 9; p.nb2 = 9;
+  // work items = taps x tiles x splits: fill whole waves of CTA groups (never a ragged last wave)
   const int base_tiles = p.tiles_m * p.tiles_n * 9;
-  int splits = (2 * s4_num_sms() + base_tiles - 1) / base_tiles;
+  const int groups = s4_num_sms() / CT;
+  int splits = groups / base_tiles;
+  if (splits < 1) splits = 1;
+  if (kblocks / splits > 512) splits = (2 * groups) / base_tiles;    // long reductions: two waves
   if (splits > kblocks) splits = kblocks;
   if (splits < 1) splits = 1;
   int kb_per = (kblocks + splits - 1) / splits;

@@ -17,6 +17,12 @@ __device__ __forceinline__ void load_cols(const float* __restrict__ p, int vi, f
   }
 }
 
+// pull a 16-byte chunk's line into L1 ahead of the iteration that loads it: a warp keeps only one
+// row in registers, so without this every row pays the full memory latency in sequence
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 template <typename T, int VPL>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const T* __restrict__ x, const int* __restrict__ row_map,
@@ -47,6 +53,15 @@ ln_fwd_kernel(const T* __restrict__ x, const int* __restrict__ row_map,
     for (int k = 0; k < VPL; ++k) {
       const int vi = lane + k * 32;
       if (vi < nvec) v[k].load(xr + vi * VN);
+    }
+    if (row + nwarps < rows) {
+      const int nsrc = row_map ? row_map[row + nwarps] : row + nwarps;
+      const T* nx = x + (size_t)nsrc * D;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nvec) prefetch_l1(nx + vi * VN);
+      }
     }
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
@@ -127,6 +142,21 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
         if (dres) rv[k].load(dres + (size_t)src * D + vi * VN);
       }
     }
+    {
+      const int nrow = row + gridDim.x * wpb;
+      if (nrow < rows) {
+        const int nsrc = row_map ? row_map[nrow] : nrow;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int vi = lane + k * 32;
+          if (vi < nvec) {
+            prefetch_l1(x + (size_t)nsrc * D + vi * VN);
+            prefetch_l1(dy + (size_t)nrow * D + vi * VN);
+            if (dres) prefetch_l1(dres + (size_t)nsrc * D + vi * VN);
+          }
+        }
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
@@ -201,15 +231,18 @@ extern "C" int s4_layernorm_fwd(const void* x, const int* row_map, const float* 
   const int vn = dtype == S4_BF16 ? 8 : 4;
   S4_REQUIRE(D % vn == 0 && D / vn <= 32 * LN_MAX_VPL, "layernorm: unsupported D=%d", D);
   if (rows == 0) return S4_OK;
-  int blocks = (rows + 7) / 8;
-  const int fcap = s4_num_sms() * 8;
+  // 4-warp blocks: the kernel holds gamma/beta in registers (~100 regs/thread), small blocks pack
+  // more warps per SM; ~5 rows per warp so the next-row prefetch has something to hide behind
+  constexpr int FT = 128;
+  int blocks = (rows + 3) / 4;
+  const int fcap = s4_num_sms() * 5;
   if (blocks > fcap) blocks = fcap;
   const int vpl = (D / vn + 31) / 32;
   if (dtype == S4_BF16) {
-    LN_DISPATCH_VPL(vpl, (ln_fwd_kernel<__nv_bfloat16, VPL><<<blocks, 256, 0, stream>>>(
+    LN_DISPATCH_VPL(vpl, (ln_fwd_kernel<__nv_bfloat16, VPL><<<blocks, FT, 0, stream>>>(
         (const __nv_bfloat16*)x, row_map, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, D, eps)));
   } else {
-    LN_DISPATCH_VPL(vpl, (ln_fwd_kernel<float, VPL><<<blocks, 256, 0, stream>>>(
+    LN_DISPATCH_VPL(vpl, (ln_fwd_kernel<float, VPL><<<blocks, FT, 0, stream>>>(
         (const float*)x, row_map, gamma, beta, (float*)y, mean, rstd, rows, D, eps)));
   }
   return s4_check_launch("layernorm_fwd");
@@ -223,10 +256,13 @@ extern "C" int s4_layernorm_bwd(const void* dy, const void* x, const int* row_ma
   const int vn = dtype == S4_BF16 ? 8 : 4;
   S4_REQUIRE(D % vn == 0 && D / vn <= 32 * LN_MAX_VPL, "layernorm: unsupported D=%d", D);
   if (rows == 0) return S4_OK;
-  int blocks = (rows + 7) / 8;
-  const int cap = s4_num_sms() * 2;
+  // 4-warp blocks (the kernel needs ~150 registers per thread: three fit per SM, two 8-warp
+  // blocks would not)
+  constexpr int BT = 128;
+  int blocks = (rows + 3) / 4;
+  const int cap = s4_num_sms() * 3;
   if (blocks > cap) blocks = cap;
-  const size_t smem = 8 * 2 * (size_t)D * sizeof(float);
+  const size_t smem = (BT / 32) * 2 * (size_t)D * sizeof(float);
   if (smem > 48 * 1024) {
     static bool attr_done = false;
     if (!attr_done) {
@@ -239,11 +275,11 @@ extern "C" int s4_layernorm_bwd(const void* dy, const void* x, const int* row_ma
   }
   const int vpl = (D / vn + 31) / 32;
   if (dtype == S4_BF16) {
-    LN_DISPATCH_VPL(vpl, (ln_bwd_kernel<__nv_bfloat16, VPL><<<blocks, 256, smem, stream>>>(
+    LN_DISPATCH_VPL(vpl, (ln_bwd_kernel<__nv_bfloat16, VPL><<<blocks, BT, smem, stream>>>(
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, row_map, gamma, mean, rstd,
         (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dgamma, dbeta, rows, D)));
   } else {
-    LN_DISPATCH_VPL(vpl, (ln_bwd_kernel<float, VPL><<<blocks, 256, smem, stream>>>(
+    LN_DISPATCH_VPL(vpl, (ln_bwd_kernel<float, VPL><<<blocks, BT, smem, stream>>>(
         (const float*)dy, (const float*)x, row_map, gamma, mean, rstd, (const float*)dres,
         (float*)dx, dgamma, dbeta, rows, D)));
   }

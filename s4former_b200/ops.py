@@ -91,14 +91,44 @@ def transpose2d(x):
     return y
 
 
+def _param_tag(p):
+    return (p._version, getattr(p, '_s4_gen', 0), p.data_ptr())
+
+
 def lowp(p):
-    """The weight in the compute dtype ([out, in] as stored)."""
-    return _cache(p, 'lp', lambda: cast(p.detach().reshape(p.shape[0], -1), compute_dtype()))
+    """The weight in the compute dtype ([out, in] as stored).
+
+    bf16: a persistent SHADOW buffer per parameter (stable address).  The fused SGD / EMA kernels
+    refresh it in the pass that updates the fp32 master (``shadow_ptrs`` / ``mark_shadows_fresh``),
+    so no per-step cast launches remain; any other in-place change of the parameter is detected
+    through its version tag and re-cast here."""
+    w2d = p.detach().reshape(p.shape[0], -1)
+    if compute_dtype() == torch.float32:
+        return w2d
+    _require_cuda(p)
+    sh = getattr(p, '_s4_shadow', None)
+    tag = _param_tag(p)
+    if sh is not None and getattr(p, '_s4_shadow_tag', None) == tag:
+        return sh
+    if sh is None:
+        sh = torch.empty(w2d.shape, dtype=torch.bfloat16, device=p.device)
+        p._s4_shadow = sh
+    src = w2d.contiguous()
+    L.call('s4_cast', _p(src), _p(sh), src.numel(), _code(src.dtype), L.BF16, _st())
+    p._s4_shadow_tag = tag
+    return sh
 
 
-def lowp_t(p):
-    """The transposed weight ([in, out]) in the compute dtype, for dgrad."""
-    return _cache(p, 'lpt', lambda: transpose2d(lowp(p)))
+def shadow_list(params):
+    """bf16 shadow buffers (or None) of ``params``, for the multi-tensor kernels."""
+    return [getattr(p, '_s4_shadow', None) for p in params]
+
+
+def mark_shadows_fresh(params):
+    """Call after a kernel that rewrote both the parameters and their shadows."""
+    for p in params:
+        if getattr(p, '_s4_shadow', None) is not None:
+            p._s4_shadow_tag = _param_tag(p)
 
 
 def conv_packed(p):
@@ -146,12 +176,11 @@ def gemm(a, b, c, M, N, K, a_str, b_str, c_sm, batch=(1, 1), a_bs=(0, 0), b_bs=(
 
 
 def _wgrad_split(M_out, N_out, K_red):
-    """split-K factor for weight gradients: enough CTAs to fill the machine."""
+    """split-K factor for weight gradients: -1 = chosen by the library's tile cost model together
+    with the tile shape (whole waves of CTA groups)."""
     if _cfg['wgrad_split_k']:
         return _cfg['wgrad_split_k']
-    tiles = ((M_out + 127) // 128) * ((N_out + 255) // 256)
-    kblocks = (K_red + 63) // 64
-    return max(1, min(kblocks, (2 * 148 + tiles - 1) // tiles))
+    return -1
 
 
 def linear_fwd(x, w_lp, bias, act=L.ACT_NONE, res=None, want_pre=False):
@@ -164,12 +193,13 @@ def linear_fwd(x, w_lp, bias, act=L.ACT_NONE, res=None, want_pre=False):
     return (y, pre) if want_pre else y
 
 
-def linear_dgrad(dy, w_lp_t, aux=None):
-    """dx = (dy @ w) * gelu'(aux) ; dy [M,N], w_lp_t [K,N] (transposed weight, K-major)."""
+def linear_dgrad(dy, w_lp, aux=None):
+    """dx = (dy @ w) * gelu'(aux) ; dy [M,N], w_lp [N,K] as stored: the weight is the MN-major B
+    operand of the GEMM, so no transposed copy is ever made."""
     M, N = dy.shape
-    K = w_lp_t.shape[0]
+    K = w_lp.shape[1]
     dx = torch.empty((M, K), dtype=dy.dtype, device=dy.device)
-    gemm(dy, w_lp_t, dx, M, K, N, (N, 1), (1, N), K, aux=aux)
+    gemm(dy, w_lp, dx, M, K, N, (N, 1), (K, 1), K, aux=aux)
     return dx
 
 
@@ -280,16 +310,16 @@ class EncoderLayerFn(torch.autograd.Function):
         fc1, fc2 = layer.ffn.layers[0][0], layer.ffn.layers[1]
         dy = dy.contiguous()
         # FFN
-        dpre = linear_dgrad(dy, lowp_t(fc2.weight), aux=pre)           # (dy W2) * gelu'(pre)
+        dpre = linear_dgrad(dy, lowp(fc2.weight), aux=pre)           # (dy W2) * gelu'(pre)
         linear_wgrad(dy, h, fc2.weight, fc2.bias)
-        dxl2 = linear_dgrad(dpre, lowp_t(fc1.weight))
+        dxl2 = linear_dgrad(dpre, lowp(fc1.weight))
         linear_wgrad(dpre, xl2, fc1.weight, fc1.bias)
         dxm = layernorm_bwd(dxl2, xm, layer.ln2.weight, layer.ln2.bias, mean2, rstd2, dres=dy)
         # attention block
-        datt = linear_dgrad(dxm, lowp_t(mha.out_proj.weight))
+        datt = linear_dgrad(dxm, lowp(mha.out_proj.weight))
         linear_wgrad(dxm, att, mha.out_proj.weight, mha.out_proj.bias)
         dqkv = attention_bwd(datt, qkv, att, lse, B, Ltok, H, hd, u0, gate, ctx.w)
-        dxl1 = linear_dgrad(dqkv, lowp_t(mha.in_proj_weight))
+        dxl1 = linear_dgrad(dqkv, lowp(mha.in_proj_weight))
         linear_wgrad(dqkv, xl1, mha.in_proj_weight, mha.in_proj_bias)
         dx = layernorm_bwd(dxl1, x, layer.ln1.weight, layer.ln1.bias, mean1, rstd1, dres=dxm)
         layer._s4_pending -= 1
@@ -644,8 +674,9 @@ class TensorTable:
         chunk = L.load().s4_chunk_elems()
         sizes = [t.numel() for t in lists[0]]
         for lst in lists:
-            assert [t.numel() for t in lst] == sizes
-        self.ptrs = [torch.tensor([t.data_ptr() for t in lst], dtype=torch.int64).to(device) for lst in lists]
+            assert [sizes[i] if t is None else t.numel() for i, t in enumerate(lst)] == sizes
+        self.ptrs = [torch.tensor([0 if t is None else t.data_ptr() for t in lst], dtype=torch.int64).to(device)
+                     for lst in lists]
         self.sizes = torch.tensor(sizes, dtype=torch.int64).to(device)
         ct, co = [], []
         for i, n in enumerate(sizes):
@@ -656,13 +687,15 @@ class TensorTable:
         self.chunk_off = torch.tensor(co, dtype=torch.int64).to(device)
         self.n_chunks = len(ct)
         self.lrs = None if lrs is None else torch.tensor(lrs, dtype=torch.float32).to(device)
-        self.key = tuple(t.data_ptr() for lst in lists for t in lst)
+        self.key = tuple(0 if t is None else t.data_ptr() for lst in lists for t in lst)
         self.keep = lists
 
 
 def ema_update(table, momentum):
-    """dst = m*dst + (1-m)*src over every tensor pair of the table (one launch)."""
-    L.call('s4_ema_multi_tensor', _p(table.ptrs[0]), _p(table.ptrs[1]), _p(table.sizes),
+    """dst = m*dst + (1-m)*src over every tensor pair of the table (one launch); a third list in
+    the table holds the bf16 shadows of dst refreshed in the same pass."""
+    shadow = table.ptrs[2] if len(table.ptrs) > 2 else None
+    L.call('s4_ema_multi_tensor', _p(table.ptrs[0]), _p(table.ptrs[1]), _p(shadow), _p(table.sizes),
            _p(table.chunk_tensor), _p(table.chunk_off), table.n_chunks, float(momentum),
            float(1 - momentum), _st())
     for t in table.keep[0]:

@@ -65,6 +65,7 @@ class FusedSGD:
         self.bufs = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
         self.steps = 0
         self._table = None
+        self._shadow_key = None
 
     def zero_grad(self):
         self.grads.zero()
@@ -75,13 +76,17 @@ class FusedSGD:
         return [poly_lr(self.base_lr * m, it, self.max_iters, self.power, self.min_lr) for m in self.lr_mult]
 
     def step(self, it=None):
-        if self._table is None:
+        shadows = ops.shadow_list(self.params)      # bf16 weight copies the GEMMs read
+        skey = tuple(0 if s is None else s.data_ptr() for s in shadows)
+        if self._table is None or self._shadow_key != skey:
             dev = self.params[0].device
             self._table = ops.TensorTable([[p.data for p in self.params], [p.grad for p in self.params],
-                                           self.bufs], dev, lrs=self.current_lrs(it))
+                                           self.bufs, shadows], dev, lrs=self.current_lrs(it))
             self._table.targets = self.params
+            self._shadow_key = skey
         ops.sgd_step(self._table, self.momentum, self.weight_decay, first_step=(self.steps == 0),
                      lrs=self.current_lrs(it))
         for p in self.params:
-            ops.bump_generation(p)
+            ops.bump_generation(p)                  # repacked conv weights are rebuilt lazily
+        ops.mark_shadows_fresh(self.params)         # ... the bf16 shadows were refreshed in the same pass
         self.steps += 1

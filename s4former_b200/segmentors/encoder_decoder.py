@@ -414,16 +414,19 @@ class EncoderDecoder(BaseSegmentor):
             if 'bn' in sn and 'num_batches_tracked' not in sn:
                 src.append(sb)
                 dst.append(tb)
-        ptr_key = tuple(t.data_ptr() for t in dst) + tuple(t.data_ptr() for t in src)
+        shadows = ops.shadow_list(dst)      # bf16 copies of the teacher weights, refreshed in the same pass
+        ptr_key = tuple(t.data_ptr() for t in dst) + tuple(t.data_ptr() for t in src) + \
+            tuple(0 if s is None else s.data_ptr() for s in shadows)
         if table is None or table.key != ptr_key:
             if not dst[0].is_cuda:
                 raise RuntimeError('s4former_b200 needs CUDA tensors: there is no CPU fallback')
-            table = ops.TensorTable([[t.data for t in dst], [t.data for t in src]], dst[0].device)
+            table = ops.TensorTable([[t.data for t in dst], [t.data for t in src], shadows], dst[0].device)
             table.targets = dst
             self._ema_tables[key] = table
         ops.ema_update(table, momentum)
         for t in table.targets:
             ops.bump_generation(t)
+        ops.mark_shadows_fresh(table.targets)
 
     def set_eval(self, ema=False):
         if not ema:

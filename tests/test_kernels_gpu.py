@@ -457,6 +457,53 @@ def test_ema_multi_tensor():
     ops.ema_update(table, 0.999)
     for d, w in zip(dst, want):
         assert torch.allclose(d, w, rtol=1e-6, atol=1e-7)
+    # with bf16 shadows (None = no shadow for that tensor), refreshed in the same pass
+    shadows = [torch.zeros(s, device=DEV, dtype=torch.bfloat16) if i != 1 else None for i, s in enumerate(shapes)]
+    want2 = [d.clone().mul_(0.5).add_(s, alpha=0.5) for d, s in zip(dst, src)]
+    table = ops.TensorTable([dst, src, shadows], DEV)
+    ops.ema_update(table, 0.5)
+    for d, w, sh in zip(dst, want2, shadows):
+        assert torch.allclose(d, w, rtol=1e-6, atol=1e-7)
+        if sh is not None:
+            assert torch.equal(sh, d.to(torch.bfloat16))
+
+
+def test_sgd_multi_tensor_with_shadows():
+    """fused SGD-momentum step (torch.optim.SGD semantics) + the bf16 weight shadows it refreshes."""
+    g = gen(12)
+    shapes = [(4099,), (64, 48), (16384 * 2 + 5,)]
+    ps = [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt = torch.optim.SGD(ref, lr=0.1, momentum=0.9, weight_decay=0.01)
+    bufs = [torch.zeros_like(p) for p in ps]
+    shadows = [torch.zeros(s, device=DEV, dtype=torch.bfloat16) if i != 0 else None for i, s in enumerate(shapes)]
+    for step in range(3):
+        grads = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+        for p, r, gr in zip(ps, ref, grads):
+            p.grad = gr.clone()
+            r.grad = gr.clone()
+        opt.step()
+        table = ops.TensorTable([[p.data for p in ps], [p.grad for p in ps], bufs, shadows], DEV, lrs=[0.1] * 3)
+        ops.sgd_step(table, 0.9, 0.01, first_step=(step == 0))
+        for p, r, sh in zip(ps, ref, shadows):
+            assert torch.allclose(p, r, rtol=1e-5, atol=1e-6)
+            if sh is not None:
+                assert torch.equal(sh, p.detach().to(torch.bfloat16))
+
+
+def test_weight_shadow_tracks_parameter_updates():
+    """ops.lowp: a persistent bf16 buffer, re-cast only when the parameter changed behind its back."""
+    p = torch.nn.Parameter(torch.randn(8, 16, device=DEV))
+    a = ops.lowp(p)
+    assert a.dtype == torch.bfloat16 and torch.equal(a, p.detach().to(torch.bfloat16))
+    assert ops.lowp(p).data_ptr() == a.data_ptr()
+    with torch.no_grad():
+        p.add_(1.0)                      # torch in-place op: version counter moves
+    b = ops.lowp(p)
+    assert b.data_ptr() == a.data_ptr() and torch.equal(b, p.detach().to(torch.bfloat16))
+    p.data.mul_(2.0)                     # raw change + explicit generation bump (what the kernels do)
+    ops.bump_generation(p)
+    assert torch.equal(ops.lowp(p), p.detach().to(torch.bfloat16))
 
 
 def test_patchify_and_tokens():

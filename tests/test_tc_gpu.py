@@ -117,6 +117,13 @@ def test_tc_gemm_a_mnmajor():
     _gemm_case(200, 72, 264, BF, L.BACKEND_TC, a_mn=True)
 
 
+@pytest.mark.parametrize('M,N,K', [(768, 768, 8200), (3072, 768, 24600), (768, 2304, 1000), (256, 256, 64)])
+def test_tc_gemm_auto_splitk(M, N, K, pair_mode):
+    """weight-gradient form (both operands MN-major, fp32 accumulate) with the split count chosen
+    by the library (split_k = -1)."""
+    _gemm_case(M, N, K, BF, L.BACKEND_TC, a_mn=True, b_mn=True, c32=True, accumulate=True, split_k=-1)
+
+
 def test_tc_gemm_ab_mnmajor_splitk():
     _gemm_case(256, 256, 512, BF, L.BACKEND_TC, a_mn=True, b_mn=True, c32=True, accumulate=True)
     _gemm_case(768, 768, 2048, BF, L.BACKEND_TC, a_mn=True, b_mn=True, c32=True, accumulate=True, split_k=8)

@@ -32,7 +32,7 @@ def timeit(fn, flops=None, name=''):
     print(f'{name:40s} {med * 1e3:9.1f} us (min {ts[0] * 1e3:.1f}){extra}', flush=True)
 
 
-B, H, Lt, hd = 8, 12, 1025, 64
+B, H, Lt, hd = int(os.environ.get('S4_BENCH_B', '8')), 12, 1025, 64
 D = H * hd
 M = B * Lt
 if what in ('attn_fwd', 'all'):
@@ -86,7 +86,7 @@ if what == 'gemm_modes':
         for mode in (0, 1, 2):
             lib.s4_set_tc_pair_mode(mode)
             timeit(lambda: ops.linear_fwd(a, w, bias), fl, f'[pair mode {mode}] {nm} fwd bias')
-            timeit(lambda: ops.linear_dgrad(dy, wt), fl, f'[pair mode {mode}] {nm} dgrad')
+            timeit(lambda: ops.linear_dgrad(dy, w), fl, f'[pair mode {mode}] {nm} dgrad')
             timeit(lambda: ops.linear_wgrad(dy, a, wp, None), fl, f'[pair mode {mode}] {nm} wgrad')
     lib.s4_set_tc_pair_mode(1)
 if what in ('gemm', 'all'):
@@ -104,7 +104,7 @@ if what in ('gemm', 'all'):
             timeit(lambda: ops.linear_fwd(a, w, bias, res=res), fl, f'{nm} fwd bias+res')
         dy = torch.randn(M, N, device=dev).to(BF)
         wt = w.t().contiguous()
-        timeit(lambda: ops.linear_dgrad(dy, wt), fl, f'{nm} dgrad')
+        timeit(lambda: ops.linear_dgrad(dy, w), fl, f'{nm} dgrad')
         wp = torch.nn.Parameter(torch.randn(N, K, device=dev))
         bp = torch.nn.Parameter(torch.randn(N, device=dev))
         timeit(lambda: ops.linear_wgrad(dy, a, wp, bp), fl, f'{nm} wgrad(+bias colsum)')
