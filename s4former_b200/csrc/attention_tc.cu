@@ -30,9 +30,10 @@ constexpr int BQ = 128;
 constexpr int BKV = 128;
 constexpr int HD = 64;
 constexpr int TILE_BYTES = 128 * HD * 2;   // 16 KB: 128 rows x 64 bf16, 128B-swizzled
-constexpr int FWD_THREADS = 256;
-constexpr int S_COL = 0;                    // TMEM columns: S fp32 [0,128), P bf16x2 [0,64)
+constexpr int FWD_THREADS = 384;
+constexpr int S_COL = 0;                    // TMEM columns: S fp32 [0,128)
 constexpr int O_COL = 128;                  // O fp32 [128,192)
+constexpr int P_COL = 192;                  // P bf16x2 [192,256)
 constexpr int TMEM_COLS = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -55,6 +56,24 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// FORWARD.  One CTA per (batch, head, 128-query tile); two CTAs are co-resident per SM so one
+// CTA's softmax overlaps the other's MMAs.  384 threads:
+//   warp 0      TMA producer: Q tile once, then K and V tiles (128 keys x 64) through two
+//               2-stage rings (cp.async.bulk.tensor.4d, 128B swizzle, zero fill past L)
+//   warp 1      MMA issuer + TMEM owner: S = Q K^T (128 x n x 64, SS) into TMEM cols [0,128);
+//               O += P V (128 x 64 x n, P read from TMEM cols [192,256), V from smem) into [128,192)
+//   warps 4-11  softmax, TWO threads per query row: warps 4-7 own key columns [0,64) of the tile,
+//               warps 8-11 columns [64,128) (a warp reaches the TMEM lanes 32*(warp%4)..+31, so warps
+//               w and w+4 share rows).  Halving the per-thread work halves the dependent chain
+//               tcgen05.ld -> max -> 64 x ex2 -> tcgen05.st that bounds a tile, and doubles the
+//               warps the MUFU / TMEM-load units can be kept busy from.  The two halves exchange
+//               their row maxima through shared memory (one 64-thread named barrier per tile), so
+//               both use the same reference maximum; online softmax in the log2 domain with LAZY
+//               rescaling (O is only rescaled when the running max grows by more than 2^8).
+// P lives in its own TMEM columns, so S(j+1) = Q K_{j+1}^T is issued right behind O += P_j V_j.
+// Register budget is moved from warps 0-3 to the softmax warps with setmaxnreg.
+// The key loop runs full 128-key tiles plus one tail tile of round_up(L % 128, 16) keys, so
+// L = 1025 (512^2 crops) costs 8 tiles + a 16-key MMA, not 9 tiles.
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -75,7 +94,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
   const uint32_t tmem_slot = bar + 8u * 12;
   uint8_t* gen = smem_raw + (base - raw);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 5 * TILE_BYTES + 8 * 12);
-  float* u0s = reinterpret_cast<float*>(gen + 5 * TILE_BYTES + 128);
+  float* xch = reinterpret_cast<float*>(gen + 5 * TILE_BYTES + 128);   // [2 parity][2 halves][128 rows]
+  float* u0s = xch + 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.q_tiles;
@@ -93,7 +113,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       tc::mbar_init(v_empty(s), 1);
     }
     tc::mbar_init(s_full, 1);
-    tc::mbar_init(p_full, 4);
+    tc::mbar_init(p_full, 8);
     tc::mbar_init(o_final, 1);
     tc::fence_barrier_init();
   }
@@ -104,7 +124,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
   const uint32_t tmem = *tmem_slot_ptr;
 
   if (warp < 4) {
-    tc::reg_dec<40>();
+    // register budget: the CTA is launched with 80 registers per thread (launch bounds 384 x 2);
+    // 128 threads x (80 - 32) released here = 256 threads x (104 - 80) claimed by the softmax warps
+    tc::reg_dec<32>();
     if (warp == 0 && lane == 0) {
       // ================================ TMA producer ========================================
       tc::mbar_expect_tx(q_full, TILE_BYTES);
@@ -119,56 +141,57 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
         tc::mbar_expect_tx(v_full(s), TILE_BYTES);
         tc::tma_load_4d(sV + s * TILE_BYTES, &tm_qkv, v_full(s), 0, j * BKV, 2 * p.H + h, b);
       }
-    } else if (warp == 1) {
-      // ================================ MMA issuer ==========================================
+    } else if (warp == 1 && lane == 0) {
+      // ================================ MMA issuer (one thread) =============================
       const uint32_t idesc_pv = tc::make_idesc_bf16(BQ, HD, 0, 1);
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        const int n = (j < p.n_full) ? BKV : p.tail_n;
+        tc::mbar_wait(k_full(s), (uint32_t)(j >> 1) & 1u);
+        tc::fence_after_sync();
+        const uint32_t idesc_s = tc::make_idesc_bf16(BQ, n, 0, 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          tc::mma_f16_ss(tmem + S_COL, tc::make_desc(sQ + k * 32, 16, 1024),
+                         tc::make_desc(sK + s * TILE_BYTES + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        tc::mma_commit(k_empty(s));
+        tc::mma_commit(s_full);
+      };
       tc::mbar_wait(q_full, 0);
+      issue_qk(0);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
         const int n = (j < p.n_full) ? BKV : p.tail_n;
-        tc::mbar_wait(k_full(s), ph);
+        tc::mbar_wait(p_full, (uint32_t)j & 1u);          // P_j written, S_j consumed
+        tc::mbar_wait(v_full(s), (uint32_t)(j >> 1) & 1u);
         tc::fence_after_sync();
-        if (lane == 0) {
-          const uint32_t idesc_s = tc::make_idesc_bf16(BQ, n, 0, 0);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            tc::mma_f16_ss(tmem + S_COL, tc::make_desc(sQ + k * 32, 16, 1024),
-                           tc::make_desc(sK + s * TILE_BYTES + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-          tc::mma_commit(k_empty(s));
-          tc::mma_commit(s_full);
-        }
-        __syncwarp();
-        tc::mbar_wait(p_full, (uint32_t)j & 1u);
-        tc::mbar_wait(v_full(s), ph);
-        tc::fence_after_sync();
-        if (lane == 0) {
-          for (int k = 0; k < n / 16; ++k)
-            tc::mma_f16_ts(tmem + O_COL, tmem + S_COL + k * 8,
-                           tc::make_desc(sV + s * TILE_BYTES + k * 2048, 16384, 1024), idesc_pv,
-                           (j > 0 || k > 0) ? 1u : 0u);
-          tc::mma_commit(v_empty(s));
-          if (j == n_tiles - 1) tc::mma_commit(o_final);
-        }
-        __syncwarp();
+        for (int k = 0; k < n / 16; ++k)
+          tc::mma_f16_ts(tmem + O_COL, tmem + P_COL + k * 8,
+                         tc::make_desc(sV + s * TILE_BYTES + k * 2048, 16384, 1024), idesc_pv,
+                         (j > 0 || k > 0) ? 1u : 0u);
+        tc::mma_commit(v_empty(s));
+        if (j == n_tiles - 1) tc::mma_commit(o_final);
+        else issue_qk(j + 1);        // s_full(j+1) therefore also means "O += P_j V_j retired"
       }
     }
   } else {
     // ================================== softmax warps =======================================
-    tc::reg_inc<216>();
+    tc::reg_inc<104>();
+    const int half = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int q = qt * BQ + row;
     const bool q_ok = q < p.L;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
-    const int t128 = threadIdx.x - 128;
+    const int t256 = threadIdx.x - 128;
+    const int pair_bar = 2 + quad;              // warps (4+quad, 8+quad): the two halves of 32 rows
     bool has_bias = p.u0 != nullptr;
     if (has_bias) {
       // an all-zero u0 row means "no bias for this image" (the batched student pass mixes biased
       // and unbiased images): detect it while staging the row and take the cheaper path
       const float* ub = p.u0 + (size_t)b * p.L;
       uint32_t nz = 0;
-      for (int i = t128; i < n_tiles * BKV; i += 128) {
+      for (int i = t256; i < n_tiles * BKV; i += 256) {
         const float v = (i < p.L) ? ub[i] : 0.f;
         u0s[i] = v;
         nz |= (v != 0.f) ? 1u : 0u;
@@ -178,7 +201,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
           "{\n"
           ".reg .pred p, q;\n"
           "setp.ne.u32 q, %1, 0;\n"
-          "bar.red.or.pred p, 1, 128, q;\n"
+          "bar.red.or.pred p, 1, 256, q;\n"
           "selp.u32 %0, 1, 0, p;\n"
           "}\n"
           : "=r"(any)
@@ -190,30 +213,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     float wgl = 0.f;
     if (has_bias) wgl = p.w * LOG2E * ((p.gate && q_ok) ? p.gate[(size_t)b * p.L + q] : 1.f);
     float m_ref = -INFINITY, l_sum = 0.f;
+    const int col0 = half * 64;                 // this thread's key columns of every tile
     for (int j = 0; j < n_tiles; ++j) {
       const bool full = j < p.n_full;
       const int n = full ? BKV : p.tail_n;
       const int valid = full ? BKV : p.rem;
+      const int mine = max(0, min(64, n - col0));          // columns of this half that exist (x16)
       tc::mbar_wait(s_full, (uint32_t)j & 1u);
       tc::fence_after_sync();
-      uint32_t r[128];
+      uint32_t r[64];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c * 32 < n) {
+      for (int c = 0; c < 2; ++c) {
+        if (c * 32 < mine) {
           uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]);
-          tc::tmem_ld32(lane_base + S_COL + c * 32, chunk);
+          tc::tmem_ld32(lane_base + S_COL + col0 + c * 32, chunk);
         }
       }
       tc::tmem_ld_wait();
       // ---- logits in the log2 domain + row max (8 independent chains) ----
-      const float* ut = u0s + j * BKV;
+      const float* ut = u0s + j * BKV + col0;
       float mx[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
       if (full) {
         if (has_bias) {
 #pragma unroll
-          for (int c4 = 0; c4 < 32; ++c4) {
+          for (int c4 = 0; c4 < 16; ++c4) {
             const float4 u4 = *reinterpret_cast<const float4*>(ut + c4 * 4);
             const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
@@ -226,15 +251,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 128; ++c) mx[c & 7] = fmaxf(mx[c & 7], __uint_as_float(r[c]));
+          for (int c = 0; c < 64; ++c) mx[c & 7] = fmaxf(mx[c & 7], __uint_as_float(r[c]));
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 128; ++c) {
-          if (c < n) {
+        for (int c = 0; c < 64; ++c) {
+          if (c < mine) {
             float t = __uint_as_float(r[c]) * c1;
             if (has_bias) t = fmaf(wgl, ut[c], t);
-            if (c >= valid) t = -INFINITY;
+            if (col0 + c >= valid) t = -INFINITY;
             r[c] = __float_as_uint(t);
             mx[c & 7] = fmaxf(mx[c & 7], t);
           }
@@ -242,8 +267,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       }
       float mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
                        fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-      const bool raw = full && !has_bias;        // r[] still holds unscaled q.k
-      if (raw) mt *= c1;
+      const bool rawdom = full && !has_bias;     // r[] still holds unscaled q.k
+      if (rawdom) mt *= c1;
+      // ---- the two halves of a row agree on the tile maximum ----
+      float* xs = xch + (j & 1) * 256;
+      xs[half * 128 + row] = mt;
+      tc::fence_before_sync();
+      tc::named_bar_sync(pair_bar, 64);          // also: both halves have finished reading S_j
+      tc::fence_after_sync();
+      mt = fmaxf(mt, xs[(half ^ 1) * 128 + row]);
       const float m_new = fmaxf(m_ref, mt);
       const bool resc = m_new > m_ref + RESCALE_THRESHOLD;
       float alpha = 1.f;
@@ -253,24 +285,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
         l_sum *= alpha;
       }
       if (j > 0 && __any_sync(0xffffffffu, resc)) {
-        // s_full(j) was committed after PV(j-1): O is quiescent here
+        // s_full(j) was committed after PV(j-1): O is quiescent here; each half owns 32 columns
         uint32_t o[32];
+        tc::tmem_ld32(lane_base + O_COL + half * 32, o);
+        tc::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tc::tmem_ld32(lane_base + O_COL + c * 32, o);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tc::tmem_st32(lane_base + O_COL + c * 32, o);
-        }
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tc::tmem_st32(lane_base + O_COL + half * 32, o);
       }
-      // ---- P = 2^(t - m_ref) -> bf16 pairs over the S columns; 4 independent sum chains ----
-      const float mul = raw ? c1 : 1.f;
+      // ---- P = 2^(t - m_ref) -> bf16 pairs into the P columns; 4 independent sum chains ----
+      const float mul = rawdom ? c1 : 1.f;
       const float neg_m = -m_ref;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c16 = 0; c16 < 8; ++c16) {
-        if (full || c16 * 16 < n) {
+      for (int c16 = 0; c16 < 4; ++c16) {
+        if (c16 * 16 < mine) {
           uint32_t pk[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -281,8 +310,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
             pk[i] = pack_bf16(p0, p1);
           }
           asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                       ::"r"(lane_base + S_COL + c16 * 8), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
-                         "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                       ::"r"(lane_base + P_COL + half * 32 + c16 * 8), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                         "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
                        : "memory");
         }
       }
@@ -292,16 +321,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(p_full);
     }
-    // ---- epilogue: O / l -> bf16, lse ----
+    // ---- epilogue: O / l -> bf16, lse; each half writes its 32 of the 64 head dims ----
+    float* xs = xch + (n_tiles & 1) * 256;
+    xs[half * 128 + row] = l_sum;
+    tc::named_bar_sync(pair_bar, 64);
+    l_sum += xs[(half ^ 1) * 128 + row];
     tc::mbar_wait(o_final, 0);
     tc::fence_after_sync();
     const float inv_l = 1.f / l_sum;
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                          ((size_t)b * p.L + (q_ok ? q : 0)) * (size_t)(p.H * HD) + h * HD;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+                          ((size_t)b * p.L + (q_ok ? q : 0)) * (size_t)(p.H * HD) + h * HD + half * 32;
+    {
       uint32_t o[32];
-      tc::tmem_ld32(lane_base + O_COL + c * 32, o);
+      tc::tmem_ld32(lane_base + O_COL + half * 32, o);
       tc::tmem_ld_wait();
       if (q_ok) {
 #pragma unroll
@@ -311,11 +343,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
           v.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
           v.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
           v.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = v;
+          *reinterpret_cast<uint4*>(orow + i * 8) = v;
         }
       }
     }
-    if (q_ok) p.lse[((size_t)b * p.H + h) * p.L + q] = (m_ref + log2f(l_sum)) * LN2;
+    if (q_ok && half == 0) p.lse[((size_t)b * p.H + h) * p.L + q] = (m_ref + log2f(l_sum)) * LN2;
   }
 
   tc::fence_before_sync();
@@ -757,7 +789,7 @@ int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, flo
   p.rem = L % BKV;
   p.tail_n = (p.rem + 15) & ~15;
   const int n_tiles = p.n_full + (p.tail_n ? 1 : 0);
-  const size_t smem = 1024 + 5 * TILE_BYTES + 128 + (size_t)n_tiles * BKV * 4;
+  const size_t smem = 1024 + 5 * TILE_BYTES + 128 + 2048 + (size_t)n_tiles * BKV * 4;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -83,7 +83,7 @@ extern "C" int s4_pseudo_label(const float* logits, long long* hard, long long* 
 // SKIP_IF_EQUAL: gradient fix-up launch -- returns at once unless gscale[0] != gscale[1]
 // (see s4_ce_ncr_grad_fixup).
 template <bool WRITE_DZ, bool HAS_T, bool SKIP_IF_EQUAL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, HAS_T ? 2 : 4)   // NCR: <= 128 registers (2 blocks/SM); CE only: <= 64 (4)
 ce_ncr_kernel(const float* __restrict__ zs, const float* __restrict__ zt,
               const long long* __restrict__ label, float* __restrict__ dz,
               float* __restrict__ partial, int C, size_t plane, size_t npix, float ce_scale,
