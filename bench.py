@@ -164,7 +164,7 @@ def reference_arm(a):
                cpu_baseline=dict(value=value, unit=unit, cores=threads, kind='port', sample=sample),
                e2e=dict(value=value, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # --------------------------------------------------------------------------------------------
@@ -198,6 +198,26 @@ def calibrate_teacher(model, img_t, target=0.5):
         return float(conf.float().mean())
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route fd 1 to stderr while the benchmark runs (NCCL prints its version banner on stdout);
+    the ONE JSON line is written to the real stdout at the end."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(line + '\n')
+    out.flush()
+
+
 def main():
     a = parse_args()
     if a.impl == 'reference':
@@ -207,6 +227,7 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}',
                '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    _quiet_stdout()
     import warnings
     warnings.filterwarnings('ignore')
     import torch
@@ -360,7 +381,7 @@ def main():
             value=(s_sup / a.sup) / csec, unit='steps/s', cores=threads, kind='port',
             sample=f'{s_sup} labeled + {s_unsup} unlabeled {a.size}x{a.size} crops, one oracle step '
                    f'({csec:.1f} s), scaled by 1/{a.sup} to the {a.sup}L+{a.unsup}U step')
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
