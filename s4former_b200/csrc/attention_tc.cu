@@ -39,6 +39,29 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 domain: P may grow up to 2^8 before O is rescaled
 
+// Optional device-side event trace (debug / profiling builds of the kernels only: the production
+// instantiations compile the hooks away).  Each traced role owns TRACE_MAX (id, clock64) pairs.
+constexpr int TRACE_MAX = 512;
+struct TraceCfg {
+  unsigned long long* buf;   // [roles][TRACE_MAX][2]
+  int block;                 // the CTA that records
+};
+template <bool TR>
+struct Tracer {
+  unsigned long long* b;
+  int n;
+  __device__ __forceinline__ Tracer(const TraceCfg& c, int role) : b(nullptr), n(0) {
+    if (TR && c.buf && (int)blockIdx.x == c.block) b = c.buf + (size_t)role * TRACE_MAX * 2;
+  }
+  __device__ __forceinline__ void ev(int id) {
+    if (TR && b && n < TRACE_MAX) {
+      b[2 * n] = (unsigned long long)id;
+      b[2 * n + 1] = (unsigned long long)clock64();
+      ++n;
+    }
+  }
+};
+
 struct FwdParams {
   void* out;          // [B, L, H*64] bf16
   float* lse;         // [B, H, L] natural-log LSE of the biased, scaled logits
@@ -49,6 +72,7 @@ struct FwdParams {
   int B, H, L;
   int q_tiles;        // ceil(L / 128)
   int n_full, rem, tail_n;   // key tiles: n_full x 128 + one tail of tail_n (rem valid) keys
+  TraceCfg trace;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -74,6 +98,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // Register budget is moved from warps 0-3 to the softmax warps with setmaxnreg.
 // The key loop runs full 128-key tiles plus one tail tile of round_up(L % 128, 16) keys, so
 // L = 1025 (512^2 crops) costs 8 tiles + a 16-key MMA, not 9 tiles.
+template <bool TR>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -91,9 +116,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
   const uint32_t s_full = bar + 8u * 9;
   const uint32_t p_full = bar + 8u * 10;
   const uint32_t o_final = bar + 8u * 11;
-  const uint32_t tmem_slot = bar + 8u * 12;
+  const uint32_t s_free = bar + 8u * 12;      // every softmax warp has S_j in registers
+  const uint32_t pv_done = bar + 8u * 13;     // O += P_j V_j retired (P columns / O reusable)
+  const uint32_t tmem_slot = bar + 8u * 14;
   uint8_t* gen = smem_raw + (base - raw);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 5 * TILE_BYTES + 8 * 12);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 5 * TILE_BYTES + 8 * 14);
   float* xch = reinterpret_cast<float*>(gen + 5 * TILE_BYTES + 128);   // [2 parity][2 halves][128 rows]
   float* u0s = xch + 512;
 
@@ -115,6 +142,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     tc::mbar_init(s_full, 1);
     tc::mbar_init(p_full, 8);
     tc::mbar_init(o_final, 1);
+    tc::mbar_init(s_free, 8);
+    tc::mbar_init(pv_done, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -141,42 +170,83 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
         tc::mbar_expect_tx(v_full(s), TILE_BYTES);
         tc::tma_load_4d(sV + s * TILE_BYTES, &tm_qkv, v_full(s), 0, j * BKV, 2 * p.H + h, b);
       }
-    } else if (warp == 1 && lane == 0) {
-      // ================================ MMA issuer (one thread) =============================
-      const uint32_t idesc_pv = tc::make_idesc_bf16(BQ, HD, 0, 1);
+    } else if (warp == 1) {
+      // ====================== MMA issuer (whole warp in uniform control flow) ================
+      // All 32 lanes run the loop and the waits, so every descriptor is a warp-uniform value held
+      // in uniform registers; the elected lane issues.  (Issuing from a `lane == 0` branch makes
+      // ptxas wrap each tcgen05.mma in a serialising elect loop: ~120 clk per MMA, which made
+      // this thread, not the tensor pipe or the softmax warps, the critical path of a tile.)
+      const bool leader = tc::elect_one();
+      Tracer<TR> tr(p.trace, 0);
+      if (!leader) tr.b = nullptr;
+      constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, HD, 0, 1);
+      constexpr uint32_t idesc_full = tc::make_idesc_bf16(BQ, BKV, 0, 0);
+      const uint32_t idesc_tail = tc::make_idesc_bf16(BQ, p.tail_n ? p.tail_n : BKV, 0, 0);
+      // descriptor = [hi: SBO 1024 B | version 1 | SWIZZLE_128B] [lo: LBO >> 4 << 16 | addr >> 4]
+      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t q_lo = ((sQ >> 4) & 0x3FFFu) | (1u << 16);
       auto issue_qk = [&](int j) {
         const int s = j & 1;
-        const int n = (j < p.n_full) ? BKV : p.tail_n;
         tc::mbar_wait(k_full(s), (uint32_t)(j >> 1) & 1u);
         tc::fence_after_sync();
-        const uint32_t idesc_s = tc::make_idesc_bf16(BQ, n, 0, 0);
+        const uint32_t idesc_s = (j < p.n_full) ? idesc_full : idesc_tail;
+        const uint32_t k_lo = (((sK + s * TILE_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          tc::mma_f16_ss(tmem + S_COL, tc::make_desc(sQ + k * 32, 16, 1024),
-                         tc::make_desc(sK + s * TILE_BYTES + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        tc::mma_commit(k_empty(s));
-        tc::mma_commit(s_full);
+          for (int k = 0; k < HD / 16; ++k)
+            tc::mma_f16_ss(tmem + S_COL, ((uint64_t)desc_hi << 32) | (uint64_t)(q_lo + k * 2),
+                           ((uint64_t)desc_hi << 32) | (uint64_t)(k_lo + k * 2), idesc_s, k > 0 ? 1u : 0u);
+          tc::mma_commit(k_empty(s));
+          tc::mma_commit(s_full);
+        }
+        __syncwarp();
+        tr.ev(2);
       };
       tc::mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
-        const int n = (j < p.n_full) ? BKV : p.tail_n;
-        tc::mbar_wait(p_full, (uint32_t)j & 1u);          // P_j written, S_j consumed
+        const bool full = j < p.n_full;
+        // S_{j+1} = Q K_{j+1}^T is issued as soon as the softmax warps hold S_j in registers, i.e.
+        // it runs on the tensor pipe WHILE they exponentiate tile j (P has its own TMEM columns)
+        if (j + 1 < n_tiles) {
+          tc::mbar_wait(s_free, (uint32_t)j & 1u);
+          tc::fence_after_sync();
+          tr.ev(1);
+          issue_qk(j + 1);
+        }
+        tc::mbar_wait(p_full, (uint32_t)j & 1u);          // P_j written
         tc::mbar_wait(v_full(s), (uint32_t)(j >> 1) & 1u);
         tc::fence_after_sync();
-        for (int k = 0; k < n / 16; ++k)
-          tc::mma_f16_ts(tmem + O_COL, tmem + P_COL + k * 8,
-                         tc::make_desc(sV + s * TILE_BYTES + k * 2048, 16384, 1024), idesc_pv,
-                         (j > 0 || k > 0) ? 1u : 0u);
-        tc::mma_commit(v_empty(s));
-        if (j == n_tiles - 1) tc::mma_commit(o_final);
-        else issue_qk(j + 1);        // s_full(j+1) therefore also means "O += P_j V_j retired"
+        tr.ev(3);
+        // V tile [128 keys][64 dims] is the MN-major B operand: LBO 16384, one 16-key step = 2048 B
+        const uint32_t v_lo = (((sV + s * TILE_BYTES) >> 4) & 0x3FFFu) | ((16384u >> 4) << 16);
+        if (leader) {
+          if (full) {
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k)
+              tc::mma_f16_ts(tmem + O_COL, tmem + P_COL + k * 8,
+                             ((uint64_t)desc_hi << 32) | (uint64_t)(v_lo + k * (2048u >> 4)), idesc_pv,
+                             (j > 0 || k > 0) ? 1u : 0u);
+          } else {
+            for (int k = 0; k < p.tail_n / 16; ++k)
+              tc::mma_f16_ts(tmem + O_COL, tmem + P_COL + k * 8,
+                             ((uint64_t)desc_hi << 32) | (uint64_t)(v_lo + k * (2048u >> 4)), idesc_pv,
+                             (j > 0 || k > 0) ? 1u : 0u);
+          }
+          tc::mma_commit(v_empty(s));
+          tc::mma_commit(pv_done);
+          if (j == n_tiles - 1) tc::mma_commit(o_final);
+        }
+        __syncwarp();
+        tr.ev(4);
       }
     }
   } else {
     // ================================== softmax warps =======================================
     tc::reg_inc<104>();
+    Tracer<TR> tr(p.trace, (lane == 0 && (warp == 4 || warp == 8)) ? (warp == 4 ? 1 : 2) : 0);
+    if (!(lane == 0 && (warp == 4 || warp == 8))) tr.b = nullptr;
     const int half = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
@@ -214,6 +284,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     if (has_bias) wgl = p.w * LOG2E * ((p.gate && q_ok) ? p.gate[(size_t)b * p.L + q] : 1.f);
     float m_ref = -INFINITY, l_sum = 0.f;
     const int col0 = half * 64;                 // this thread's key columns of every tile
+    // the tail tile (L % 128 keys, padded to x16) runs through a compact rolled path that re-reads
+    // S from TMEM chunk by chunk: it executes once per CTA, so its code must stay small (a fully
+    // unrolled, predicated copy of the main path cost ~5700 clk per CTA in instruction fetch)
+    auto tail_t16 = [&](int j, int c16, int valid, float (&t)[16]) {
+      uint32_t rr[16];
+      tc::tmem_ld16(lane_base + S_COL + col0 + c16 * 16, rr);
+      tc::tmem_ld_wait();
+      const float* ut = u0s + j * BKV + col0 + c16 * 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float v = __uint_as_float(rr[i]) * c1;
+        if (has_bias) v = fmaf(wgl, ut[i], v);
+        t[i] = (col0 + c16 * 16 + i < valid) ? v : -INFINITY;
+      }
+    };
     for (int j = 0; j < n_tiles; ++j) {
       const bool full = j < p.n_full;
       const int n = full ? BKV : p.tail_n;
@@ -221,21 +306,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       const int mine = max(0, min(64, n - col0));          // columns of this half that exist (x16)
       tc::mbar_wait(s_full, (uint32_t)j & 1u);
       tc::fence_after_sync();
+      tr.ev(10);
       uint32_t r[64];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        if (c * 32 < mine) {
-          uint32_t(&chunk)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]);
-          tc::tmem_ld32(lane_base + S_COL + col0 + c * 32, chunk);
-        }
-      }
-      tc::tmem_ld_wait();
-      // ---- logits in the log2 domain + row max (8 independent chains) ----
-      const float* ut = u0s + j * BKV + col0;
-      float mx[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+      float mt = -INFINITY;
+      const bool rawdom = full && !has_bias;     // r[] holds unscaled q.k
       if (full) {
+        tc::tmem_ld32(lane_base + S_COL + col0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tc::tmem_ld32(lane_base + S_COL + col0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tc::tmem_ld_wait();
+        // S_j now lives in registers: let the MMA warp overwrite the S columns with S_{j+1}
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(s_free);
+        tr.ev(11);
+        // ---- logits in the log2 domain + row max (8 independent chains) ----
+        const float* ut = u0s + j * BKV + col0;
+        float mx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
         if (has_bias) {
 #pragma unroll
           for (int c4 = 0; c4 < 16; ++c4) {
@@ -253,29 +341,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
 #pragma unroll
           for (int c = 0; c < 64; ++c) mx[c & 7] = fmaxf(mx[c & 7], __uint_as_float(r[c]));
         }
+        mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                   fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+        if (rawdom) mt *= c1;
       } else {
+        for (int c16 = 0; c16 < (mine >> 4); ++c16) {
+          float t[16];
+          tail_t16(j, c16, valid, t);
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          if (c < mine) {
-            float t = __uint_as_float(r[c]) * c1;
-            if (has_bias) t = fmaf(wgl, ut[c], t);
-            if (col0 + c >= valid) t = -INFINITY;
-            r[c] = __float_as_uint(t);
-            mx[c & 7] = fmaxf(mx[c & 7], t);
-          }
+          for (int i = 0; i < 16; ++i) mt = fmaxf(mt, t[i]);
         }
+        tr.ev(11);
       }
-      float mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
-                       fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-      const bool rawdom = full && !has_bias;     // r[] still holds unscaled q.k
-      if (rawdom) mt *= c1;
       // ---- the two halves of a row agree on the tile maximum ----
       float* xs = xch + (j & 1) * 256;
       xs[half * 128 + row] = mt;
-      tc::fence_before_sync();
-      tc::named_bar_sync(pair_bar, 64);          // also: both halves have finished reading S_j
-      tc::fence_after_sync();
+      tc::named_bar_sync(pair_bar, 64);
+      tr.ev(12);
       mt = fmaxf(mt, xs[(half ^ 1) * 128 + row]);
+      // O += P_{j-1} V_{j-1} must have retired before O is rescaled or the P columns are rewritten
+      // (it was issued a whole S-load / max phase ago: this wait is normally already satisfied)
+      if (j > 0) {
+        tc::mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);
+        tc::fence_after_sync();
+      }
+      tr.ev(13);
       const float m_new = fmaxf(m_ref, mt);
       const bool resc = m_new > m_ref + RESCALE_THRESHOLD;
       float alpha = 1.f;
@@ -285,7 +375,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
         l_sum *= alpha;
       }
       if (j > 0 && __any_sync(0xffffffffu, resc)) {
-        // s_full(j) was committed after PV(j-1): O is quiescent here; each half owns 32 columns
+        // PV(j-1) has retired and PV(j) waits for this tile's P: O is quiescent; each half owns 32 columns
         uint32_t o[32];
         tc::tmem_ld32(lane_base + O_COL + half * 32, o);
         tc::tmem_ld_wait();
@@ -294,12 +384,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
         tc::tmem_st32(lane_base + O_COL + half * 32, o);
       }
       // ---- P = 2^(t - m_ref) -> bf16 pairs into the P columns; 4 independent sum chains ----
-      const float mul = rawdom ? c1 : 1.f;
       const float neg_m = -m_ref;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      if (full) {
+        const float mul = rawdom ? c1 : 1.f;
 #pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {
-        if (c16 * 16 < mine) {
+        for (int c16 = 0; c16 < 4; ++c16) {
           uint32_t pk[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -314,12 +404,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
                          "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
                        : "memory");
         }
+      } else {
+        for (int c16 = 0; c16 < (mine >> 4); ++c16) {
+          float t[16];
+          tail_t16(j, c16, valid, t);
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float p0 = tc::ex2(t[2 * i] + neg_m);
+            const float p1 = tc::ex2(t[2 * i + 1] + neg_m);
+            ls[i & 3] += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                       ::"r"(lane_base + P_COL + half * 32 + c16 * 8), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                         "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                       : "memory");
+        }
       }
       l_sum += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      tr.ev(14);
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(p_full);
+      tr.ev(15);
     }
     // ---- epilogue: O / l -> bf16, lse; each half writes its 32 of the 64 head dims ----
     float* xs = xch + (n_tiles & 1) * 256;
@@ -385,6 +494,7 @@ struct BwdParams {
   const float* gate;
   float w, scale;
   int B, H, L, q_tiles;
+  TraceCfg trace;
 };
 
 __device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, uint32_t ssrc, uint32_t bytes) {
@@ -399,6 +509,7 @@ __device__ __forceinline__ int bwd_half_n(int L, int i, int h) {
   return qn > 64 ? qn - 64 : 16;    // at least a 16-wide (all masked) MMA keeps both halves in step
 }
 
+template <bool TR>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const BwdParams p) {
@@ -471,37 +582,65 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================================ MMA issuer (one thread) =============================
-      const uint32_t idesc_dvk = tc::make_idesc_bf16(128, HD, 0, 1);
-      const uint32_t idesc_dq = tc::make_idesc_bf16(128, HD, 1, 1);
+    // ====================== MMA issuer (whole warp in uniform control flow) ==================
+    // All 32 lanes run the loop and the waits; every descriptor is a warp-uniform value in uniform
+    // registers and the elected lane issues (see the forward kernel for why not `lane == 0`).
+    {
+      const bool leader = tc::elect_one();
+      Tracer<TR> tr(p.trace, 0);
+      if (!leader) tr.b = nullptr;
+      constexpr uint32_t idesc_dvk = tc::make_idesc_bf16(128, HD, 0, 1);
+      constexpr uint32_t idesc_dq = tc::make_idesc_bf16(128, HD, 1, 1);
+      // descriptor = [hi: SBO 1024 B | version 1 | SWIZZLE_128B] [lo: LBO >> 4 << 16 | addr >> 4]
+      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t KM = 1u << 16;                    // K-major operand: LBO field 1
+      constexpr uint32_t MN = (16384u >> 4) << 16;         // MN-major operand: LBO 16384
+      auto dsc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+      const uint32_t k_lo = (sK >> 4) & 0x3FFFu, v_lo = (sV >> 4) & 0x3FFFu, ds_lo = (sdS >> 4) & 0x3FFFu;
       uint32_t acc_dvk = 0;
       auto issue_sdp = [&](int i, int hh) {
         const int st = i & 1;
         const uint32_t idesc = tc::make_idesc_bf16(128, bwd_half_n(p.L, i, hh), 0, 0);
-        const uint32_t q_rows = sQ + st * TILE_BYTES + hh * 8192;
-        const uint32_t do_rows = sdO + st * TILE_BYTES + hh * 8192;
+        const uint32_t q_lo = ((sQ + st * TILE_BYTES + hh * 8192) >> 4) & 0x3FFFu;
+        const uint32_t do_lo = ((sdO + st * TILE_BYTES + hh * 8192) >> 4) & 0x3FFFu;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc::mma_f16_ss(tmem + hh * 64, tc::make_desc(sK + k * 32, 16, 1024),
-                         tc::make_desc(q_rows + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            tc::mma_f16_ss(tmem + hh * 64, dsc((k_lo + k * 2) | KM), dsc((q_lo + k * 2) | KM), idesc,
+                           k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc::mma_f16_ss(tmem + DP_COL + hh * 64, tc::make_desc(sV + k * 32, 16, 1024),
-                         tc::make_desc(do_rows + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
-        tc::mma_commit(sdp_full(hh));
+          for (int k = 0; k < 4; ++k)
+            tc::mma_f16_ss(tmem + DP_COL + hh * 64, dsc((v_lo + k * 2) | KM), dsc((do_lo + k * 2) | KM), idesc,
+                           k > 0 ? 1u : 0u);
+          tc::mma_commit(sdp_full(hh));
+        }
+        __syncwarp();
       };
       auto issue_dvk = [&](int i, int hh, uint32_t acc) {
         const int st = i & 1;
         const int steps = bwd_half_n(p.L, i, hh) >> 4;
-        const uint32_t q_rows = sQ + st * TILE_BYTES + hh * 8192;
-        const uint32_t do_rows = sdO + st * TILE_BYTES + hh * 8192;
-        for (int s = 0; s < steps; ++s)
-          tc::mma_f16_ts(tmem + DV_COL, tmem + hh * 64 + s * 8, tc::make_desc(do_rows + s * 2048, 16384, 1024),
-                         idesc_dvk, (acc | (uint32_t)s) ? 1u : 0u);
-        for (int s = 0; s < steps; ++s)
-          tc::mma_f16_ts(tmem + DK_COL, tmem + DP_COL + hh * 64 + s * 8,
-                         tc::make_desc(q_rows + s * 2048, 16384, 1024), idesc_dvk, (acc | (uint32_t)s) ? 1u : 0u);
+        const uint32_t q_lo = (((sQ + st * TILE_BYTES + hh * 8192) >> 4) & 0x3FFFu) | MN;
+        const uint32_t do_lo = (((sdO + st * TILE_BYTES + hh * 8192) >> 4) & 0x3FFFu) | MN;
+        if (leader) {
+          if (steps == 4) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              tc::mma_f16_ts(tmem + DV_COL, tmem + hh * 64 + s * 8, dsc(do_lo + s * 128), idesc_dvk,
+                             (acc | (uint32_t)s) ? 1u : 0u);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              tc::mma_f16_ts(tmem + DK_COL, tmem + DP_COL + hh * 64 + s * 8, dsc(q_lo + s * 128), idesc_dvk,
+                             (acc | (uint32_t)s) ? 1u : 0u);
+          } else {
+            for (int s = 0; s < steps; ++s)
+              tc::mma_f16_ts(tmem + DV_COL, tmem + hh * 64 + s * 8, dsc(do_lo + s * 128), idesc_dvk,
+                             (acc | (uint32_t)s) ? 1u : 0u);
+            for (int s = 0; s < steps; ++s)
+              tc::mma_f16_ts(tmem + DK_COL, tmem + DP_COL + hh * 64 + s * 8, dsc(q_lo + s * 128), idesc_dvk,
+                             (acc | (uint32_t)s) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
       };
       tc::mbar_wait(kv_full, 0);
       tc::mbar_wait(qd_full(0), 0);
@@ -513,32 +652,48 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         const uint32_t ph = (uint32_t)i & 1u;
         tc::mbar_wait(pds_full(0), ph);
         tc::fence_after_sync();
+        tr.ev(1);
         issue_dvk(i, 0, acc_dvk);
+        tr.ev(2);
         if (i + 1 < nq) {
           tc::mbar_wait(qd_full(st ^ 1), ((uint32_t)(i + 1) >> 1) & 1u);
           tc::fence_after_sync();
+          tr.ev(3);
           issue_sdp(i + 1, 0);
+          tr.ev(4);
         }
         tc::mbar_wait(pds_full(1), ph);
         tc::fence_after_sync();
+        tr.ev(5);
         issue_dvk(i, 1, 1u);
         acc_dvk = 1;
-        tc::mma_commit(qd_empty(st));
+        if (leader) tc::mma_commit(qd_empty(st));
+        __syncwarp();
+        tr.ev(6);
         tc::mbar_wait(dq_empty, ph ^ 1u);
         tc::fence_after_sync();
+        tr.ev(7);
+        if (leader) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s)
-          tc::mma_f16_ss(tmem + DQ_COL, tc::make_desc(sdS + s * 2048, 16384, 1024),
-                         tc::make_desc(sK + s * 2048, 16384, 1024), idesc_dq, s > 0 ? 1u : 0u);
-        tc::mma_commit(dq_done);
+          for (int s = 0; s < 8; ++s)
+            tc::mma_f16_ss(tmem + DQ_COL, dsc((ds_lo + s * 128) | MN), dsc((k_lo + s * 128) | MN), idesc_dq,
+                           s > 0 ? 1u : 0u);
+          tc::mma_commit(dq_done);
+        }
+        __syncwarp();
+        tr.ev(8);
         if (i + 1 < nq) issue_sdp(i + 1, 1);
+        tr.ev(9);
       }
-      tc::mma_commit(dvk_full);
+      if (leader) tc::mma_commit(dvk_full);
+      __syncwarp();
     }
   } else if (warp >= 4 && warp < 12) {
     // ================================== softmax warps =======================================
     const int hh = (warp - 4) >> 2;             // query half handled by this warpgroup
     const int quad = warp & 3;
+    Tracer<TR> tr(p.trace, 1 + hh);
+    if (!(lane == 0 && quad == 0)) tr.b = nullptr;
     const int row = quad * 32 + lane;           // key row (TMEM lane)
     const int key = jt * 128 + row;
     const bool key_ok = key < p.L;
@@ -565,6 +720,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const int n = bwd_half_n(p.L, i, hh);
       tc::mbar_wait(sdp_full(hh), (uint32_t)i & 1u);
       tc::fence_after_sync();
+      tr.ev(10);
       const int qbase = i * 128 + hh * 64;
       for (int c16 = 0; c16 < (n >> 4); ++c16) {
         uint32_t sv[16], dv[16];
@@ -603,7 +759,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                      ::"r"(lane_base + DP_COL + hh * 64 + c16 * 8), "r"(dsp[0]), "r"(dsp[1]), "r"(dsp[2]),
                        "r"(dsp[3]), "r"(dsp[4]), "r"(dsp[5]), "r"(dsp[6]), "r"(dsp[7]) : "memory");
         if (c16 == 0 && i > 0) {   // the dQ MMA of the previous tile must have consumed sdS
+          tr.ev(11);
           tc::mbar_wait(dq_done, (uint32_t)(i - 1) & 1u);
+          tr.ev(12);
         }
         // dS^T row (this key) for queries [c16*16, +16): two 16-byte chunks of the swizzled row
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + ((((uint32_t)(2 * c16)) ^ swz) << 4)),
@@ -611,11 +769,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + ((((uint32_t)(2 * c16 + 1)) ^ swz) << 4)),
                      "r"(dsp[4]), "r"(dsp[5]), "r"(dsp[6]), "r"(dsp[7]) : "memory");
       }
+      tr.ev(13);
       tc::tmem_st_wait();
       tc::fence_proxy_async();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(pds_full(hh));
+      tr.ev(14);
     }
     // ---- final: dV (warpgroup 0) / dK (warpgroup 1) -> bf16 rows of dqkv ----
     tc::mbar_wait(dvk_full, 0);
@@ -644,6 +804,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   } else if (warp >= 12) {
     // ================================== dQ epilogue =========================================
     const int quad = warp & 3;
+    Tracer<TR> tr(p.trace, 3);
+    if (!(lane == 0 && quad == 0)) tr.b = nullptr;
     const int row = quad * 32 + lane;           // query row of the tile
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
     const uint32_t srow = sdQ + row * 256;
@@ -652,6 +814,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     for (int i = 0; i < nq; ++i) {
       tc::mbar_wait(dq_done, (uint32_t)i & 1u);
       tc::fence_after_sync();
+      tr.ev(20);
       uint32_t o0[32], o1[32];
       tc::tmem_ld32(lane_base + DQ_COL, o0);
       tc::tmem_ld32(lane_base + DQ_COL + 32, o1);
@@ -662,6 +825,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       // the previous tile's bulk reduce must have finished reading the staging buffer
       if (threadIdx.x == 12 * 32) tc::bulk_wait_read<0>();
       tc::named_bar_sync(2, 128);
+      tr.ev(21);
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((((uint32_t)c) ^ swz) << 4)),
@@ -676,6 +840,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         bulk_reduce_add_f32(acc_base + (size_t)i * (128 * 64), sdQ, 128 * 64 * 4);
         tc::bulk_commit();
       }
+      tr.ev(22);
     }
     if (threadIdx.x == 12 * 32) tc::bulk_wait<0>();
   }
@@ -741,6 +906,8 @@ attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restr
   *reinterpret_cast<uint4*>(dqkv + (size_t)bq * 3 * H * HD + hh * HD + g8 * 8) = v;
 }
 
+TraceCfg g_trace{nullptr, 0};
+
 int env_composed() {
   static int v = -1;
   if (v < 0) {
@@ -751,6 +918,14 @@ int env_composed() {
 }
 
 }  // namespace
+
+// Debug hook: record a device-side event trace of CTA `block` of the following attention launches
+// into `dev_buf` (roles x TRACE_MAX x 2 uint64, zero-filled by the caller); nullptr switches it off.
+extern "C" int s4_attention_set_trace(void* dev_buf, int block) {
+  g_trace.buf = (unsigned long long*)dev_buf;
+  g_trace.block = block;
+  return TRACE_MAX;
+}
 
 bool s4_attention_tc_fwd_supported(int B, int H, int L, int hd, int dtype) {
   if (env_composed()) return false;
@@ -792,7 +967,9 @@ int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, flo
   const size_t smem = 1024 + 5 * TILE_BYTES + 128 + 2048 + (size_t)n_tiles * BKV * 4;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       s4_set_error("attention_tc_fwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return S4_ERR_CUDA;
@@ -801,7 +978,9 @@ int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, flo
   }
   const double flops = 4.0 * B * H * (double)L * L * HD;
   S4ProfScope prof("attn_fwd_tc", flops, 0, st);
-  attn_fwd_kernel<<<B * H * p.q_tiles, FWD_THREADS, smem, st>>>(tm, p);
+  p.trace = g_trace;
+  if (g_trace.buf) attn_fwd_kernel<true><<<B * H * p.q_tiles, FWD_THREADS, smem, st>>>(tm, p);
+  else attn_fwd_kernel<false><<<B * H * p.q_tiles, FWD_THREADS, smem, st>>>(tm, p);
   return s4_check_launch("attn_fwd_tc");
 }
 
@@ -844,7 +1023,9 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
   const size_t smem = 1024 + 10 * TILE_BYTES + 128 + (size_t)3 * q_tiles * 128 * 4;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       s4_set_error("attention_tc_bwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return S4_ERR_CUDA;
@@ -863,7 +1044,9 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
         (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, delta, B, H, L);
     if ((rc = s4_check_launch("attn_bwd_delta"))) return rc;
   }
-  attn_bwd_kernel<<<B * H * q_tiles, BWD_THREADS, smem, st>>>(tq, tdo, p);
+  p.trace = g_trace;
+  if (g_trace.buf) attn_bwd_kernel<true><<<B * H * q_tiles, BWD_THREADS, smem, st>>>(tq, tdo, p);
+  else attn_bwd_kernel<false><<<B * H * q_tiles, BWD_THREADS, smem, st>>>(tq, tdo, p);
   if ((rc = s4_check_launch("attn_bwd_tc"))) return rc;
   {
     const long long total = (long long)B * L * H * 8;

@@ -272,6 +272,21 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// One lane of the (converged) warp: lets the whole warp run an issue loop in uniform control flow
+// (descriptors and addresses then live in uniform registers) with the elected lane doing the
+// tcgen05.mma / commit / TMA instructions.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- descriptors -----------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle.  Fields (PTX ISA):
 //   [0,14)  start address >> 4      [16,30) leading-dim byte offset >> 4
