@@ -18,6 +18,7 @@
 // Register budget is moved from warps 0-3 to the softmax warps with setmaxnreg.
 // The key loop runs full 128-key tiles plus one tail tile of round_up(L % 128, 16) keys, so
 // L = 1025 (512^2 crops) costs 8 tiles + a 16-key MMA, not 9 tiles.
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 
@@ -118,17 +119,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
   const uint32_t o_final = bar + 8u * 11;
   const uint32_t s_free = bar + 8u * 12;      // every softmax warp has S_j in registers
   const uint32_t pv_done = bar + 8u * 13;     // O += P_j V_j retired (P columns / O reusable)
-  const uint32_t tmem_slot = bar + 8u * 14;
+  const uint32_t q_empty = bar + 8u * 14;     // every S = Q K^T of the work item has retired
+  const uint32_t tmem_slot = bar + 8u * 15;
   uint8_t* gen = smem_raw + (base - raw);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 5 * TILE_BYTES + 8 * 14);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 5 * TILE_BYTES + 8 * 15);
   float* xch = reinterpret_cast<float*>(gen + 5 * TILE_BYTES + 128);   // [2 parity][2 halves][128 rows]
-  float* u0s = xch + 512;
+  float* xch_l = xch + 512;                                            // [2 halves][128 rows]: row sums
+  float* u0s = xch + 768;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x % p.q_tiles;
-  const int bh = blockIdx.x / p.q_tiles;
-  const int h = bh % p.H, b = bh / p.H;
   const int n_tiles = p.n_full + (p.tail_n ? 1 : 0);
+  // PERSISTENT: the CTA walks work items (batch, head, query tile) blockIdx.x, +gridDim.x, ...;
+  // TMEM, barriers and the instruction cache stay warm, and the producer prefetches the next
+  // item's Q / K / V while the current item drains.  All barrier parities run on counters that
+  // continue across items (`t0` = tiles done before the item, `it` = items done).
+  const int n_items = p.B * p.H * p.q_tiles;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tm_qkv);
@@ -144,6 +149,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     tc::mbar_init(o_final, 1);
     tc::mbar_init(s_free, 8);
     tc::mbar_init(pv_done, 1);
+    tc::mbar_init(q_empty, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -158,17 +164,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     tc::reg_dec<32>();
     if (warp == 0 && lane == 0) {
       // ================================ TMA producer ========================================
-      tc::mbar_expect_tx(q_full, TILE_BYTES);
-      tc::tma_load_4d(sQ, &tm_qkv, q_full, 0, qt * BQ, h, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        tc::mbar_wait(k_empty(s), ph ^ 1u);
-        tc::mbar_expect_tx(k_full(s), TILE_BYTES);
-        tc::tma_load_4d(sK + s * TILE_BYTES, &tm_qkv, k_full(s), 0, j * BKV, p.H + h, b);
-        tc::mbar_wait(v_empty(s), ph ^ 1u);
-        tc::mbar_expect_tx(v_full(s), TILE_BYTES);
-        tc::tma_load_4d(sV + s * TILE_BYTES, &tm_qkv, v_full(s), 0, j * BKV, 2 * p.H + h, b);
+      int it = 0, t0 = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it, t0 += n_tiles) {
+        const int qt = item % p.q_tiles;
+        const int bh = item / p.q_tiles;
+        const int h = bh % p.H, b = bh / p.H;
+        if (it > 0) tc::mbar_wait(q_empty, (uint32_t)(it - 1) & 1u);
+        tc::mbar_expect_tx(q_full, TILE_BYTES);
+        tc::tma_load_4d(sQ, &tm_qkv, q_full, 0, qt * BQ, h, b);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int t = t0 + j;
+          const int s = t & 1;
+          const uint32_t ph = (uint32_t)(t >> 1) & 1u;
+          tc::mbar_wait(k_empty(s), ph ^ 1u);
+          tc::mbar_expect_tx(k_full(s), TILE_BYTES);
+          tc::tma_load_4d(sK + s * TILE_BYTES, &tm_qkv, k_full(s), 0, j * BKV, p.H + h, b);
+          tc::mbar_wait(v_empty(s), ph ^ 1u);
+          tc::mbar_expect_tx(v_full(s), TILE_BYTES);
+          tc::tma_load_4d(sV + s * TILE_BYTES, &tm_qkv, v_full(s), 0, j * BKV, 2 * p.H + h, b);
+        }
       }
     } else if (warp == 1) {
       // ====================== MMA issuer (whole warp in uniform control flow) ================
@@ -185,9 +199,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       // descriptor = [hi: SBO 1024 B | version 1 | SWIZZLE_128B] [lo: LBO >> 4 << 16 | addr >> 4]
       constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t q_lo = ((sQ >> 4) & 0x3FFFu) | (1u << 16);
-      auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        tc::mbar_wait(k_full(s), (uint32_t)(j >> 1) & 1u);
+      auto issue_qk = [&](int j, int t, bool last) {
+        const int s = t & 1;
+        tc::mbar_wait(k_full(s), (uint32_t)(t >> 1) & 1u);
         tc::fence_after_sync();
         const uint32_t idesc_s = (j < p.n_full) ? idesc_full : idesc_tail;
         const uint32_t k_lo = (((sK + s * TILE_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
@@ -198,25 +212,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
                            ((uint64_t)desc_hi << 32) | (uint64_t)(k_lo + k * 2), idesc_s, k > 0 ? 1u : 0u);
           tc::mma_commit(k_empty(s));
           tc::mma_commit(s_full);
+          if (last) tc::mma_commit(q_empty);     // the Q tile may be overwritten by the next item's
         }
         __syncwarp();
         tr.ev(2);
       };
-      tc::mbar_wait(q_full, 0);
-      issue_qk(0);
+      int it = 0, t0 = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it, t0 += n_tiles) {
+      tc::mbar_wait(q_full, (uint32_t)it & 1u);
+      if (t0 > 0) {          // the previous item's last S tile must have been read out
+        tc::mbar_wait(s_free, (uint32_t)(t0 - 1) & 1u);
+        tc::fence_after_sync();
+      }
+      issue_qk(0, t0, n_tiles == 1);
       for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
+        const int t = t0 + j;
+        const int s = t & 1;
         const bool full = j < p.n_full;
         // S_{j+1} = Q K_{j+1}^T is issued as soon as the softmax warps hold S_j in registers, i.e.
         // it runs on the tensor pipe WHILE they exponentiate tile j (P has its own TMEM columns)
         if (j + 1 < n_tiles) {
-          tc::mbar_wait(s_free, (uint32_t)j & 1u);
+          tc::mbar_wait(s_free, (uint32_t)t & 1u);
           tc::fence_after_sync();
           tr.ev(1);
-          issue_qk(j + 1);
+          issue_qk(j + 1, t + 1, j + 2 == n_tiles);
         }
-        tc::mbar_wait(p_full, (uint32_t)j & 1u);          // P_j written
-        tc::mbar_wait(v_full(s), (uint32_t)(j >> 1) & 1u);
+        tc::mbar_wait(p_full, (uint32_t)t & 1u);          // P_j written
+        tc::mbar_wait(v_full(s), (uint32_t)(t >> 1) & 1u);
         tc::fence_after_sync();
         tr.ev(3);
         // V tile [128 keys][64 dims] is the MN-major B operand: LBO 16384, one 16-key step = 2048 B
@@ -241,6 +263,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
         __syncwarp();
         tr.ev(4);
       }
+      }
     }
   } else {
     // ================================== softmax warps =======================================
@@ -250,16 +273,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     const int half = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int q = qt * BQ + row;
-    const bool q_ok = q < p.L;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
     const int t256 = threadIdx.x - 128;
     const int pair_bar = 2 + quad;              // warps (4+quad, 8+quad): the two halves of 32 rows
-    bool has_bias = p.u0 != nullptr;
+    const float c1 = p.scale * LOG2E;
+    const int col0 = half * 64;                 // this thread's key columns of every tile
+    bool has_bias = false;
+    float wgl = 0.f;
+    // the tail tile (L % 128 keys, padded to x16) runs through a compact rolled path that re-reads
+    // S from TMEM chunk by chunk: it executes once per item, so its code must stay small (a fully
+    // unrolled, predicated copy of the main path cost ~5700 clk per CTA in instruction fetch)
+    auto tail_t16 = [&](int j, int c16, int valid, float (&t)[16]) {
+      uint32_t rr[16];
+      tc::tmem_ld16(lane_base + S_COL + col0 + c16 * 16, rr);
+      tc::tmem_ld_wait();
+      const float* ut = u0s + j * BKV + col0 + c16 * 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float v = __uint_as_float(rr[i]) * c1;
+        if (has_bias) v = fmaf(wgl, ut[i], v);
+        t[i] = (col0 + c16 * 16 + i < valid) ? v : -INFINITY;
+      }
+    };
+    int it = 0, t0 = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it, t0 += n_tiles) {
+    const int qt = item % p.q_tiles;
+    const int bh = item / p.q_tiles;
+    const int h = bh % p.H, b = bh / p.H;
+    const int q = qt * BQ + row;
+    const bool q_ok = q < p.L;
+    has_bias = p.u0 != nullptr;
     if (has_bias) {
       // an all-zero u0 row means "no bias for this image" (the batched student pass mixes biased
       // and unbiased images): detect it while staging the row and take the cheaper path
       const float* ub = p.u0 + (size_t)b * p.L;
+      if (it > 0) tc::named_bar_sync(1, 256);   // every softmax thread is done with the old row
       uint32_t nz = 0;
       for (int i = t256; i < n_tiles * BKV; i += 256) {
         const float v = (i < p.L) ? ub[i] : 0.f;
@@ -279,32 +327,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
           : "memory");
       has_bias = any != 0;
     }
-    const float c1 = p.scale * LOG2E;
-    float wgl = 0.f;
+    wgl = 0.f;
     if (has_bias) wgl = p.w * LOG2E * ((p.gate && q_ok) ? p.gate[(size_t)b * p.L + q] : 1.f);
     float m_ref = -INFINITY, l_sum = 0.f;
-    const int col0 = half * 64;                 // this thread's key columns of every tile
-    // the tail tile (L % 128 keys, padded to x16) runs through a compact rolled path that re-reads
-    // S from TMEM chunk by chunk: it executes once per CTA, so its code must stay small (a fully
-    // unrolled, predicated copy of the main path cost ~5700 clk per CTA in instruction fetch)
-    auto tail_t16 = [&](int j, int c16, int valid, float (&t)[16]) {
-      uint32_t rr[16];
-      tc::tmem_ld16(lane_base + S_COL + col0 + c16 * 16, rr);
-      tc::tmem_ld_wait();
-      const float* ut = u0s + j * BKV + col0 + c16 * 16;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float v = __uint_as_float(rr[i]) * c1;
-        if (has_bias) v = fmaf(wgl, ut[i], v);
-        t[i] = (col0 + c16 * 16 + i < valid) ? v : -INFINITY;
-      }
-    };
     for (int j = 0; j < n_tiles; ++j) {
       const bool full = j < p.n_full;
       const int n = full ? BKV : p.tail_n;
       const int valid = full ? BKV : p.rem;
       const int mine = max(0, min(64, n - col0));          // columns of this half that exist (x16)
-      tc::mbar_wait(s_full, (uint32_t)j & 1u);
+      const int t = t0 + j;
+      tc::mbar_wait(s_full, (uint32_t)t & 1u);
       tc::fence_after_sync();
       tr.ev(10);
       uint32_t r[64];
@@ -354,7 +386,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
         tr.ev(11);
       }
       // ---- the two halves of a row agree on the tile maximum ----
-      float* xs = xch + (j & 1) * 256;
+      float* xs = xch + (t & 1) * 256;
       xs[half * 128 + row] = mt;
       tc::named_bar_sync(pair_bar, 64);
       tr.ev(12);
@@ -362,7 +394,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       // O += P_{j-1} V_{j-1} must have retired before O is rescaled or the P columns are rewritten
       // (it was issued a whole S-load / max phase ago: this wait is normally already satisfied)
       if (j > 0) {
-        tc::mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);
+        tc::mbar_wait(pv_done, (uint32_t)(t - 1) & 1u);
         tc::fence_after_sync();
       }
       tr.ev(13);
@@ -421,6 +453,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
                          "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
                        : "memory");
         }
+        // second pass done: the S columns may now be overwritten (by the next item's first tile)
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(s_free);
       }
       l_sum += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       tr.ev(14);
@@ -431,11 +467,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       tr.ev(15);
     }
     // ---- epilogue: O / l -> bf16, lse; each half writes its 32 of the 64 head dims ----
-    float* xs = xch + (n_tiles & 1) * 256;
-    xs[half * 128 + row] = l_sum;
+    xch_l[half * 128 + row] = l_sum;
     tc::named_bar_sync(pair_bar, 64);
-    l_sum += xs[(half ^ 1) * 128 + row];
-    tc::mbar_wait(o_final, 0);
+    l_sum += xch_l[(half ^ 1) * 128 + row];
+    tc::mbar_wait(o_final, (uint32_t)it & 1u);
     tc::fence_after_sync();
     const float inv_l = 1.f / l_sum;
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
@@ -457,6 +492,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       }
     }
     if (q_ok && half == 0) p.lse[((size_t)b * p.H + h) * p.L + q] = (m_ref + log2f(l_sum)) * LN2;
+    }   // work items
   }
 
   tc::fence_before_sync();
@@ -484,6 +520,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
 // =============================================================================================
 constexpr int BWD_THREADS = 512;
 constexpr int DP_COL = 128, DV_COL = 256, DK_COL = 320, DQ_COL = 384;
+// K_j and V_j are the A operands of EVERY S^T / dP^T MMA of the CTA: they are copied once into the
+// last 64 TMEM columns (bf16 pairs, 32 columns each), so those MMAs read only the 2 KB B operand
+// from shared memory (an SS 128x64x16 MMA moves 6 KB per 32-clk slot: shared-memory bound)
+constexpr int KT_COL = 448, VT_COL = 480;
 
 struct BwdParams {
   void* dqkv;            // [B, L, 3*H*64] bf16 (dK, dV written here; dQ by the convert kernel)
@@ -520,22 +560,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const uint32_t sV = base + TILE_BYTES;
   const uint32_t sQ = base + 2 * TILE_BYTES;      // 2 stages
   const uint32_t sdO = base + 4 * TILE_BYTES;     // 2 stages
-  const uint32_t sdS = base + 6 * TILE_BYTES;     // 32 KB: [2 query halves][128 keys][64 q] bf16
-  const uint32_t sdQ = base + 8 * TILE_BYTES;     // 32 KB fp32 staging
-  const uint32_t bar = base + 10 * TILE_BYTES;
+  const uint32_t sdS = base + 6 * TILE_BYTES;     // 2 x 32 KB: [tile parity][2 query halves][128 keys][64 q] bf16
+  const uint32_t sdQ = base + 10 * TILE_BYTES;    // 32 KB fp32 staging
+  const uint32_t bar = base + 12 * TILE_BYTES;
   const uint32_t kv_full = bar;
   auto qd_full = [&](int s) { return bar + 8u * (1 + s); };
   auto qd_empty = [&](int s) { return bar + 8u * (3 + s); };
   auto sdp_full = [&](int h) { return bar + 8u * (5 + h); };
   auto pds_full = [&](int h) { return bar + 8u * (7 + h); };
-  const uint32_t dq_done = bar + 8u * 9;
-  const uint32_t dq_empty = bar + 8u * 10;
-  const uint32_t dvk_full = bar + 8u * 11;
-  const uint32_t tmem_slot = bar + 8u * 12;
+  // dQ_i = dS_i K retired: one barrier per dS staging buffer (tile parity), so "tile i-2 done" can
+  // never be confused with "tile i-1 done"
+  auto dq_done = [&](int par) { return bar + 8u * (9 + par); };
+  const uint32_t dq_empty = bar + 8u * 11;
+  const uint32_t dvk_full = bar + 8u * 12;
+  const uint32_t kvt_full = bar + 8u * 13;    // K_j / V_j copied into TMEM
+  const uint32_t tmem_slot = bar + 8u * 14;
   uint8_t* gen = smem_raw + (base - raw);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 10 * TILE_BYTES + 8 * 12);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 12 * TILE_BYTES + 8 * 14);
   const int lpad = p.q_tiles * 128;
-  float* lse2s = reinterpret_cast<float*>(gen + 10 * TILE_BYTES + 128);
+  float* lse2s = reinterpret_cast<float*>(gen + 12 * TILE_BYTES + 128);
   float* dlts = lse2s + lpad;
   float* wgls = dlts + lpad;
 
@@ -556,9 +599,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tc::mbar_init(sdp_full(s), 1);
       tc::mbar_init(pds_full(s), 4);
     }
-    tc::mbar_init(dq_done, 1);
+    tc::mbar_init(dq_done(0), 1);
+    tc::mbar_init(dq_done(1), 1);
     tc::mbar_init(dq_empty, 4);
     tc::mbar_init(dvk_full, 1);
+    tc::mbar_init(kvt_full, 8);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
@@ -596,7 +641,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       constexpr uint32_t KM = 1u << 16;                    // K-major operand: LBO field 1
       constexpr uint32_t MN = (16384u >> 4) << 16;         // MN-major operand: LBO 16384
       auto dsc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
-      const uint32_t k_lo = (sK >> 4) & 0x3FFFu, v_lo = (sV >> 4) & 0x3FFFu, ds_lo = (sdS >> 4) & 0x3FFFu;
+      const uint32_t k_lo = (sK >> 4) & 0x3FFFu, ds_lo = (sdS >> 4) & 0x3FFFu;
       uint32_t acc_dvk = 0;
       auto issue_sdp = [&](int i, int hh) {
         const int st = i & 1;
@@ -606,11 +651,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc::mma_f16_ss(tmem + hh * 64, dsc((k_lo + k * 2) | KM), dsc((q_lo + k * 2) | KM), idesc,
+            tc::mma_f16_ts(tmem + hh * 64, tmem + KT_COL + k * 8, dsc((q_lo + k * 2) | KM), idesc,
                            k > 0 ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc::mma_f16_ss(tmem + DP_COL + hh * 64, dsc((v_lo + k * 2) | KM), dsc((do_lo + k * 2) | KM), idesc,
+            tc::mma_f16_ts(tmem + DP_COL + hh * 64, tmem + VT_COL + k * 8, dsc((do_lo + k * 2) | KM), idesc,
                            k > 0 ? 1u : 0u);
           tc::mma_commit(sdp_full(hh));
         }
@@ -643,6 +688,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         __syncwarp();
       };
       tc::mbar_wait(kv_full, 0);
+      tc::mbar_wait(kvt_full, 0);
       tc::mbar_wait(qd_full(0), 0);
       tc::fence_after_sync();
       issue_sdp(0, 0);
@@ -670,20 +716,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         if (leader) tc::mma_commit(qd_empty(st));
         __syncwarp();
         tr.ev(6);
+        // S^T / dP^T of the next tile's second half go first: warpgroup 1 restarts without waiting
+        // for dQ_i (the dS staging buffer is double-buffered, nobody is blocked on dQ_i)
+        if (i + 1 < nq) issue_sdp(i + 1, 1);
+        tr.ev(9);
         tc::mbar_wait(dq_empty, ph ^ 1u);
         tc::fence_after_sync();
         tr.ev(7);
         if (leader) {
+          const uint32_t dsb = ds_lo + (uint32_t)st * (32768u >> 4);
 #pragma unroll
           for (int s = 0; s < 8; ++s)
-            tc::mma_f16_ss(tmem + DQ_COL, dsc((ds_lo + s * 128) | MN), dsc((k_lo + s * 128) | MN), idesc_dq,
+            tc::mma_f16_ss(tmem + DQ_COL, dsc((dsb + s * 128) | MN), dsc((k_lo + s * 128) | MN), idesc_dq,
                            s > 0 ? 1u : 0u);
-          tc::mma_commit(dq_done);
+          tc::mma_commit(dq_done(st));
         }
         __syncwarp();
         tr.ev(8);
-        if (i + 1 < nq) issue_sdp(i + 1, 1);
-        tr.ev(9);
       }
       if (leader) tc::mma_commit(dvk_full);
       __syncwarp();
@@ -712,45 +761,59 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
       tc::named_bar_sync(1, 256);
     }
+    {
+      // this thread's key row of K_j (warpgroup 0) / V_j (warpgroup 1): 128 B of the 128B-swizzled
+      // TMA tile -> 32 TMEM columns of bf16 pairs (the A-operand layout of a kind::f16 MMA)
+      tc::mbar_wait(kv_full, 0);
+      const uint32_t src = (hh == 0 ? sK : sV) + row * 128;
+      uint32_t kv[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(kv[4 * c]), "=r"(kv[4 * c + 1]), "=r"(kv[4 * c + 2]), "=r"(kv[4 * c + 3])
+                     : "r"(src + ((((uint32_t)c) ^ (uint32_t)(row & 7)) << 4)));
+      tc::tmem_st32(lane_base + (hh == 0 ? KT_COL : VT_COL), kv);
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(kvt_full);
+    }
     const float u0k = (p.u0 && key_ok) ? p.u0[(size_t)b * p.L + key] : 0.f;
     const float c1 = p.scale * LOG2E;
-    const uint32_t ds_row = sdS + hh * 16384 + row * 128;
+    const uint32_t ds_row0 = sdS + hh * 16384 + row * 128;
     const uint32_t swz = (uint32_t)(row & 7);
     for (int i = 0; i < nq; ++i) {
       const int n = bwd_half_n(p.L, i, hh);
+      const uint32_t ds_row = ds_row0 + (uint32_t)(i & 1) * 32768u;
       tc::mbar_wait(sdp_full(hh), (uint32_t)i & 1u);
       tc::fence_after_sync();
       tr.ev(10);
       const int qbase = i * 128 + hh * 64;
-      for (int c16 = 0; c16 < (n >> 4); ++c16) {
-        uint32_t sv[16], dv[16];
-        tc::tmem_ld16(lane_base + hh * 64 + c16 * 16, sv);
-        tc::tmem_ld16(lane_base + DP_COL + hh * 64 + c16 * 16, dv);
-        float ls[16], dd[16], wg[16];
+      // one 16-query chunk: P^T = 2^(S^T c + bias - lse), dS^T = P^T (dP^T - D) -> bf16 over S / dP in
+      // TMEM (the A operands of the dV / dK MMAs) and dS^T into the swizzled staging tile (dQ MMA)
+      auto chunk = [&](int c16, const uint32_t (&sv)[16], const uint32_t (&dv)[16]) {
+        uint32_t pp[8], dsp[8];
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
           const float4 a4 = *reinterpret_cast<const float4*>(lse2s + qbase + c16 * 16 + v4 * 4);
           const float4 b4 = *reinterpret_cast<const float4*>(dlts + qbase + c16 * 16 + v4 * 4);
           const float4 c4 = *reinterpret_cast<const float4*>(wgls + qbase + c16 * 16 + v4 * 4);
-          ls[v4 * 4] = a4.x; ls[v4 * 4 + 1] = a4.y; ls[v4 * 4 + 2] = a4.z; ls[v4 * 4 + 3] = a4.w;
-          dd[v4 * 4] = b4.x; dd[v4 * 4 + 1] = b4.y; dd[v4 * 4 + 2] = b4.z; dd[v4 * 4 + 3] = b4.w;
-          wg[v4 * 4] = c4.x; wg[v4 * 4 + 1] = c4.y; wg[v4 * 4 + 2] = c4.z; wg[v4 * 4 + 3] = c4.w;
-        }
-        tc::tmem_ld_wait();
-        uint32_t pp[8], dsp[8];
+          const float ls[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float dd[4] = {b4.x, b4.y, b4.z, b4.w};
+          const float wg[4] = {c4.x, c4.y, c4.z, c4.w};
+          float pv[4], dsv[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float pv[2], dsv[2];
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            const int c = 2 * e + x;
-            const float t = fmaf(__uint_as_float(sv[c]), c1, fmaf(wg[c], u0k, -ls[c]));
+          for (int x = 0; x < 4; ++x) {
+            const int c = 4 * v4 + x;
+            const float t = fmaf(__uint_as_float(sv[c]), c1, fmaf(wg[x], u0k, -ls[x]));
             const float pe = key_ok ? tc::ex2(t) : 0.f;
             pv[x] = pe;
-            dsv[x] = pe * (__uint_as_float(dv[c]) - dd[c]);
+            dsv[x] = pe * (__uint_as_float(dv[c]) - dd[x]);
           }
-          pp[e] = pack_bf16(pv[0], pv[1]);
-          dsp[e] = pack_bf16(dsv[0], dsv[1]);
+          pp[2 * v4] = pack_bf16(pv[0], pv[1]);
+          pp[2 * v4 + 1] = pack_bf16(pv[2], pv[3]);
+          dsp[2 * v4] = pack_bf16(dsv[0], dsv[1]);
+          dsp[2 * v4 + 1] = pack_bf16(dsv[2], dsv[3]);
         }
         asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                      ::"r"(lane_base + hh * 64 + c16 * 8), "r"(pp[0]), "r"(pp[1]), "r"(pp[2]), "r"(pp[3]),
@@ -758,9 +821,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                      ::"r"(lane_base + DP_COL + hh * 64 + c16 * 8), "r"(dsp[0]), "r"(dsp[1]), "r"(dsp[2]),
                        "r"(dsp[3]), "r"(dsp[4]), "r"(dsp[5]), "r"(dsp[6]), "r"(dsp[7]) : "memory");
-        if (c16 == 0 && i > 0) {   // the dQ MMA of the previous tile must have consumed sdS
+        if (c16 == 0 && i > 1) {   // dQ_{i-2} must have consumed this dS staging buffer
           tr.ev(11);
-          tc::mbar_wait(dq_done, (uint32_t)(i - 1) & 1u);
+          tc::mbar_wait(dq_done(i & 1), (uint32_t)((i >> 1) - 1) & 1u);
           tr.ev(12);
         }
         // dS^T row (this key) for queries [c16*16, +16): two 16-byte chunks of the swizzled row
@@ -768,6 +831,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                      "r"(dsp[0]), "r"(dsp[1]), "r"(dsp[2]), "r"(dsp[3]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + ((((uint32_t)(2 * c16 + 1)) ^ swz) << 4)),
                      "r"(dsp[4]), "r"(dsp[5]), "r"(dsp[6]), "r"(dsp[7]) : "memory");
+      };
+      if (n == 64) {
+        // full half tile: the TMEM loads of chunk c+1 are in flight while chunk c is computed
+        uint32_t sa[16], da[16], sb[16], db[16];
+        tc::tmem_ld16(lane_base + hh * 64, sa);
+        tc::tmem_ld16(lane_base + DP_COL + hh * 64, da);
+        tc::tmem_ld_wait();
+        tc::tmem_ld16(lane_base + hh * 64 + 16, sb);
+        tc::tmem_ld16(lane_base + DP_COL + hh * 64 + 16, db);
+        chunk(0, sa, da);
+        tc::tmem_ld_wait();
+        tc::tmem_ld16(lane_base + hh * 64 + 32, sa);
+        tc::tmem_ld16(lane_base + DP_COL + hh * 64 + 32, da);
+        chunk(1, sb, db);
+        tc::tmem_ld_wait();
+        tc::tmem_ld16(lane_base + hh * 64 + 48, sb);
+        tc::tmem_ld16(lane_base + DP_COL + hh * 64 + 48, db);
+        chunk(2, sa, da);
+        tc::tmem_ld_wait();
+        chunk(3, sb, db);
+      } else {
+        for (int c16 = 0; c16 < (n >> 4); ++c16) {
+          uint32_t sv[16], dv[16];
+          tc::tmem_ld16(lane_base + hh * 64 + c16 * 16, sv);
+          tc::tmem_ld16(lane_base + DP_COL + hh * 64 + c16 * 16, dv);
+          tc::tmem_ld_wait();
+          chunk(c16, sv, dv);
+        }
       }
       tr.ev(13);
       tc::tmem_st_wait();
@@ -812,7 +903,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const uint32_t swz = (uint32_t)(row & 15);
     float* acc_base = p.dq_accum + ((size_t)(b * p.H + h) * p.q_tiles) * (128 * 64);
     for (int i = 0; i < nq; ++i) {
-      tc::mbar_wait(dq_done, (uint32_t)i & 1u);
+      tc::mbar_wait(dq_done(i & 1), (uint32_t)(i >> 1) & 1u);
       tc::fence_after_sync();
       tr.ev(20);
       uint32_t o0[32], o1[32];
@@ -964,7 +1055,7 @@ int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, flo
   p.rem = L % BKV;
   p.tail_n = (p.rem + 15) & ~15;
   const int n_tiles = p.n_full + (p.tail_n ? 1 : 0);
-  const size_t smem = 1024 + 5 * TILE_BYTES + 128 + 2048 + (size_t)n_tiles * BKV * 4;
+  const size_t smem = 1024 + 5 * TILE_BYTES + 128 + 3072 + (size_t)n_tiles * BKV * 4;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -979,8 +1070,10 @@ int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, flo
   const double flops = 4.0 * B * H * (double)L * L * HD;
   S4ProfScope prof("attn_fwd_tc", flops, 0, st);
   p.trace = g_trace;
-  if (g_trace.buf) attn_fwd_kernel<true><<<B * H * p.q_tiles, FWD_THREADS, smem, st>>>(tm, p);
-  else attn_fwd_kernel<false><<<B * H * p.q_tiles, FWD_THREADS, smem, st>>>(tm, p);
+  const int n_items = B * H * p.q_tiles;
+  const int grid = std::min(n_items, 2 * s4_num_sms());     // persistent: two co-resident CTAs per SM
+  if (g_trace.buf) attn_fwd_kernel<true><<<grid, FWD_THREADS, smem, st>>>(tm, p);
+  else attn_fwd_kernel<false><<<grid, FWD_THREADS, smem, st>>>(tm, p);
   return s4_check_launch("attn_fwd_tc");
 }
 
@@ -1020,7 +1113,7 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
   p.dqkv = dqkv; p.dq_accum = dq_accum; p.lse = lse; p.delta = delta; p.u0 = u0; p.gate = gate;
   p.w = w; p.scale = 1.0f / sqrtf((float)hd);
   p.B = B; p.H = H; p.L = L; p.q_tiles = q_tiles;
-  const size_t smem = 1024 + 10 * TILE_BYTES + 128 + (size_t)3 * q_tiles * 128 * 4;
+  const size_t smem = 1024 + 12 * TILE_BYTES + 128 + (size_t)3 * q_tiles * 128 * 4;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -7,7 +7,7 @@ from s4former_b200 import ops, _lib as L
 
 what = sys.argv[1] if len(sys.argv) > 1 else 'fwd'
 B, H, Lt, hd = int(os.environ.get('S4_BENCH_B', '24')), 12, 1025, 64
-block = int(sys.argv[2]) if len(sys.argv) > 2 else (B * H * 9) // 2 + 3
+block = int(sys.argv[2]) if len(sys.argv) > 2 else 101
 dev = 'cuda'
 lib = L.load()
 D = H * hd
