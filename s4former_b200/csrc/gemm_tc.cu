@@ -188,10 +188,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ================================ TMA producer ==========================================
-    // One thread.  The per-k-block body is kept to a handful of instructions (it must stay
-    // well under the 4 x 128-cycle MMA time of a k-block): all coordinate arithmetic is
-    // incremental, no divisions inside the loop.
-    if (lane == 0) {
+    // The whole warp walks the tiles in uniform control flow (coordinates live in uniform
+    // registers); the elected lane issues the TMA instructions.  The per-k-block body is kept to a
+    // handful of instructions (it must stay well under the 4 x 128-cycle MMA time of a k-block):
+    // all coordinate arithmetic is incremental, no divisions inside the loop.
+    {
+      const bool leader = tc::elect_one();
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t a_bytes = (p.a_mode == OP_CONV_K) ? (uint32_t)(p.cTW * p.cTH * BK * 2)
@@ -199,8 +201,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // pair mode: the leader's barrier counts the bytes landing in BOTH CTAs
       const uint32_t tx_bytes = (a_bytes + (uint32_t)C::B_STAGE_BYTES) * CT;
       auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
-        if (PAIR) tc::tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
-        else tc::tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+        if (leader) {
+          if (PAIR) tc::tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
+          else tc::tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+        }
       };
       const int nb_off = rank * C::BN_CTA;          // this CTA's slice of the B tile
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
@@ -211,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kb = t.kb0; kb < t.kb1; ++kb, k0 += BK) {
             tc::mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = base + stage * C::STAGE_BYTES;
-            if (rank == 0) tc::mbar_expect_tx(full_bar(stage), tx_bytes);
+            if (rank == 0 && leader) tc::mbar_expect_tx(full_bar(stage), tx_bytes);
             load(sa, &tmA, full_bar(stage), k0, t.m0, t.z2, t.z1);
             load(sa + A_STAGE_BYTES, &tmB, full_bar(stage), k0, t.n0 + nb_off, t.z2, t.z1);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -250,7 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
-          if (rank == 0) tc::mbar_expect_tx(full_bar(stage), tx_bytes);
+          if (rank == 0 && leader) tc::mbar_expect_tx(full_bar(stage), tx_bytes);
           // ---- A ----
           if (p.a_mode == OP_KMAJOR) {
             load(sa, &tmA, full_bar(stage), k0, t.m0, t.z2, t.z1);
@@ -290,10 +294,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
-    // ONE thread runs the whole loop (tcgen05.mma / commit are single-thread instructions): no
-    // per-k-block elect / warp sync, descriptors are built from precomputed constants with one
-    // add per MMA, so the issue loop is far shorter than the MMAs it feeds.
-    if (lane == 0 && rank == 0) {
+    // The WHOLE warp runs the loop and the waits in uniform control flow, so tile coordinates and
+    // descriptors are warp-uniform values in uniform registers; the elected lane issues the
+    // tcgen05.mma / commit instructions.  (Issuing from a `lane == 0` branch makes ptxas wrap every
+    // tcgen05.mma in a serialising elect loop with five R2UR.BROADCASTs: ~100 clk per MMA, as
+    // long as a 128x128x16 MMA itself.)
+    if (rank == 0) {
+      const bool leader = tc::elect_one();
       const int a_mn = (p.a_mode == OP_MNMAJOR) ? 1 : 0;
       const int b_mn = (p.b_mode == OP_MNMAJOR || p.b_mode == OP_CONV_MN) ? 1 : 0;
       const uint32_t idesc = tc::make_idesc_bf16(BM * CT, BN, a_mn, b_mn);
@@ -323,16 +330,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | a_lo_fixed;
           const uint32_t b_lo = (((sa + A_STAGE_BYTES) >> 4) & 0x3FFFu) | b_lo_fixed;
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * a_kstep);
-            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * b_kstep);
-            if (PAIR) tc::mma_f16_ss_pair(d_tmem, ad, bd, idesc, accum);
-            else tc::mma_f16_ss(d_tmem, ad, bd, idesc, accum);
-            accum = 1;
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * a_kstep);
+              const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * b_kstep);
+              if (PAIR) tc::mma_f16_ss_pair(d_tmem, ad, bd, idesc, (k > 0) ? 1u : accum);
+              else tc::mma_f16_ss(d_tmem, ad, bd, idesc, (k > 0) ? 1u : accum);
+            }
+            commit(empty_bar(stage));                       // frees the smem slot when MMAs retire
+            if (kb == t.kb1 - 1) commit(tfull_bar(acc));    // accumulator ready
           }
-          commit(empty_bar(stage));                       // frees the smem slot when MMAs retire
-          if (kb == t.kb1 - 1) commit(tfull_bar(acc));    // accumulator ready
+          __syncwarp();
+          accum = 1;
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
