@@ -258,6 +258,7 @@ def main():
 
     img, gt, metas = make_batch(a.sup, n_unsup, a.size, a.classes, seed=1999 + rank)
     img_h, gt_h = img.pin_memory(), gt.pin_memory()
+    img_h2, gt_h2 = [img_h, img.clone().pin_memory()], [gt_h, gt.clone().pin_memory()]   # two pinned batches
     img_d, gt_d = img_h.to(dev), gt_h.to(dev)
     mask_ratio = None
     if n_unsup:
@@ -273,12 +274,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, k):
+    host_ms = [0.0]
+
+    def timed(fn, k, after=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         for i in range(k):
             fn(i)
+        host_ms[0] = (time.perf_counter() - t_host) * 1e3 / k     # host enqueue time per step
+        if after is not None:
+            after()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -294,10 +301,23 @@ def main():
 
     last = {}
 
-    def run_e2e(_):
-        loss, lv = step.step_from_host(img_h, fresh_metas(metas), gt_h, it[0])
-        last.update(lv)
+    pend = []
+
+    def run_e2e(i, k=None):
+        # the dataloader's next pinned batch is copied on a side stream while this step runs (every
+        # step's H2D copy is issued inside the timed region; the last one prefetches nothing) and
+        # the step's log variables are read back one step late (every step's D2H read happens too)
+        if k is not None and i + 1 < k:
+            step.prefetch(img_h2[(i + 1) & 1], gt_h2[(i + 1) & 1])
+        loss, p_ = step.step_from_host(img_h2[i & 1], fresh_metas(metas), gt_h2[i & 1], it[0], deferred=True)
+        pend.append(p_)
+        if len(pend) > 1:
+            last.update(pend.pop(0)())
         it[0] += 1
+
+    def drain_e2e():
+        while pend:
+            last.update(pend.pop(0)())
 
     for i in range(max(a.warmup, 3)):
         run_resident(i)
@@ -306,9 +326,11 @@ def main():
         clocks.start()
     l0 = lib.s4_launch_count()
     ms = timed(run_resident, a.steps)
+    host_enqueue_ms = host_ms[0]
     launches = (lib.s4_launch_count() - l0) // a.steps
     run_e2e(0)
-    ms_e2e = timed(run_e2e, a.steps)
+    drain_e2e()
+    ms_e2e = timed(lambda i: run_e2e(i, a.steps), a.steps, after=drain_e2e)
     clk = clocks.stop() if rank == 0 else None
     loss_val = last.get('loss')
     assert loss_val == loss_val, 'loss is NaN'
@@ -372,6 +394,7 @@ def main():
                         h2d_bytes_per_step=img_h.numel() * 4 + gt_h.numel() * 8,
                         d2h_bytes_per_step=4 * len(last)),
                gpu_launches=int(launches) * a.steps, gpu_launches_per_step=int(launches),
+               host_enqueue_ms_per_step=host_enqueue_ms,
                clocks=clk, roofline=roofline,
                kernels=sorted(kinds, key=lambda k: -k["ms_per_step"])[:40])
     if world == 1 and not a.no_cpu_baseline:

@@ -696,14 +696,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       for (int i = 0; i < nq; ++i) {
         const int st = i & 1;
         const uint32_t ph = (uint32_t)i & 1u;
+        // Q_{i+1} / dO_{i+1} were requested a whole tile ago: waiting for them here (idle time of
+        // this warp) keeps the wait off the dV/dK -> S^T/dP^T critical path below
+        if (i + 1 < nq) tc::mbar_wait(qd_full(st ^ 1), ((uint32_t)(i + 1) >> 1) & 1u);
         tc::mbar_wait(pds_full(0), ph);
         tc::fence_after_sync();
         tr.ev(1);
         issue_dvk(i, 0, acc_dvk);
         tr.ev(2);
         if (i + 1 < nq) {
-          tc::mbar_wait(qd_full(st ^ 1), ((uint32_t)(i + 1) >> 1) & 1u);
-          tc::fence_after_sync();
           tr.ev(3);
           issue_sdp(i + 1, 0);
           tr.ev(4);

@@ -42,9 +42,75 @@ class TrainStep:
             log_vars = type(log_vars)(zip(log_vars.keys(), packed))
         return loss, log_vars
 
-    def step_from_host(self, img_host, img_metas, gt_host, it):
+    # ---- end-to-end iteration (host batch in, host log variables out) ---------------------------
+    # Two persistent device staging slots (no allocator traffic in the loop): the copy of batch
+    # i+1 runs on a side stream while step i computes; a slot is rewritten only after the step
+    # that read it has finished on the compute stream.
+    def _slot(self, k, img_host, gt_host):
+        slots = self.__dict__.setdefault('_slots', [None, None])
+        sl = slots[k]
+        if sl is None or sl['img'].shape != img_host.shape or sl['gt'].shape != gt_host.shape:
+            sl = dict(img=torch.empty(img_host.shape, dtype=img_host.dtype, device=self.device),
+                      gt=torch.empty(gt_host.shape, dtype=gt_host.dtype, device=self.device),
+                      free=None, ready=None, log_host=None)
+            slots[k] = sl
+        return sl
+
+    def _start_copy(self, k, img_host, gt_host):
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        s = self._copy_stream
+        sl = self._slot(k, img_host, gt_host)
+        if sl['free'] is not None:
+            s.wait_event(sl['free'])
+        else:
+            s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            sl['img'].copy_(img_host, non_blocking=True)
+            sl['gt'].copy_(gt_host, non_blocking=True)
+            sl['ready'] = torch.cuda.Event()
+            sl['ready'].record(s)
+        return sl
+
+    def prefetch(self, img_host, gt_host):
+        """Start the host->device copy of a coming batch on a side stream, so that it overlaps the
+        step in flight (the dataloader's pinned batch is known one iteration ahead).  The next
+        ``step_from_host`` call on the same host tensors consumes it."""
+        k = getattr(self, '_next_slot', 0)
+        self._start_copy(k, img_host, gt_host)
+        self._prefetched = (img_host.data_ptr(), gt_host.data_ptr(), k)
+
+    def step_from_host(self, img_host, img_metas, gt_host, it, deferred=False):
         """End-to-end iteration: pinned host batch -> device, step, log variables back on the host
-        (what the runner's dataloader scatter + ``log_vars`` ``.item()`` do in the reference)."""
-        img = img_host.to(self.device, non_blocking=True)
-        gt = gt_host.to(self.device, non_blocking=True)
-        return self(img, img_metas, gt, it, sync=True)
+        (what the runner's dataloader scatter + ``log_vars`` ``.item()`` do in the reference).
+
+        ``deferred=True`` returns ``(loss, pending)`` where ``pending()`` yields the host log
+        variables: the device->host copy is queued behind the step and read later, so the host
+        can enqueue the next iteration instead of idling the GPU at every step boundary."""
+        pf = getattr(self, '_prefetched', None)
+        self._prefetched = None
+        if pf is not None and pf[0] == img_host.data_ptr() and pf[1] == gt_host.data_ptr():
+            k = pf[2]
+            sl = self._slot(k, img_host, gt_host)
+        else:
+            k = getattr(self, '_next_slot', 0)
+            sl = self._start_copy(k, img_host, gt_host)
+        self._next_slot = k ^ 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(sl['ready'])
+        loss, log_vars = self(sl['img'], img_metas, sl['gt'], it, sync=False)
+        keys = list(log_vars.keys())
+        if sl['log_host'] is None or sl['log_host'].numel() != len(keys):
+            sl['log_host'] = torch.empty(len(keys), dtype=torch.float32, pin_memory=True)
+        host = sl['log_host']
+        host.copy_(torch.stack([v.detach().float().reshape(()) for v in log_vars.values()]), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        sl['free'] = ev            # the slot (and its pinned log buffer) is reusable after this point
+
+        def pending():
+            ev.synchronize()
+            return type(log_vars)(zip(keys, host.tolist()))
+        if deferred:
+            return loss, pending
+        return loss, pending()
