@@ -107,7 +107,7 @@ ln_fwd_kernel(const T* __restrict__ x, const int* __restrict__ row_map,
 // dgamma/dbeta: every warp keeps register partials over its rows, the block folds them through
 // shared memory (plain stores, one slab per warp) and issues ONE global atomic per column.
 template <typename T, int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 4)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __restrict__ row_map,
               const float* __restrict__ gamma, const float* __restrict__ mean,
               const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx,
@@ -260,7 +260,7 @@ extern "C" int s4_layernorm_bwd(const void* dy, const void* x, const int* row_ma
   // blocks would not)
   constexpr int BT = 128;
   int blocks = (rows + 3) / 4;
-  const int cap = s4_num_sms() * 3;
+  const int cap = s4_num_sms() * 4;
   if (blocks > cap) blocks = cap;
   const size_t smem = (BT / 32) * 2 * (size_t)D * sizeof(float);
   if (smem > 48 * 1024) {

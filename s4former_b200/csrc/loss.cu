@@ -58,6 +58,63 @@ pseudo_label_kernel(const float* __restrict__ z, long long* __restrict__ hard,
   }
 }
 
+// Two pixels per thread (W % 64 == 0): every class plane is read as 8-byte vectors, a block row
+// covers 256 contiguous bytes of each plane (a 32-thread row of the scalar kernel touches 128 B
+// at a 2 KB stride: poor DRAM page locality, ~1 TB/s).  Arithmetic per pixel is unchanged.
+template <int MAXC>
+__global__ void __launch_bounds__(512)
+pseudo_label_vec2_kernel(const float* __restrict__ z, long long* __restrict__ hard,
+                         long long* __restrict__ conf, float* __restrict__ u, int C, int H, int W,
+                         int patch, float thr) {
+  __shared__ int cnt[2 * 8];  // up to (16/8) x (64/8) patch cells
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * 32 + tx;
+  if (tid < 16) cnt[tid] = 0;
+  __syncthreads();
+  const int x = blockIdx.x * 64 + tx * 2, y = blockIdx.y * 16 + ty, b = blockIdx.z;
+  const size_t plane = (size_t)H * W;
+  const float* zp = z + (size_t)b * C * plane + (size_t)y * W + x;
+  float2 v[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+    if (c < C) v[c] = __ldg(reinterpret_cast<const float2*>(zp + c * plane));
+  long long hv[2], cv[2];
+  int unconf = 0;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    float m = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) {
+        const float val = e == 0 ? v[c].x : v[c].y;
+        if (val > m) { m = val; arg = c; }   // first index wins on ties
+      }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) s += expf((e == 0 ? v[c].x : v[c].y) - m);
+    const float pmax = 1.0f / s;               // expf(0)/sum
+    const int confident = pmax > thr;
+    hv[e] = confident ? (long long)arg : 255ll;
+    cv[e] = confident;
+    unconf += confident ? 0 : 1;
+  }
+  const size_t o = (size_t)b * plane + (size_t)y * W + x;
+  *reinterpret_cast<longlong2*>(hard + o) = make_longlong2(hv[0], hv[1]);
+  *reinterpret_cast<longlong2*>(conf + o) = make_longlong2(cv[0], cv[1]);
+  const int cells_x = 64 / patch;              // 2 consecutive pixels never straddle a cell
+  if (unconf) atomicAdd(&cnt[(ty / patch) * cells_x + (tx * 2) / patch], unconf);
+  __syncthreads();
+  const int cells_y = 16 / patch;
+  if (tid < cells_x * cells_y) {
+    const int cy = tid / cells_x, cx = tid % cells_x;
+    const int gh = H / patch, gw = W / patch;
+    const int py = blockIdx.y * cells_y + cy, px = blockIdx.x * cells_x + cx;
+    u[((size_t)b * gh + py) * gw + px] = (float)cnt[tid] / (float)(patch * patch);
+  }
+}
+
 extern "C" int s4_pseudo_label(const float* logits, long long* hard, long long* conf, float* u,
                                int B, int C, int H, int W, int patch, float threshold,
                                cudaStream_t stream) {
@@ -67,6 +124,14 @@ extern "C" int s4_pseudo_label(const float* logits, long long* hard, long long* 
   S4_REQUIRE(H % 16 == 0 && W % 32 == 0, "pseudo_label: H%%16, W%%32 required (H=%d W=%d)", H, W);
   if (B == 0) return S4_OK;
   dim3 grid(W / 32, H / 16, B), block(32, 16);
+  if (W % 64 == 0 && (((uintptr_t)logits | (uintptr_t)hard | (uintptr_t)conf) & 15) == 0) {
+    grid.x = W / 64;
+    if (C <= 24)
+      pseudo_label_vec2_kernel<24><<<grid, block, 0, stream>>>(logits, hard, conf, u, C, H, W, patch, threshold);
+    else
+      pseudo_label_vec2_kernel<S4_MAXC><<<grid, block, 0, stream>>>(logits, hard, conf, u, C, H, W, patch, threshold);
+    return s4_check_launch("pseudo_label");
+  }
   pseudo_label_kernel<<<grid, block, 0, stream>>>(logits, hard, conf, u, C, H, W, patch, threshold);
   return s4_check_launch("pseudo_label");
 }
@@ -83,7 +148,7 @@ extern "C" int s4_pseudo_label(const float* logits, long long* hard, long long* 
 // SKIP_IF_EQUAL: gradient fix-up launch -- returns at once unless gscale[0] != gscale[1]
 // (see s4_ce_ncr_grad_fixup).
 template <bool WRITE_DZ, bool HAS_T, bool SKIP_IF_EQUAL>
-__global__ void __launch_bounds__(256, HAS_T ? 2 : 4)   // NCR: <= 128 registers (2 blocks/SM); CE only: <= 64 (4)
+__global__ void __launch_bounds__(256, HAS_T ? 3 : 4)   // NCR: <= 85 registers (3 blocks/SM); CE only: <= 64 (4)
 ce_ncr_kernel(const float* __restrict__ zs, const float* __restrict__ zt,
               const long long* __restrict__ label, float* __restrict__ dz,
               float* __restrict__ partial, int C, size_t plane, size_t npix, float ce_scale,

@@ -355,6 +355,18 @@ def test_pseudo_label_large_random():
     assert int(near.sum()) < 16
     if int(near.sum()) == 0:
         assert torch.equal(u.cpu(), O.patch_unconfidence(c0, 16))
+    # W % 64 != 0: scalar kernel; C > 24: wide instantiation of the vector kernel; patch 8
+    for shape in ((1, 19, 32, 96), (1, 30, 32, 128)):
+        z = (torch.randn(*shape, generator=g) * 4)
+        hard, conf, u = ops.pseudo_label(z.to(DEV), 0.95, 8)
+        h0, c0, mv = O.pseudo_label(z, 0.95)
+        near = (mv - 0.95).abs() < 1e-6
+        assert torch.equal(conf.cpu()[~near], c0[~near])
+        assert torch.equal(hard.cpu()[~near], h0[~near])
+        if int(near.sum()) == 0:
+            bb, hh, ww = c0.shape
+            want = (1 - c0).view(bb, hh // 8, 8, ww // 8, 8).permute(0, 1, 3, 2, 4).reshape(bb, hh // 8, ww // 8, -1)
+            assert torch.equal(u.cpu(), want.sum(-1) / 64)
 
 
 def test_ce_ncr_golden_and_grad(golden_dir):
@@ -513,3 +525,14 @@ def test_patchify_and_tokens():
     L.call('s4_patchify', img.data_ptr(), a.data_ptr(), 2, 3, 64, 64, 16, L.F32, torch.cuda.current_stream().cuda_stream)
     want = F.unfold(img, 16, stride=16).transpose(1, 2).reshape(32, 768)
     assert torch.equal(a, want)
+    # bf16 vector path (8 pixels per thread), including the reference's corner padding
+    # (embed.py:58-80: H, W padded up to a multiple of the patch size with zeros)
+    for (Hh, Ww) in ((64, 64), (56, 72)):
+        img = torch.randn(3, 3, Hh, Ww, generator=g).to(DEV)
+        gh, gw = (Hh + 15) // 16, (Ww + 15) // 16
+        a16 = torch.empty(3 * gh * gw, 768, device=DEV, dtype=torch.bfloat16)
+        L.call('s4_patchify', img.data_ptr(), a16.data_ptr(), 3, 3, Hh, Ww, 16, L.BF16,
+               torch.cuda.current_stream().cuda_stream)
+        pad = F.pad(img, (0, gw * 16 - Ww, 0, gh * 16 - Hh))
+        want = F.unfold(pad, 16, stride=16).transpose(1, 2).reshape(3 * gh * gw, 768).to(torch.bfloat16)
+        assert torch.equal(a16, want)
