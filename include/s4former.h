@@ -166,8 +166,8 @@ int s4_pack_conv3x3_weight(const float* w, void* w_fwd, void* w_dgrad, int Cin, 
  * momentum (unbiased var), as torch.nn.BatchNorm2d / SyncBatchNorm.  running_* may be NULL. */
 int s4_bn_finalize(const float* sum, const float* sumsq, double count, float eps, float momentum,
                    const float* gamma, const float* beta, float* mean, float* invstd,
-                   float* scale, float* shift, float* running_mean, float* running_var, int C,
-                   cudaStream_t stream);
+                   float* scale, float* shift, float* running_mean, float* running_var,
+                   long long* num_batches_tracked /* +1 when non-NULL */, int C, cudaStream_t stream);
 /* eval mode: scale/shift from running statistics */
 int s4_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma,
                       const float* beta, float eps, float* scale, float* shift, int C,

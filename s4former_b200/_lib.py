@@ -61,7 +61,7 @@ _SPEC = {
     's4_conv3x3_dgrad': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     's4_conv3x3_wgrad': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     's4_pack_conv3x3_weight': (_I, [_P, _P, _P, _I, _I, _I, _P]),
-    's4_bn_finalize': (_I, [_P, _P, _D, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    's4_bn_finalize': (_I, [_P, _P, _D, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     's4_bn_eval_affine': (_I, [_P, _P, _P, _P, _F, _P, _P, _I, _P]),
     's4_bn_relu_upsample_fwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     's4_bn_relu_upsample_bwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -262,9 +262,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ mean, float* __restrict__ invstd,
                                    float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ rmean, float* __restrict__ rvar, int C) {
+                                   float* __restrict__ rmean, float* __restrict__ rvar,
+                                   long long* __restrict__ nbt, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (c == 0 && nbt) *nbt += 1;        // BatchNorm's num_batches_tracked, no extra launch
   const double mu = (double)sum[c] / count;
   double var = (double)sumsq[c] / count - mu * mu;
   if (var < 0) var = 0;
@@ -284,12 +286,14 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
 extern "C" int s4_bn_finalize(const float* sum, const float* sumsq, double count, float eps,
                               float momentum, const float* gamma, const float* beta, float* mean,
                               float* invstd, float* scale, float* shift, float* running_mean,
-                              float* running_var, int C, cudaStream_t stream) {
+                              float* running_var, long long* num_batches_tracked, int C,
+                              cudaStream_t stream) {
   S4ProfScope prof_("bn_finalize", 0.0, 1, stream);
   if (C == 0) return S4_OK;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum, sumsq, count, eps, momentum, gamma,
                                                          beta, mean, invstd, scale, shift,
-                                                         running_mean, running_var, C);
+                                                         running_mean, running_var,
+                                                         num_batches_tracked, C);
   return s4_check_launch("bn_finalize");
 }
 

@@ -7,7 +7,7 @@ on the device runs in the CUDA library.
 import torch
 import torch.distributed as dist
 
-from . import configs
+from . import configs, ops
 from .optim import FusedSGD
 from .parallel import GradReducer
 
@@ -31,6 +31,7 @@ class TrainStep:
         """Device-resident batch -> one optimisation step.  Returns ``(loss, log_vars)``; with
         ``sync=False`` the log variables stay device tensors (no host synchronisation)."""
         self.optimizer.zero_grad()
+        ops.reset_arena()
         losses = self.model(img, img_metas, return_loss=True, gt_semantic_seg=gt_semantic_seg, iter=it)
         loss, log_vars = self.model._parse_losses(losses, sync=False)
         loss.backward()
@@ -52,7 +53,7 @@ class TrainStep:
         if sl is None or sl['img'].shape != img_host.shape or sl['gt'].shape != gt_host.shape:
             sl = dict(img=torch.empty(img_host.shape, dtype=img_host.dtype, device=self.device),
                       gt=torch.empty(gt_host.shape, dtype=gt_host.dtype, device=self.device),
-                      free=None, ready=None, log_host=None)
+                      free=None, ready=None)
             slots[k] = sl
         return sl
 
@@ -74,11 +75,22 @@ class TrainStep:
 
     def prefetch(self, img_host, gt_host):
         """Start the host->device copy of a coming batch on a side stream, so that it overlaps the
-        step in flight (the dataloader's pinned batch is known one iteration ahead).  The next
-        ``step_from_host`` call on the same host tensors consumes it."""
-        k = getattr(self, '_next_slot', 0)
-        self._start_copy(k, img_host, gt_host)
-        self._prefetched = (img_host.data_ptr(), gt_host.data_ptr(), k)
+        step in flight (the dataloader's pinned batch is known one iteration ahead).  The
+        ``step_from_host`` call on the same host tensors consumes it.  With two staging slots at
+        most one batch besides the one being consumed can be in flight; a further call is a no-op
+        (that step then copies for itself)."""
+        pending = self.__dict__.setdefault('_pending', {})
+        key = (img_host.data_ptr(), gt_host.data_ptr())
+        if key in pending:
+            return
+        used = set(pending.values())
+        free = [k for k in (0, 1) if k not in used]
+        if not free:
+            return
+        # (the free slot may still be read by the step in flight: the copy waits for that step's
+        # completion event on the side stream and then overlaps the NEXT step's compute)
+        self._start_copy(free[0], img_host, gt_host)
+        pending[key] = free[0]
 
     def step_from_host(self, img_host, img_metas, gt_host, it, deferred=False):
         """End-to-end iteration: pinned host batch -> device, step, log variables back on the host
@@ -87,30 +99,33 @@ class TrainStep:
         ``deferred=True`` returns ``(loss, pending)`` where ``pending()`` yields the host log
         variables: the device->host copy is queued behind the step and read later, so the host
         can enqueue the next iteration instead of idling the GPU at every step boundary."""
-        pf = getattr(self, '_prefetched', None)
-        self._prefetched = None
-        if pf is not None and pf[0] == img_host.data_ptr() and pf[1] == gt_host.data_ptr():
-            k = pf[2]
-            sl = self._slot(k, img_host, gt_host)
-        else:
-            k = getattr(self, '_next_slot', 0)
-            sl = self._start_copy(k, img_host, gt_host)
-        self._next_slot = k ^ 1
+        pending = self.__dict__.setdefault('_pending', {})
+        k = pending.pop((img_host.data_ptr(), gt_host.data_ptr()), None)
+        if k is None:
+            used = set(pending.values())
+            free = [j for j in (0, 1) if j not in used]
+            if not free:                       # both slots hold prefetched batches: drop one
+                dropped = next(iter(pending))
+                free = [pending.pop(dropped)]
+            idle = [j for j in free if j != getattr(self, '_busy_slot', None)]
+            k = (idle or free)[0]
+            self._start_copy(k, img_host, gt_host)
+        sl = self._slot(k, img_host, gt_host)
+        self._busy_slot = k
         cur = torch.cuda.current_stream()
         cur.wait_event(sl['ready'])
         loss, log_vars = self(sl['img'], img_metas, sl['gt'], it, sync=False)
         keys = list(log_vars.keys())
-        if sl['log_host'] is None or sl['log_host'].numel() != len(keys):
-            sl['log_host'] = torch.empty(len(keys), dtype=torch.float32, pin_memory=True)
-        host = sl['log_host']
+        # (the pinned-host allocator caches its blocks: no cudaHostAlloc after the first steps)
+        host = torch.empty(len(keys), dtype=torch.float32, pin_memory=True)
         host.copy_(torch.stack([v.detach().float().reshape(()) for v in log_vars.values()]), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(cur)
-        sl['free'] = ev            # the slot (and its pinned log buffer) is reusable after this point
+        sl['free'] = ev            # the slot is reusable once this step has run
 
-        def pending():
+        def pending_logs():
             ev.synchronize()
             return type(log_vars)(zip(keys, host.tolist()))
         if deferred:
-            return loss, pending
-        return loss, pending()
+            return loss, pending_logs
+        return loss, pending_logs()

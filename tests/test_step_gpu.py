@@ -201,3 +201,50 @@ def test_missing_cuda_tensor_fails_loudly():
     img, gt, metas = gc.tiny_batch('sup')
     with pytest.raises(Exception):
         m.cpu().forward_train(img, metas, gt_semantic_seg=gt, iter=0)
+
+
+def test_train_step_runner_host_path_matches_resident():
+    """TrainStep.step_from_host (side-stream prefetch into the staging slots, deferred log
+    read-back) must produce exactly the numbers of the device-resident call, step after step,
+    and num_batches_tracked must advance once per BatchNorm invocation (fused into bn_finalize)."""
+    import copy as _copy
+    from s4former_b200.runner import TrainStep
+
+    def run(host):
+        m, _ = _build('ours')
+        step = TrainStep(m)
+        img, gt, metas = gc.tiny_batch('ours')
+        img_h, gt_h = img.pin_memory(), gt.pin_memory()
+        img_h2, gt_h2 = img.clone().pin_memory(), gt.clone().pin_memory()
+        hosts = [(img_h, gt_h), (img_h2, gt_h2)]
+        O.seed_host_rng(1999)
+        out, pend = [], []
+        for it in range(3):
+            if host:
+                if it + 1 < 3:
+                    step.prefetch(*hosts[(it + 1) & 1])
+                _, p = step.step_from_host(hosts[it & 1][0], _copy.deepcopy(metas), hosts[it & 1][1], it, deferred=True)
+                pend.append(p)
+            else:
+                _, lv = step(img.to(DEV), _copy.deepcopy(metas), gt.to(DEV), it, sync=True)
+                out.append(lv)
+        out += [p() for p in pend]
+        torch.cuda.synchronize()
+        nbt = [int(b) for n, b in m.named_buffers() if n.endswith('num_batches_tracked') and 'ema' not in n]
+        return out, {n: p.detach().float().cpu().clone() for n, p in m.named_parameters()}, nbt
+
+    a, pa, nbt_a = run(False)
+    b, pb, nbt_b = run(True)
+    assert len(a) == len(b) == 3
+    # (fp32 atomics in the split-K weight gradients / BN statistics make two runs agree to rounding,
+    # not bit for bit)
+    # the first step sees identical weights and inputs; later steps inherit the bf16 rounding noise
+    # of the previous update through a tiny, badly conditioned model
+    for i, (la, lb) in enumerate(zip(a, b)):
+        assert la.keys() == lb.keys()
+        tol = 1e-3 if i == 0 else 5e-2
+        for k in la:
+            assert abs(la[k] - lb[k]) <= tol * abs(la[k]) + 1e-5, (i, k, la[k], lb[k])
+    for k in pa:
+        assert float((pa[k] - pb[k]).norm()) <= 1e-3 * float(pa[k].norm()) + 1e-6, k
+    assert nbt_a == nbt_b and max(nbt_a) >= 3
