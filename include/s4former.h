@@ -126,6 +126,12 @@ int s4_attention_bwd(const void* dout, const void* qkv, const void* out, const f
                      void* workspace, size_t ws_bytes, int B, int H, int L, int hd, int dtype,
                      int backend, cudaStream_t stream);
 
+/* Debug / profiling hook (no reference counterpart): record a device-side event timeline of CTA
+ * `block` of the following fused attention launches into dev_buf (4 roles x N x {id, clock64}
+ * uint64, zero-filled by the caller; N is the return value).  NULL switches tracing off; the
+ * production kernel instantiations carry no trace code.  See tools/attn_trace.py. */
+int s4_attention_set_trace(void* dev_buf, int block);
+
 /* ---- backbone glue -------------------------------------------------------------------------- */
 /* img [B,Cin,H,W] f32 NCHW -> [B*gh*gw, Cin*P*P] (k = (c*P+ky)*P+kx), zero corner padding
  * (embed.py:58-80, 183-204). */

@@ -51,6 +51,7 @@ _SPEC = {
     's4_attention_workspace': (_Z, [_I, _I, _I, _I, _I, _I]),
     's4_attention_fwd': (_I, [_P, _P, _P, _F, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _P]),
     's4_attention_bwd': (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _P]),
+    's4_attention_set_trace': (_I, [_P, _I]),
     's4_patchify': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     's4_assemble_tokens': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     's4_assemble_tokens_bwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -73,6 +73,12 @@ struct FwdParams {
   int B, H, L;
   int q_tiles;        // ceil(L / 128)
   int n_full, rem, tail_n;   // key tiles: n_full x 128 + one tail of tail_n (rem valid) keys
+  // L = 128 k + 1 (a ViT's cls token + a square patch grid): the one extra key is not worth a
+  // tile of its own (a 16-key tail tile costs a full tile's chain of barriers): its logit is a
+  // 64-element dot product per query row on the CUDA cores and it is folded into (m, l, O) in the
+  // item's epilogue.  `qkv` is the plain pointer behind the tensor map.
+  int peel;
+  const void* qkv;
   TraceCfg trace;
 };
 
@@ -330,6 +336,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     wgl = 0.f;
     if (has_bias) wgl = p.w * LOG2E * ((p.gate && q_ok) ? p.gate[(size_t)b * p.L + q] : 1.f);
     float m_ref = -INFINITY, l_sum = 0.f;
+    float t_x = 0.f;          // peeled key L-1: its biased logit in the log2 domain
+    if (p.peel) {
+      // (n_full >= 2: the producer cannot overwrite the Q tile before this warp has released
+      // S_0 further down, so the rows read here are this item's)
+      tc::mbar_wait(q_full, (uint32_t)it & 1u);
+      const int xk = p.L - 1;
+      const uint4* kx = reinterpret_cast<const uint4*>(
+          reinterpret_cast<const __nv_bfloat16*>(p.qkv) + ((size_t)(b * p.L + xk) * 3 * p.H + p.H + h) * HD);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 qv;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(qv.x), "=r"(qv.y), "=r"(qv.z), "=r"(qv.w)
+                     : "r"(sQ + row * 128 + ((((uint32_t)c) ^ (uint32_t)(row & 7)) << 4)));
+        const uint4 kv = __ldg(kx + c);
+        const __nv_bfloat162* qa = reinterpret_cast<const __nv_bfloat162*>(&qv);
+        const __nv_bfloat162* ka = reinterpret_cast<const __nv_bfloat162*>(&kv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 qf = __bfloat1622float2(qa[e]), kf = __bfloat1622float2(ka[e]);
+          acc = fmaf(qf.x, kf.x, acc);
+          acc = fmaf(qf.y, kf.y, acc);
+        }
+      }
+      t_x = acc * c1;
+      if (has_bias) t_x = fmaf(wgl, p.u0[(size_t)b * p.L + xk], t_x);
+    }
     for (int j = 0; j < n_tiles; ++j) {
       const bool full = j < p.n_full;
       const int n = full ? BKV : p.tail_n;
@@ -472,6 +506,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     l_sum += xch_l[(half ^ 1) * 128 + row];
     tc::mbar_wait(o_final, (uint32_t)it & 1u);
     tc::fence_after_sync();
+    float alpha_x = 1.f, p_x = 0.f;
+    if (p.peel) {
+      const float m_new = fmaxf(m_ref, t_x);
+      alpha_x = tc::ex2(m_ref - m_new);
+      p_x = tc::ex2(t_x - m_new);
+      l_sum = fmaf(l_sum, alpha_x, p_x);
+      m_ref = m_new;
+    }
     const float inv_l = 1.f / l_sum;
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
                           ((size_t)b * p.L + (q_ok ? q : 0)) * (size_t)(p.H * HD) + h * HD + half * 32;
@@ -479,6 +521,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       uint32_t o[32];
       tc::tmem_ld32(lane_base + O_COL + half * 32, o);
       tc::tmem_ld_wait();
+      if (p.peel) {
+        // O <- O alpha + p_x V[L-1]  (this half's 32 head dims)
+        const uint4* vx = reinterpret_cast<const uint4*>(
+            reinterpret_cast<const __nv_bfloat16*>(p.qkv) +
+            ((size_t)(b * p.L + p.L - 1) * 3 * p.H + 2 * p.H + h) * HD + half * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 vv = __ldg(vx + c);
+          const __nv_bfloat162* va = reinterpret_cast<const __nv_bfloat162*>(&vv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 vf = __bfloat1622float2(va[e]);
+            o[8 * c + 2 * e] = __float_as_uint(fmaf(__uint_as_float(o[8 * c + 2 * e]), alpha_x, p_x * vf.x));
+            o[8 * c + 2 * e + 1] = __float_as_uint(fmaf(__uint_as_float(o[8 * c + 2 * e + 1]), alpha_x, p_x * vf.y));
+          }
+        }
+      }
       if (q_ok) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1054,6 +1113,9 @@ int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, flo
   p.q_tiles = (L + BQ - 1) / BQ;
   p.n_full = L / BKV;
   p.rem = L % BKV;
+  p.qkv = qkv;
+  p.peel = (p.rem == 1 && p.n_full >= 2) ? 1 : 0;
+  if (p.peel) p.rem = 0;
   p.tail_n = (p.rem + 15) & ~15;
   const int n_tiles = p.n_full + (p.tail_n ? 1 : 0);
   const size_t smem = 1024 + 5 * TILE_BYTES + 128 + 3072 + (size_t)n_tiles * BKV * 4;

@@ -19,8 +19,8 @@ dout = torch.randn(B * Lt, D, device=dev).to(torch.bfloat16)
 ops.attention_bwd(dout, qkv, out, lse, B, Lt, H, hd, None, None, 0.0)
 torch.cuda.synchronize()
 import ctypes as C
-lib.s4_attention_set_trace.restype = C.c_int
-lib.s4_attention_set_trace.argtypes = [C.c_void_p, C.c_int]
+
+
 tmax = lib.s4_attention_set_trace(None, 0)
 buf = torch.zeros(4 * tmax * 2, dtype=torch.int64, device=dev)
 lib.s4_attention_set_trace(buf.data_ptr(), block)
