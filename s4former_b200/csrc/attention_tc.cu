@@ -308,6 +308,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     const int h = bh % p.H, b = bh / p.H;
     const int q = qt * BQ + row;
     const bool q_ok = q < p.L;
+    if (p.peel && lane < 2) {
+      // pull the peeled key's K row (and this half's V slice) towards the SM now: they are
+      // consumed after the Q tile has landed / in the epilogue
+      const __nv_bfloat16* kvx = reinterpret_cast<const __nv_bfloat16*>(p.qkv) +
+                                 ((size_t)(b * p.L + p.L - 1) * 3 * p.H + (lane == 0 ? p.H : 2 * p.H) + h) * HD;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(kvx));
+    }
     has_bias = p.u0 != nullptr;
     if (has_bias) {
       // an all-zero u0 row means "no bias for this image" (the batched student pass mixes biased
@@ -337,13 +344,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
     if (has_bias) wgl = p.w * LOG2E * ((p.gate && q_ok) ? p.gate[(size_t)b * p.L + q] : 1.f);
     float m_ref = -INFINITY, l_sum = 0.f;
     float t_x = 0.f;          // peeled key L-1: its biased logit in the log2 domain
+    tr.ev(20);
     if (p.peel) {
       // (n_full >= 2: the producer cannot overwrite the Q tile before this warp has released
       // S_0 further down, so the rows read here are this item's)
-      tc::mbar_wait(q_full, (uint32_t)it & 1u);
       const int xk = p.L - 1;
       const uint4* kx = reinterpret_cast<const uint4*>(
           reinterpret_cast<const __nv_bfloat16*>(p.qkv) + ((size_t)(b * p.L + xk) * 3 * p.H + p.H + h) * HD);
+      // all eight 16-byte pieces of the key row are requested before the first is used (the row was
+      // prefetched towards L1 at the top of the item; a rolled loop exposed one L2 latency per piece)
+      uint4 kv[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) kv[c] = __ldg(kx + c);
+      tc::mbar_wait(q_full, (uint32_t)it & 1u);
+      tr.ev(21);
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -351,9 +365,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(qv.x), "=r"(qv.y), "=r"(qv.z), "=r"(qv.w)
                      : "r"(sQ + row * 128 + ((((uint32_t)c) ^ (uint32_t)(row & 7)) << 4)));
-        const uint4 kv = __ldg(kx + c);
         const __nv_bfloat162* qa = reinterpret_cast<const __nv_bfloat162*>(&qv);
-        const __nv_bfloat162* ka = reinterpret_cast<const __nv_bfloat162*>(&kv);
+        const __nv_bfloat162* ka = reinterpret_cast<const __nv_bfloat162*>(&kv[c]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 qf = __bfloat1622float2(qa[e]), kf = __bfloat1622float2(ka[e]);
@@ -363,6 +376,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       }
       t_x = acc * c1;
       if (has_bias) t_x = fmaf(wgl, p.u0[(size_t)b * p.L + xk], t_x);
+      tr.ev(22);
     }
     for (int j = 0; j < n_tiles; ++j) {
       const bool full = j < p.n_full;
@@ -501,11 +515,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       tr.ev(15);
     }
     // ---- epilogue: O / l -> bf16, lse; each half writes its 32 of the 64 head dims ----
+    uint4 vxv[4];
+    if (p.peel) {
+      // requested now, consumed after the last PV has retired
+      const uint4* vx = reinterpret_cast<const uint4*>(
+          reinterpret_cast<const __nv_bfloat16*>(p.qkv) +
+          ((size_t)(b * p.L + p.L - 1) * 3 * p.H + 2 * p.H + h) * HD + half * 32);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) vxv[c] = __ldg(vx + c);
+    }
     xch_l[half * 128 + row] = l_sum;
     tc::named_bar_sync(pair_bar, 64);
     l_sum += xch_l[(half ^ 1) * 128 + row];
+    tr.ev(16);
     tc::mbar_wait(o_final, (uint32_t)it & 1u);
     tc::fence_after_sync();
+    tr.ev(17);
     float alpha_x = 1.f, p_x = 0.f;
     if (p.peel) {
       const float m_new = fmaxf(m_ref, t_x);
@@ -521,35 +546,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
       uint32_t o[32];
       tc::tmem_ld32(lane_base + O_COL + half * 32, o);
       tc::tmem_ld_wait();
-      if (p.peel) {
-        // O <- O alpha + p_x V[L-1]  (this half's 32 head dims)
-        const uint4* vx = reinterpret_cast<const uint4*>(
-            reinterpret_cast<const __nv_bfloat16*>(p.qkv) +
-            ((size_t)(b * p.L + p.L - 1) * 3 * p.H + 2 * p.H + h) * HD + half * 32);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint4 vv = __ldg(vx + c);
-          const __nv_bfloat162* va = reinterpret_cast<const __nv_bfloat162*>(&vv);
+      for (int i = 0; i < 4; ++i) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[8 * i + e]);
+        if (p.peel) {
+          // O <- O alpha + p_x V[L-1]
+          const __nv_bfloat162* va = reinterpret_cast<const __nv_bfloat162*>(&vxv[i]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 vf = __bfloat1622float2(va[e]);
-            o[8 * c + 2 * e] = __float_as_uint(fmaf(__uint_as_float(o[8 * c + 2 * e]), alpha_x, p_x * vf.x));
-            o[8 * c + 2 * e + 1] = __float_as_uint(fmaf(__uint_as_float(o[8 * c + 2 * e + 1]), alpha_x, p_x * vf.y));
+            f[2 * e] = fmaf(f[2 * e], alpha_x, p_x * vf.x);
+            f[2 * e + 1] = fmaf(f[2 * e + 1], alpha_x, p_x * vf.y);
           }
         }
-      }
-      if (q_ok) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        if (q_ok) {
           uint4 v;
-          v.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-          v.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-          v.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-          v.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+          v.x = pack_bf16(f[0] * inv_l, f[1] * inv_l);
+          v.y = pack_bf16(f[2] * inv_l, f[3] * inv_l);
+          v.z = pack_bf16(f[4] * inv_l, f[5] * inv_l);
+          v.w = pack_bf16(f[6] * inv_l, f[7] * inv_l);
           *reinterpret_cast<uint4*>(orow + i * 8) = v;
         }
       }
     }
+    // every warp's O reads are complete before its p_full arrival for the next item's first tile,
+    // which is what lets the MMA warp overwrite O
+    tc::fence_before_sync();
+    tr.ev(18);
     if (q_ok && half == 0) p.lse[((size_t)b * p.H + h) * p.L + q] = (m_ref + log2f(l_sum)) * LN2;
     }   // work items
   }

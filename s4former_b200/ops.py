@@ -342,6 +342,11 @@ class EncoderLayerFn(torch.autograd.Function):
         att, lse = attention_fwd(qkv, B, Ltok, H, hd, u0, gate, w)
         xm = linear_fwd(att, lowp(mha.out_proj.weight), mha.out_proj.bias, res=x)
         xl2, mean2, rstd2 = layernorm_fwd(xm, layer.ln2.weight, layer.ln2.bias, eps)
+        if not ctx.needs_input_grad[0]:
+            # no-grad pass (the EMA teacher): the pre-activation copy (one extra [M, 4D] store) and
+            # the saved activations are only needed by backward
+            h = linear_fwd(xl2, lowp(fc1.weight), fc1.bias, act=L.ACT_GELU)
+            return linear_fwd(h, lowp(fc2.weight), fc2.bias, res=xm)
         h, pre = linear_fwd(xl2, lowp(fc1.weight), fc1.bias, act=L.ACT_GELU, want_pre=True)
         y = linear_fwd(h, lowp(fc2.weight), fc2.bias, res=xm)
         ctx.layer, ctx.dims, ctx.w = layer, (B, Ltok, H, hd), w
