@@ -83,6 +83,9 @@ typedef struct S4GemmParams {
   int split_k;         /* tcgen05 path: >1 splits K over CTAs and accumulates atomically
                           into a float32 C (requires accumulate=1, c_dtype=f32, no epilogue);
                           <0 lets the library pick the split count (same requirements) */
+  float* colsum;       /* optional [N]: colsum[n] += sum_m C[m,n] from the epilogue (tcgen05 path,
+                          plain store, nb1 = nb2 = 1): the bias gradient of the layer whose dY this
+                          GEMM produces.  NULL = off.  Check s4_gemm_uses_tc() first. */
 } S4GemmParams;
 
 int s4_gemm(const S4GemmParams* p, cudaStream_t stream);
@@ -158,6 +161,13 @@ int s4_transpose(const void* x, void* y, int batch, int rows, int cols, int dtyp
  * k = (ky*3+kx)*Cin + ci  (s4_pack_conv3x3_weight builds it and the dgrad form). */
 int s4_conv3x3_fwd(const void* x, const void* w_packed, void* y, int B, int H, int W, int Cin,
                    int Cout, int dtype, int backend, cudaStream_t stream);
+/* Same convolution, plus the BatchNorm batch statistics of its output in the same pass:
+ * sum[c] += sum_pix y[pix,c], sumsq[c] += sum_pix y[pix,c]^2 (float32, caller-zeroed).  On the
+ * tcgen05 path they come out of the GEMM epilogue (fp32 accumulators, before the bf16 rounding
+ * of y); otherwise the library runs s4_colsum on y itself. */
+int s4_conv3x3_fwd_stats(const void* x, const void* w_packed, void* y, float* sum, float* sumsq,
+                         int B, int H, int W, int Cin, int Cout, int dtype, int backend,
+                         cudaStream_t stream);
 /* dx = conv3x3(dy, w_dgrad) with w_dgrad: [Cin, 9*Cout], taps flipped */
 int s4_conv3x3_dgrad(const void* dy, const void* w_dgrad, void* dx, int B, int H, int W, int Cin,
                      int Cout, int dtype, int backend, cudaStream_t stream);

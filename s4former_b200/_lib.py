@@ -28,6 +28,7 @@ class GemmParams(C.Structure):
         ('c_sm', C.c_longlong), ('c_b1', C.c_longlong), ('c_b2', C.c_longlong),
         ('alpha', C.c_float), ('act', C.c_int), ('accumulate', C.c_int), ('dtype', C.c_int),
         ('c_dtype', C.c_int), ('backend', C.c_int), ('split_k', C.c_int),
+        ('colsum', C.c_void_p),
     ]
 
 
@@ -59,6 +60,7 @@ _SPEC = {
     's4_cast': (_I, [_P, _P, _L, _I, _I, _P]),
     's4_transpose': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     's4_conv3x3_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    's4_conv3x3_fwd_stats': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     's4_conv3x3_dgrad': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     's4_conv3x3_wgrad': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     's4_pack_conv3x3_weight': (_I, [_P, _P, _P, _I, _I, _I, _P]),

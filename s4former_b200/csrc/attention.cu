@@ -115,7 +115,7 @@ static int attention_fwd_t(const T* qkv, const float* u0, const float* gate, flo
   const size_t e = (size_t)B * H * L * Lp;
   float* S = (float*)ws;
   T* P = (T*)((char*)ws + e * 4);
-  S4GemmParams g;
+  S4GemmParams g{};
   // S = scale * Q K^T
   base_params(g, dtype, backend);
   g.a = qkv; g.b = qkv + D; g.c = S; g.c_dtype = S4_F32;
@@ -153,7 +153,7 @@ static int attention_bwd_t(const T* dout, const T* qkv, const float* lse, const 
   const float scale = 1.0f / sqrtf((float)hd);
   const long long qkv_b1 = (long long)L * 3 * D;
   const long long pb1 = (long long)H * L * Lp, pb2 = (long long)L * Lp;
-  S4GemmParams g;
+  S4GemmParams g{};
   int rc;
   // recompute P from the saved lse
   base_params(g, dtype, backend);

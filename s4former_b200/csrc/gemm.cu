@@ -22,6 +22,10 @@ extern "C" int s4_gemm(const S4GemmParams* p, cudaStream_t stream) {
   S4_REQUIRE(p->M >= 0 && p->N >= 0 && p->K >= 0, "gemm: negative dimension");
   S4_REQUIRE(p->nb1 >= 1 && p->nb2 >= 1, "gemm: batch counts must be >= 1");
   if (s4_gemm_uses_tc(p)) return s4_gemm_tc_launch(*p, stream);
+  if (p->colsum) {
+    s4_set_error("gemm: the fused column sum exists on the tcgen05 path only (check s4_gemm_uses_tc)");
+    return S4_ERR_UNSUPPORTED;
+  }
   if (p->backend == S4_BACKEND_TC) {
     s4_set_error("gemm: tcgen05 path does not support this problem (M=%d N=%d K=%d dtype=%d)",
                  p->M, p->N, p->K, p->dtype);

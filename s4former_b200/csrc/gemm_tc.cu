@@ -61,6 +61,11 @@ struct TcParams {
   // TMA-staged epilogue (coalesced stores through smem): tmC stores / reduce-adds C, tmX is the
   // one extra [M,N] bf16 operand: 1 = pre-activation store, 2 = residual load, 3 = GELU' input load
   int tma_epi, x_mode;
+  // fused column statistics of the OUTPUT (TMA-staged epilogue only): colsum[n] += sum_m C[m,n],
+  // colsq[n] += sum_m C[m,n]^2 (fp32 atomics).  Used for bias gradients (the dgrad GEMM that
+  // produces dY also emits colsum(dY)) and BatchNorm batch statistics (conv forward).
+  float* colsum;
+  float* colsq;
 };
 
 constexpr int EPI_WARP_BYTES = 8192;     // per epilogue warp: OUT[2] + X[2] boxes of 2 KB
@@ -104,6 +109,35 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float* v) {
   }
 }
 
+// Column sums of a 32 (lanes = rows) x 32 (registers = columns) tile held one row per lane:
+// reduce-scatter butterfly, 31 shuffles; lane l returns the sum of column l.
+__device__ __forceinline__ float warp_colsum32(const float (&s)[32], int lane) {
+  float a[16], b[8], c[4], d[2];
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float mine = u16 ? s[16 + i] : s[i], theirs = u16 ? s[i] : s[16 + i];
+    a[i] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float mine = u8 ? a[8 + i] : a[i], theirs = u8 ? a[i] : a[8 + i];
+    b[i] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float mine = u4 ? b[4 + i] : b[i], theirs = u4 ? b[i] : b[4 + i];
+    c[i] = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float mine = u2 ? c[2 + i] : c[i], theirs = u2 ? c[i] : c[2 + i];
+    d[i] = mine + __shfl_xor_sync(0xffffffffu, theirs, 2);
+  }
+  const float mine = u1 ? d[1] : d[0], theirs = u1 ? d[0] : d[1];
+  return mine + __shfl_xor_sync(0xffffffffu, theirs, 1);
+}
+
 struct TileCoord {
   int m0, n0, z1, z2, kb0, kb1;
 };
@@ -126,7 +160,11 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
   return t;
 }
 
-template <int BN, int CT>
+// STATS: the epilogue also emits column sums (/ sums of squares) of the output.  A separate
+// instantiation: the two reduce-scatter butterflies add ~250 instructions per 32-column chunk,
+// and compiled into every GEMM they slowed the plain epilogues down (register count 118 -> 151,
+// a longer chunk loop body) by more than the fusion saved.
+template <int BN, int CT, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
@@ -448,6 +486,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
         }
+        if (STATS && p.colsum) {
+          // rows past the problem / the conv tile contribute nothing (TMA clips their stores)
+          const bool lane_ok = quad * 32 + lane < p.rows_valid && row0 + lane < p.M;
+          float sv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sv[j] = lane_ok ? v[j] : 0.f;
+          const float cs = warp_colsum32(sv, lane);
+          if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, cs);
+          if (p.colsq) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sv[j] *= sv[j];
+            const float cq = warp_colsum32(sv, lane);
+            if (col0 + lane < p.N) atomicAdd(p.colsq + col0 + lane, cq);
+          }
+        }
         if (p.c_f32) {
 #pragma unroll
           for (int hb = 0; hb < 2; ++hb) {
@@ -651,13 +704,13 @@ EncodeFn get_encode_fn() {
 }
 
 // p.tiles_m already counts CTA-group tiles (pairs for CT = 2)
-template <int BN, int CT>
-int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const CUtensorMap& txm,
-              const TcParams& p, cudaStream_t stream) {
+template <int BN, int CT, bool STATS>
+int launch_bn_s(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const CUtensorMap& txm,
+                const TcParams& p, cudaStream_t stream) {
   using C = Cfg<BN, CT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) {
       s4_set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -668,7 +721,7 @@ int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   const long long total = (long long)p.tiles_m * p.tiles_n * p.nb * p.splits;
   const int groups = (int)std::min<long long>(total, s4_num_sms() / CT);
   if (CT == 1) {
-    gemm_tc_kernel<BN, CT><<<groups, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tcm, txm, p);
+    gemm_tc_kernel<BN, CT, STATS><<<groups, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tcm, txm, p);
     return s4_check_launch("gemm_tc");
   }
   cudaLaunchConfig_t cfg = {};
@@ -683,12 +736,19 @@ int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CT>, ta, tb, tcm, txm, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CT, STATS>, ta, tb, tcm, txm, p);
   if (e != cudaSuccess) {
     s4_set_error("gemm_tc: cluster launch failed: %s", cudaGetErrorString(e));
     return S4_ERR_CUDA;
   }
   return s4_check_launch("gemm_tc");
+}
+
+template <int BN, int CT>
+int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const CUtensorMap& txm,
+              const TcParams& p, cudaStream_t stream) {
+  if (p.colsum) return launch_bn_s<BN, CT, true>(ta, tb, tcm, txm, p, stream);
+  return launch_bn_s<BN, CT, false>(ta, tb, tcm, txm, p, stream);
 }
 
 int launch_any(int BN, int CT, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm,
@@ -925,6 +985,13 @@ int s4_gemm_tc_launch(const S4GemmParams& g, cudaStream_t stream) {
     p.x_mode = g.pre ? 1 : (g.res ? 2 : (g.aux ? 3 : 0));
     p.accumulate = need_add ? 1 : 0;
   }
+  if (g.colsum) {
+    if (!p.tma_epi || need_add || nb != 1) {
+      s4_set_error("gemm_tc: the fused column sum needs the TMA-staged, non-accumulating, unbatched epilogue");
+      return S4_ERR_ARG;
+    }
+    p.colsum = g.colsum;
+  }
   S4ProfScope prof("gemm_tc", 2.0 * g.M * g.N * (double)g.K * nb, 0, stream);
   return launch_any(BN, CT, ta, tb, tcm, txm, p, stream);
 }
@@ -954,8 +1021,23 @@ bool s4_conv3x3_tc_supported(int B, int H, int W, int Cin, int Cout, int dtype) 
   return conv_tile_shape(H, W, TW, TH);
 }
 
+int s4_conv3x3_tc_stats(const void* x, const void* w_packed, void* y, float* sum, float* sumsq, int B,
+                        int H, int W, int Cin, int Cout, cudaStream_t stream);
+
 int s4_conv3x3_tc(const void* x, const void* w_packed, void* y, int B, int H, int W, int Cin,
                   int Cout, cudaStream_t stream) {
+  return s4_conv3x3_tc_stats(x, w_packed, y, nullptr, nullptr, B, H, W, Cin, Cout, stream);
+}
+
+// true when the conv forward can emit the BatchNorm statistics from its epilogue
+bool s4_conv3x3_tc_stats_supported(int B, int H, int W, int Cin, int Cout, int dtype) {
+  int TW, TH;
+  return s4_conv3x3_tc_supported(B, H, W, Cin, Cout, dtype) && conv_tile_shape(H, W, TW, TH) &&
+         (TW * TH) % 32 == 0 && !env_no_tma_epilogue();
+}
+
+int s4_conv3x3_tc_stats(const void* x, const void* w_packed, void* y, float* sum, float* sumsq, int B,
+                        int H, int W, int Cin, int Cout, cudaStream_t stream) {
   int TW, TH;
   if (!conv_tile_shape(H, W, TW, TH)) {
     s4_set_error("conv3x3_tc: unsupported spatial shape %dx%d", H, W);
@@ -1001,6 +1083,14 @@ int s4_conv3x3_tc(const void* x, const void* w_packed, void* y, int B, int H, in
   if (p.rows_valid % 32 == 0 && !env_no_tma_epilogue()) {
     if ((rc = make_epilogue_maps(&tcm, &txm, y, nullptr, false, p.M, Cout, 1, 1, Cout, 0, 0))) return rc;
     p.tma_epi = 1;
+  }
+  if (sum) {
+    if (!p.tma_epi) {
+      s4_set_error("conv3x3_tc: fused BN statistics need the TMA-staged epilogue");
+      return S4_ERR_ARG;
+    }
+    p.colsum = sum;
+    p.colsq = sumsq;
   }
   S4ProfScope prof("conv3x3_tc", 2.0 * B * H * W * (double)Cout * 9.0 * Cin, 0, stream);
   return launch_any(BN, 1, ta, tb, tcm, txm, p, stream);

@@ -170,6 +170,9 @@ conv3x3_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, flo
 int s4_conv3x3_tc(const void* x, const void* w_packed, void* y, int B, int H, int W, int Cin,
                   int Cout, cudaStream_t stream);
 bool s4_conv3x3_tc_supported(int B, int H, int W, int Cin, int Cout, int dtype);
+int s4_conv3x3_tc_stats(const void* x, const void* w_packed, void* y, float* sum, float* sumsq, int B,
+                        int H, int W, int Cin, int Cout, cudaStream_t stream);
+bool s4_conv3x3_tc_stats_supported(int B, int H, int W, int Cin, int Cout, int dtype);
 int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin,
                         int Cout, cudaStream_t stream);
 bool s4_conv3x3_wgrad_tc_supported(int B, int H, int W, int Cin, int Cout, int dtype);
@@ -195,6 +198,22 @@ extern "C" int s4_conv3x3_fwd(const void* x, const void* w_packed, void* y, int 
                               int Cin, int Cout, int dtype, int backend, cudaStream_t stream) {
   S4ProfScope prof_("conv3x3_fwd", 0.0, 1, stream);
   return conv3x3_any(x, w_packed, y, B, H, W, Cin, Cout, dtype, backend, stream);
+}
+
+extern "C" int s4_colsum(const void* x, float* sum, float* sumsq, long long rows, int cols, int dtype,
+                         cudaStream_t stream);
+
+extern "C" int s4_conv3x3_fwd_stats(const void* x, const void* w_packed, void* y, float* sum,
+                                    float* sumsq, int B, int H, int W, int Cin, int Cout, int dtype,
+                                    int backend, cudaStream_t stream) {
+  if ((long long)B * H * W == 0) return S4_OK;
+  if (backend != S4_BACKEND_SIMT && s4_conv3x3_tc_stats_supported(B, H, W, Cin, Cout, dtype)) {
+    S4ProfScope prof_("conv3x3_fwd", 0.0, 1, stream);
+    return s4_conv3x3_tc_stats(x, w_packed, y, sum, sumsq, B, H, W, Cin, Cout, stream);
+  }
+  int rc = s4_conv3x3_fwd(x, w_packed, y, B, H, W, Cin, Cout, dtype, backend, stream);
+  if (rc) return rc;
+  return s4_colsum(y, sum, sumsq, (long long)B * H * W, Cout, dtype, stream);
 }
 
 extern "C" int s4_conv3x3_dgrad(const void* dy, const void* w_dgrad, void* dx, int B, int H, int W,

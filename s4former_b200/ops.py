@@ -202,8 +202,11 @@ def grad_buffer(p):
 # ----------------------------------------------------------------------------------------------
 def gemm(a, b, c, M, N, K, a_str, b_str, c_sm, batch=(1, 1), a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0),
          bias=None, aux=None, res=None, pre=None, alpha=1.0, act=L.ACT_NONE, accumulate=False,
-         split_k=1, dtype=None, backend_override=None):
-    """C = epi(alpha * A @ B) with element strides a_str=(sm, sk), b_str=(sk, sn)."""
+         split_k=1, dtype=None, backend_override=None, colsum=None):
+    """C = epi(alpha * A @ B) with element strides a_str=(sm, sk), b_str=(sk, sn).
+
+    ``colsum`` (float32 [N]): the epilogue also accumulates the column sums of C into it when the
+    problem runs on the tcgen05 path; returns True if it did (False: the caller sums C itself)."""
     g = L.GemmParams()
     g.a, g.b, g.c = _p(a), _p(b), _p(c)
     g.bias, g.aux, g.res, g.pre = _p(bias), _p(aux), _p(res), _p(pre)
@@ -220,7 +223,14 @@ def gemm(a, b, c, M, N, K, a_str, b_str, c_sm, batch=(1, 1), a_bs=(0, 0), b_bs=(
     g.c_dtype = _code(c.dtype)
     g.backend = backend() if backend_override is None else backend_override
     g.split_k = split_k
+    fused = False
+    if colsum is not None:
+        g.colsum = None
+        if L.load().s4_gemm_uses_tc(C.byref(g)):
+            g.colsum = _p(colsum)
+            fused = True
     L.check(L.load().s4_gemm(C.byref(g), _st()), 's4_gemm')
+    return fused
 
 
 def _wgrad_split(M_out, N_out, K_red):
@@ -241,13 +251,19 @@ def linear_fwd(x, w_lp, bias, act=L.ACT_NONE, res=None, want_pre=False):
     return (y, pre) if want_pre else y
 
 
-def linear_dgrad(dy, w_lp, aux=None):
+def linear_dgrad(dy, w_lp, aux=None, colsum_param=None):
     """dx = (dy @ w) * gelu'(aux) ; dy [M,N], w_lp [N,K] as stored: the weight is the MN-major B
-    operand of the GEMM, so no transposed copy is ever made."""
+    operand of the GEMM, so no transposed copy is ever made.
+
+    ``colsum_param``: a bias parameter whose gradient is colsum(dx) (dx is the dY of the linear
+    layer below): accumulated from the GEMM epilogue when possible, by ``s4_colsum`` otherwise."""
     M, N = dy.shape
     K = w_lp.shape[1]
     dx = torch.empty((M, K), dtype=dy.dtype, device=dy.device)
-    gemm(dy, w_lp, dx, M, K, N, (N, 1), (K, 1), K, aux=aux)
+    gb = grad_buffer(colsum_param) if colsum_param is not None else None
+    fused = gemm(dy, w_lp, dx, M, K, N, (N, 1), (K, 1), K, aux=aux, colsum=gb)
+    if gb is not None and not fused:
+        L.call('s4_colsum', _p(dx), _p(gb), None, M, K, _code(dx.dtype), _st())
     return dx
 
 
@@ -363,10 +379,11 @@ class EncoderLayerFn(torch.autograd.Function):
         fc1, fc2 = layer.ffn.layers[0][0], layer.ffn.layers[1]
         dy = dy.contiguous()
         # FFN
-        dpre = linear_dgrad(dy, lowp(fc2.weight), aux=pre)           # (dy W2) * gelu'(pre)
+        # (dy W2) * gelu'(pre); the same epilogue accumulates fc1.bias.grad = colsum(dpre)
+        dpre = linear_dgrad(dy, lowp(fc2.weight), aux=pre, colsum_param=fc1.bias)
         linear_wgrad(dy, h, fc2.weight, fc2.bias)
         dxl2 = linear_dgrad(dpre, lowp(fc1.weight))
-        linear_wgrad(dpre, xl2, fc1.weight, fc1.bias)
+        linear_wgrad(dpre, xl2, fc1.weight, None)
         dxm = layernorm_bwd(dxl2, xm, layer.ln2.weight, layer.ln2.bias, mean2, rstd2, dres=dy)
         # attention block
         datt = linear_dgrad(dxm, lowp(mha.out_proj.weight))
@@ -468,7 +485,22 @@ class HeadLNFn(torch.autograd.Function):
         return dx, None, None, None, None
 
 
-def _bn_scale_shift(conv_bn, y2d, rows, training, group_info):
+def _conv_fwd(stage, x, B, H, W, Cin, Cout, training):
+    """conv3x3 forward; in training mode the BatchNorm batch statistics [sum, sumsq] of its output
+    come out of the same launch (GEMM epilogue).  Returns (y, stats or None)."""
+    wf, _ = conv_packed(stage.conv.weight)
+    dt = _code(x.dtype)
+    y = torch.empty((B * H * W, Cout), dtype=x.dtype, device=x.device)
+    if not training:
+        L.call('s4_conv3x3_fwd', _p(x), _p(wf), _p(y), B, H, W, Cin, Cout, dt, backend(), _st())
+        return y, None
+    stats = arena_zeros((2, Cout), x.device)
+    L.call('s4_conv3x3_fwd_stats', _p(x), _p(wf), _p(y), _p(stats[0]), _p(stats[1]), B, H, W, Cin, Cout,
+           dt, backend(), _st())
+    return y, stats
+
+
+def _bn_scale_shift(conv_bn, y2d, rows, training, group_info, stats=None):
     """BatchNorm statistics of the conv output (training: batch stats, all-reduced for SyncBN;
     eval: running stats).  Returns (scale, shift, mean, invstd, count)."""
     bn = conv_bn.bn
@@ -480,8 +512,9 @@ def _bn_scale_shift(conv_bn, y2d, rows, training, group_info):
         L.call('s4_bn_eval_affine', _p(bn.running_mean), _p(bn.running_var), _p(bn.weight.detach()),
                _p(bn.bias.detach()), bn.eps, _p(scale), _p(shift), Cc, _st())
         return scale, shift, None, None, 0.0
-    stats = arena_zeros((2, Cc), dev)
-    L.call('s4_colsum', _p(y2d), _p(stats[0]), _p(stats[1]), rows, Cc, _code(y2d.dtype), _st())
+    if stats is None:
+        stats = arena_zeros((2, Cc), dev)
+        L.call('s4_colsum', _p(y2d), _p(stats[0]), _p(stats[1]), rows, Cc, _code(y2d.dtype), _st())
     count = float(rows)
     if group_info is not None and group_info.get('world', 1) > 1:
         _all_reduce_stats(stats, group_info)
@@ -502,11 +535,9 @@ class ConvBNReLUUpFn(torch.autograd.Function):
     def forward(ctx, x, stage, B, H, W, s, training, group_info):
         conv = stage.conv
         Cout, Cin = conv.weight.shape[0], conv.weight.shape[1]
-        wf, _ = conv_packed(conv.weight)
         dt = _code(x.dtype)
-        y = torch.empty((B * H * W, Cout), dtype=x.dtype, device=x.device)
-        L.call('s4_conv3x3_fwd', _p(x), _p(wf), _p(y), B, H, W, Cin, Cout, dt, backend(), _st())
-        scale, shift, mean, invstd, count = _bn_scale_shift(stage, y, B * H * W, training, group_info)
+        y, stats = _conv_fwd(stage, x, B, H, W, Cin, Cout, training)
+        scale, shift, mean, invstd, count = _bn_scale_shift(stage, y, B * H * W, training, group_info, stats)
         out = torch.empty((B * H * s * W * s, Cout), dtype=x.dtype, device=x.device)
         L.call('s4_bn_relu_upsample_fwd', _p(y), _p(scale), _p(shift), _p(out), B, H, W, Cout, s, dt, _st())
         ctx.stage, ctx.dims, ctx.group_info, ctx.count = stage, (B, H, W, s, Cin, Cout), group_info, count
@@ -570,12 +601,10 @@ class ConvBNReLUClsUpFn(torch.autograd.Function):
         conv = stage.conv
         Cout, Cin = conv.weight.shape[0], conv.weight.shape[1]
         NC = conv_seg.weight.shape[0]
-        wf, _ = conv_packed(conv.weight)
         dt = _code(x.dtype)
         rows = B * H * W
-        y = torch.empty((rows, Cout), dtype=x.dtype, device=x.device)
-        L.call('s4_conv3x3_fwd', _p(x), _p(wf), _p(y), B, H, W, Cin, Cout, dt, backend(), _st())
-        scale, shift, mean, invstd, count = _bn_scale_shift(stage, y, rows, training, group_info)
+        y, stats = _conv_fwd(stage, x, B, H, W, Cin, Cout, training)
+        scale, shift, mean, invstd, count = _bn_scale_shift(stage, y, rows, training, group_info, stats)
         z = torch.empty((rows, NC), dtype=torch.float32, device=x.device)
         w2 = conv_seg.weight.detach().reshape(NC, Cout)
         L.call('s4_bn_relu_conv1x1_fwd', _p(y), _p(scale), _p(shift), _p(w2), _p(conv_seg.bias.detach()),

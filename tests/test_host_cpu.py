@@ -46,7 +46,7 @@ def test_abi_argument_counts_match_header(built_lib):
 
 def test_gemm_params_struct_layout(built_lib):
     # 7 pointers, 5 ints (+pad), 11 long longs, float + 6 ints
-    assert ctypes.sizeof(built_lib.GemmParams) == 7 * 8 + 5 * 4 + 4 + 11 * 8 + 7 * 4 + 4
+    assert ctypes.sizeof(built_lib.GemmParams) == 7 * 8 + 5 * 4 + 4 + 11 * 8 + 7 * 4 + 4 + 8   # + colsum pointer
 
 
 def test_library_is_sm100a_only():

@@ -159,6 +159,41 @@ def test_tc_conv3x3_fwd_dgrad(B, H, W, Cin, Cout):
         assert rel(dx.float().permute(0, 3, 1, 2), xr.grad) < 2e-2
 
 
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 32, 32, 128, 64), (1, 64, 64, 64, 256), (1, 128, 128, 64, 128),
+                                            (2, 16, 16, 64, 64), (3, 24, 24, 64, 256)])
+def test_tc_conv3x3_fwd_fused_bn_stats(B, H, W, Cin, Cout):
+    """conv forward + BatchNorm batch statistics from the GEMM epilogue == conv, then column sums
+    (ragged pixel tiles: 24x24 has 120-pixel tiles, i.e. rows of the 128-row MMA tile that are not
+    real must not be counted)."""
+    x, dy, wf, wd, xr, wr, yr, st = _conv_case(B, H, W, Cin, Cout)
+    y = torch.empty(B, H, W, Cout, device=DEV, dtype=BF)
+    stats = torch.zeros(2, Cout, device=DEV)
+    L.call('s4_conv3x3_fwd_stats', x.data_ptr(), wf.data_ptr(), y.data_ptr(), stats[0].data_ptr(),
+           stats[1].data_ptr(), B, H, W, Cin, Cout, L.BF16, L.BACKEND_AUTO, st)
+    assert rel(y.float().permute(0, 3, 1, 2), yr) < 2e-2
+    y2 = y.float().reshape(-1, Cout)
+    assert torch.allclose(stats[0], y2.sum(0), rtol=2e-3, atol=2e-2 * float(y2.abs().sum(0).max()) / 100)
+    assert rel(stats[1], (y2 * y2).sum(0)) < 5e-3
+
+
+def test_tc_gemm_fused_colsum():
+    """dX = dY W (* gelu'(aux)) with the column sums of dX from the same epilogue (bias gradient of
+    the layer below); M is not a multiple of the tile so padded rows must not be counted."""
+    g = gen(21)
+    for (M, N, K, use_aux) in ((1000, 256, 512, True), (260, 136, 192, False), (4100, 3072, 768, True)):
+        dy = torch.randn(M, N, generator=g).to(DEV, BF)
+        w = (torch.randn(N, K, generator=g) * 0.1).to(DEV, BF)
+        aux = torch.randn(M, K, generator=g).to(DEV, BF) if use_aux else None
+        p = torch.nn.Parameter(torch.zeros(K, device=DEV))
+        p.grad = torch.full((K,), 0.5, device=DEV)
+        dx = ops.linear_dgrad(dy, w, aux=aux, colsum_param=p)
+        ref = ops.linear_dgrad(dy, w, aux=aux)
+        assert torch.equal(dx, ref)
+        want = 0.5 + ref.float().sum(0)
+        scale = float(ref.float().abs().sum(0).max())
+        assert float((p.grad - want).abs().max()) < 4e-3 * scale, float((p.grad - want).abs().max()) / scale
+
+
 @pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 32, 32, 128, 64), (1, 64, 64, 64, 256), (2, 128, 128, 256, 256)])
 def test_tc_conv3x3_wgrad(B, H, W, Cin, Cout, pair_mode):
     x, dy, wf, wd, xr, wr, yr, st = _conv_case(B, H, W, Cin, Cout)
