@@ -371,15 +371,24 @@ def main():
     value = world / sec
     roofline = dict(bound='tensor', achieved=None, peak=tc_peak, unit='TFLOP/s', frac=None, traffic=None,
                     peak_source=peak_src)
-    tcs = [k for k in kinds if k['unit'] == 'flop' and k['work_per_step'] > 0 and k['ms_per_step'] > 0]
+    # the dominant kernel is gemm_tc_kernel: the linear-layer GEMMs and the implicit-GEMM 3x3
+    # convolutions (forward / dgrad / wgrad) are launches of the same tcgen05 kernel
+    fam = ('gemm_tc', 'conv3x3_tc', 'conv3x3_wgrad_tc')
+    tcs = [k for k in kinds if k['name'] in fam and k['work_per_step'] > 0 and k['ms_per_step'] > 0]
     if tcs:
-        dom = max(tcs, key=lambda k: k['ms_per_step'])
-        ach = dom['work_per_step'] / (dom['ms_per_step'] * 1e-3) / 1e12
-        roofline.update(kernel=dom['name'], achieved=ach, frac=ach / tc_peak,
-                        launches_per_step=dom['launches_per_step'],
-                        avg_launch_ms=dom['ms_per_step'] / dom['launches_per_step'],
-                        flop_per_launch=dom['work_per_step'] / dom['launches_per_step'],
-                        share_of_step=dom['ms_per_step'] / (sec * 1e3))
+        work = sum(k['work_per_step'] for k in tcs)
+        kms = sum(k['ms_per_step'] for k in tcs)
+        nl = sum(k['launches_per_step'] for k in tcs)
+        ach = work / (kms * 1e-3) / 1e12
+        roofline.update(kernel='gemm_tc_kernel (linear GEMMs + implicit-GEMM 3x3 conv fwd/dgrad/wgrad)',
+                        achieved=ach, frac=ach / tc_peak, launches_per_step=nl, avg_launch_ms=kms / nl,
+                        flop_per_launch=work / nl, share_of_step=kms / (sec * 1e3))
+        try:      # DRAM bytes per launch of the same launches, from the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')))
+            roofline.update(traffic=tr['dram_bytes_per_launch'], traffic_unit='bytes/launch',
+                            traffic_source=tr['source'])
+        except Exception:
+            pass
     out = dict(metric='train_steps_per_s', value=value, unit='steps/s', n_gpus=world, steps=a.steps,
                warmup=max(a.warmup, 3), ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak',
                vs_baseline=None, dtype=a.dtype, data='synthetic',

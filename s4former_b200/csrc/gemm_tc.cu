@@ -483,8 +483,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (p.act == S4_ACT_GELU) {
+          if (p.c_f32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_bf16(v[j]);
+          }
         }
         if (STATS && p.colsum) {
           // rows past the problem / the conv tile contribute nothing (TMA clips their stores)
