@@ -6,18 +6,13 @@
 //     bias[b,h,q,k] = w * gate[b,q] * u0[b,k]           (rank 1; same for all heads / layers)
 // which is added to the scaled logits inside the softmax warps: no L x L tensor ever exists.
 //
-// FORWARD.  One CTA per (batch, head, 128-query tile); two CTAs are co-resident per SM so one
-// CTA's softmax overlaps the other's MMAs.  256 threads:
-//   warp 0      TMA producer: Q tile once, then K and V tiles (128 keys x 64) through two
-//               2-stage rings (cp.async.bulk.tensor.4d, 128B swizzle, zero fill past L)
-//   warp 1      MMA issuer + TMEM owner: S = Q K^T (128 x n x 64, SS) into TMEM cols [0,128);
-//               O += P V (128 x 64 x n, P read from TMEM, V from smem) into cols [128,192)
-//   warps 4-7   softmax: one query row per thread; tcgen05.ld S -> registers, online softmax in
-//               the log2 domain with LAZY rescaling (O is only rescaled when the running max
-//               grows by more than 2^8), P packed to bf16 and stored over S with tcgen05.st
-// Register budget is moved from warps 0-3 to the softmax warps with setmaxnreg.
-// The key loop runs full 128-key tiles plus one tail tile of round_up(L % 128, 16) keys, so
-// L = 1025 (512^2 crops) costs 8 tiles + a 16-key MMA, not 9 tiles.
+// FORWARD (attn_fwd_kernel): persistent, two co-resident CTAs per SM walk (batch, head, 128-query
+// tile) work items; TMA K/V rings, S = Q K^T and O += P V on tcgen05 with S, O and P in separate
+// TMEM columns, two softmax threads per query row, online softmax with lazy rescaling, the bias
+// added in registers.  BACKWARD (attn_bwd_kernel): one CTA per (batch, head, 128-key tile) walking
+// the query tiles, all five GEMMs on tcgen05, dQ reduced across key tiles with bulk fp32 adds.
+// Details at each kernel.  Both were tuned with the device-side event trace below
+// (s4_attention_set_trace / tools/attn_trace.py).
 #include <algorithm>
 #include <math.h>
 #include <stdlib.h>
@@ -87,11 +82,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// FORWARD.  One CTA per (batch, head, 128-query tile); two CTAs are co-resident per SM so one
-// CTA's softmax overlaps the other's MMAs.  384 threads:
+// FORWARD.  PERSISTENT: 2 x #SM CTAs (two co-resident per SM, so one CTA's softmax overlaps the
+// other's MMAs) walk the (batch, head, 128-query tile) work items.  384 threads:
 //   warp 0      TMA producer: Q tile once, then K and V tiles (128 keys x 64) through two
 //               2-stage rings (cp.async.bulk.tensor.4d, 128B swizzle, zero fill past L)
-//   warp 1      MMA issuer + TMEM owner: S = Q K^T (128 x n x 64, SS) into TMEM cols [0,128);
+//   warp 1      MMA issuer + TMEM owner (whole warp in uniform control flow, elected lane issues):
+//               S = Q K^T (128 x n x 64, SS) into TMEM cols [0,128);
 //               O += P V (128 x 64 x n, P read from TMEM cols [192,256), V from smem) into [128,192)
 //   warps 4-11  softmax, TWO threads per query row: warps 4-7 own key columns [0,64) of the tile,
 //               warps 8-11 columns [64,128) (a warp reaches the TMEM lanes 32*(warp%4)..+31, so warps
@@ -101,10 +97,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 //               their row maxima through shared memory (one 64-thread named barrier per tile), so
 //               both use the same reference maximum; online softmax in the log2 domain with LAZY
 //               rescaling (O is only rescaled when the running max grows by more than 2^8).
-// P lives in its own TMEM columns, so S(j+1) = Q K_{j+1}^T is issued right behind O += P_j V_j.
+// P lives in its own TMEM columns, so S(j+1) = Q K_{j+1}^T is issued as soon as the softmax warps
+// hold S_j in registers (s_free) and runs under tile j's exponentials; O += P_j V_j follows P_j
+// (p_full) and releases the P columns / O through pv_done.
 // Register budget is moved from warps 0-3 to the softmax warps with setmaxnreg.
-// The key loop runs full 128-key tiles plus one tail tile of round_up(L % 128, 16) keys, so
-// L = 1025 (512^2 crops) costs 8 tiles + a 16-key MMA, not 9 tiles.
+// Keys: full 128-key tiles, then either one compact tail tile of round_up(L % 128, 16) keys or -
+// for L = 128 k + 1 (cls token + square patch grid: 1025, 2305) - NO tail tile: the one extra key
+// is a 64-element dot product per row on the CUDA cores, folded into (m, l, O) in the epilogue.
 template <bool TR>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
@@ -599,8 +598,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
 //   dQ_i  = dS K_j     (A = dS^T staged in smem, MN-major)      TMEM cols [384,448)
 // dQ tiles are reduced over the key tiles with cp.reduce.async.bulk (fp32 add in L2) into a
 // [B,H,q_tiles,128,64] accumulator that a small kernel converts to bf16.
-// Warps: 0 TMA producer, 1 MMA issuer (one thread), 4-7 / 8-11 softmax for query half 0 / 1
-// (software-pipelined against each other by the issue order), 12-15 dQ epilogue.
+// Warps: 0 TMA producer, 1 MMA issuer (uniform control flow, elected lane), 4-7 / 8-11 softmax for
+// query half 0 / 1 (software-pipelined against each other by the issue order; TMEM loads of
+// chunk c+1 in flight under chunk c), 12-15 dQ epilogue.  K_j / V_j are staged once into TMEM as
+// the A operands of S^T / dP^T; the dS^T staging tile for dQ is double-buffered.
 // =============================================================================================
 constexpr int BWD_THREADS = 512;
 constexpr int DP_COL = 128, DV_COL = 256, DK_COL = 320, DQ_COL = 384;

@@ -103,6 +103,72 @@ ln_fwd_kernel(const T* __restrict__ x, const int* __restrict__ row_map,
   }
 }
 
+// Variant for many rows (the encoder's [B*L, D] launches): gamma / beta are NOT held in registers
+// (2 x VPL x VN = 48 of the ~100 registers of the kernel above) but re-read through L1 for every
+// row, so 3x more warps are resident and hide the ~1 us row round trip through L2.
+template <typename T, int VPL>
+__global__ void __launch_bounds__(128, 10)
+ln_fwd_lean_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
+                   float* __restrict__ rstd_out, int rows, int D, float eps) {
+  constexpr int VN = Vec16<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int nvec = D / VN;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float inv_d = 1.f / (float)D;
+  for (int row = warp0; row < rows; row += nwarps) {
+    const T* xr = x + (size_t)row * D;
+    Vec16<T> v[VPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) v[k].load(xr + vi * VN);
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
+#pragma unroll
+        for (int e = 0; e < VN; ++e) sum += v[k].get(e);
+      }
+    }
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          const float d = v[k].get(e) - mean;
+          sq = fmaf(d, d, sq);
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    T* yr = y + (size_t)row * D;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
+        float gm[VN], bt[VN];
+        load_cols<VN>(gamma, vi, gm);
+        load_cols<VN>(beta, vi, bt);
+        Vec16<T> o;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) o.set(e, fmaf((v[k].get(e) - mean) * rstd, gm[e], bt[e]));
+        o.store(yr + vi * VN);
+      }
+    }
+  }
+}
+
 // dx (written at the mapped source row of a pre-zeroed buffer when row_map != null).
 // dgamma/dbeta: every warp keeps register partials over its rows, the block folds them through
 // shared memory (plain stores, one slab per warp) and issues ONE global atomic per column.
@@ -238,6 +304,14 @@ extern "C" int s4_layernorm_fwd(const void* x, const int* row_map, const float* 
   const int fcap = s4_num_sms() * 5;
   if (blocks > fcap) blocks = fcap;
   const int vpl = (D / vn + 31) / 32;
+  if (dtype == S4_BF16 && row_map == nullptr && rows >= 4096) {
+    int lb = (rows + 3) / 4;
+    const int lcap = s4_num_sms() * 10;
+    if (lb > lcap) lb = lcap;
+    LN_DISPATCH_VPL(vpl, (ln_fwd_lean_kernel<__nv_bfloat16, VPL><<<lb, FT, 0, stream>>>(
+        (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, D, eps)));
+    return s4_check_launch("layernorm_fwd");
+  }
   if (dtype == S4_BF16) {
     LN_DISPATCH_VPL(vpl, (ln_fwd_kernel<__nv_bfloat16, VPL><<<blocks, FT, 0, stream>>>(
         (const __nv_bfloat16*)x, row_map, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, D, eps)));

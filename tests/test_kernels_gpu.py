@@ -85,6 +85,22 @@ def test_layernorm_fwd_bwd(dtype, tol, D):
     assert rel(bp.grad, br.grad) < max(tol, 1e-4)
 
 
+def test_layernorm_fwd_many_rows_lean_kernel():
+    """>= 4096 bf16 rows without a row map take the high-occupancy kernel (gamma/beta via L1)."""
+    g = gen(3)
+    rows, D = 5001, 768
+    x = torch.randn(rows, D, generator=g)
+    gamma = torch.randn(D, generator=g) * 0.1 + 1
+    beta = torch.randn(D, generator=g) * 0.1
+    gp, bp = torch.nn.Parameter(gamma.to(DEV)), torch.nn.Parameter(beta.to(DEV))
+    y, mean, rstd = ops.layernorm_fwd(x.to(DEV, torch.bfloat16), gp, bp, 1e-6)
+    xr = x.to(torch.bfloat16).float()
+    want = F.layer_norm(xr, (D,), gamma, beta, 1e-6)
+    assert rel(y.float().cpu(), want) < 1e-2
+    assert torch.allclose(mean.cpu(), xr.mean(1), atol=1e-4)
+    assert torch.allclose(rstd.cpu(), (xr.var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-3)
+
+
 def test_layernorm_row_map():
     g = gen(2)
     x = torch.randn(50, 128, generator=g).to(DEV)
