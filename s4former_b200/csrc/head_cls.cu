@@ -455,13 +455,28 @@ cls_upsample_fwd_kernel(const float* __restrict__ z, float* __restrict__ out, in
   }
   __syncthreads();
   float* ob = out + (size_t)b * NC * OH * OW + (size_t)oy * OW;
+  const bool vec4 = (OW & 3) == 0 && (n & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   for (int j = threadIdx.x / 32; j < NC; j += blockDim.x / 32) {     // one warp per class row
     float* orow = ob + (size_t)j * OH * OW;
-    for (int ox = threadIdx.x & 31; ox < OW; ox += 32) {
-      const int pk = xi[ox];
-      const float lx = xl[ox];
-      const float v0 = zs[(pk & 0xffff) * NC + j], v1 = zs[(pk >> 16) * NC + j];
-      orow[ox] = (1.f - lx) * v0 + lx * v1;
+    if (vec4) {
+      // four consecutive outputs per lane: one 16-byte store instead of four 4-byte ones
+      for (int ox = (threadIdx.x & 31) * 4; ox < OW; ox += 128) {
+        const int4 pk = *reinterpret_cast<const int4*>(xi + ox);
+        const float4 lx = *reinterpret_cast<const float4*>(xl + ox);
+        float4 o;
+        o.x = (1.f - lx.x) * zs[(pk.x & 0xffff) * NC + j] + lx.x * zs[(pk.x >> 16) * NC + j];
+        o.y = (1.f - lx.y) * zs[(pk.y & 0xffff) * NC + j] + lx.y * zs[(pk.y >> 16) * NC + j];
+        o.z = (1.f - lx.z) * zs[(pk.z & 0xffff) * NC + j] + lx.z * zs[(pk.z >> 16) * NC + j];
+        o.w = (1.f - lx.w) * zs[(pk.w & 0xffff) * NC + j] + lx.w * zs[(pk.w >> 16) * NC + j];
+        *reinterpret_cast<float4*>(orow + ox) = o;
+      }
+    } else {
+      for (int ox = threadIdx.x & 31; ox < OW; ox += 32) {
+        const int pk = xi[ox];
+        const float lx = xl[ox];
+        const float v0 = zs[(pk & 0xffff) * NC + j], v1 = zs[(pk >> 16) * NC + j];
+        orow[ox] = (1.f - lx) * v0 + lx * v1;
+      }
     }
   }
 }
