@@ -49,6 +49,10 @@ struct TcParams {
   int rows_valid;                  // rows of the 128-row tile that are real (conv fwd)
   int row_pitch;                   // global rows advanced per m-tile (BM, or rows_valid for conv)
   int a_nobatch;                   // A tensor map has no batch dims (coordinates forced to 0)
+  // conv wgrad with W not expressible in 64-pixel k-blocks (48, 96, ... : 768^2 crops): a k-block
+  // carries k_rows < 64 pixels (TMA boxes of k_rows rows); rows [k_rows, 64) of every operand
+  // sub-tile are zeroed ONCE at kernel start and never written again, so the K = 64 MMAs see zeros.
+  int k_rows;                      // 0 / 64 = full k-blocks
   // epilogue
   void* c;
   const float* bias;
@@ -218,6 +222,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (PAIR) tc::tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
     else tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
   }
+  if (p.k_rows > 0 && p.k_rows < BK) {
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw + (base - raw));
+    const int n16 = C::STAGES * C::STAGE_BYTES / 16;
+    for (int i = threadIdx.x; i < n16; i += NUM_THREADS) ring[i] = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_proxy_async();        // generic-proxy zeros ordered before the TMA / MMA accesses
+  }
   tc::fence_before_sync();
   if (PAIR) tc::cluster_sync();     // peer barriers initialised before any remote arrive / TMA signal
   else __syncthreads();
@@ -234,10 +244,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool leader = tc::elect_one();
       int stage = 0;
       uint32_t phase = 0;
+      const int krows = (p.k_rows > 0 && p.k_rows < BK) ? p.k_rows : BK;   // pixels per k-block (wgrad)
       const uint32_t a_bytes = (p.a_mode == OP_CONV_K) ? (uint32_t)(p.cTW * p.cTH * BK * 2)
-                                                        : (uint32_t)A_STAGE_BYTES;
+                                                        : (uint32_t)(A_STAGE_BYTES / BK * krows);
       // pair mode: the leader's barrier counts the bytes landing in BOTH CTAs
-      const uint32_t tx_bytes = (a_bytes + (uint32_t)C::B_STAGE_BYTES) * CT;
+      const uint32_t tx_bytes = (a_bytes + (uint32_t)(C::B_STAGE_BYTES / BK * krows)) * CT;
       auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
         if (leader) {
           if (PAIR) tc::tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
@@ -277,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // conv wgrad: k-block = 64 consecutive pixels (a row segment or whole rows) of image wb
         int wb = 0, wy = 0, wx = 0, wdx = 0, wdy = 0;
         if (p.b_mode == OP_CONV_MN) {
-          const int pix = t.kb0 * BK;
+          const int pix = t.kb0 * krows;
           const int hw = p.cH * p.cW;
           wb = pix / hw;
           const int r = pix % hw;
@@ -287,8 +298,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           wdy = t.z2 / 3 - 1;
         }
         const int az2 = p.a_nobatch ? 0 : t.z2, az1 = p.a_nobatch ? 0 : t.z1;
-        int k0 = t.kb0 * BK;
-        for (int kb = t.kb0; kb < t.kb1; ++kb, k0 += BK) {
+        int k0 = t.kb0 * krows;
+        for (int kb = t.kb0; kb < t.kb1; ++kb, k0 += krows) {
           tc::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
@@ -1102,19 +1113,40 @@ int s4_conv3x3_tc_stats(const void* x, const void* w_packed, void* y, float* sum
 }
 
 // dw[co][ci][tap] += sum_pix dy[pix][co] * x[pix+tap][ci]   (split over pixels, fp32 atomics)
+// pixel window of one wgrad k-block: TW x TH pixels, TW * TH <= 64.  64-pixel windows when W allows
+// (W % 64 == 0, or whole rows with 64 % W == 0); otherwise the widest row segment <= 64 that
+// divides W and is a multiple of 8 (W = 48, 96: 48 pixels; the k-block is zero-padded to 64).
+static bool conv_wgrad_kblock(int H, int W, int* TW, int* TH) {
+  int tw = 0, th = 1;
+  if (W >= 64 && W % 64 == 0) tw = 64;
+  else if (W < 64 && 64 % W == 0 && H % (64 / W) == 0 && W % 8 == 0) { tw = W; th = 64 / W; }
+  else {
+    for (int t = 64; t >= 16; t -= 8)
+      if (W % t == 0) { tw = t; break; }
+  }
+  if (tw == 0) return false;
+  if (TW) *TW = tw;
+  if (TH) *TH = th;
+  return true;
+}
+
 bool s4_conv3x3_wgrad_tc_supported(int B, int H, int W, int Cin, int Cout, int dtype) {
   if (dtype != S4_BF16 || env_tc_disable_mn()) return false;
   if (Cin % 8 || Cout % 8) return false;
-  // a k-block is 64 consecutive pixels inside one image: a row segment, or whole rows
-  if (W >= 64) return W % 64 == 0;
-  return 64 % W == 0 && H % (64 / W) == 0 && W % 8 == 0;
+  // a k-block is up to 64 consecutive pixels inside one image: a row segment, or whole rows
+  return conv_wgrad_kblock(H, W, nullptr, nullptr);
 }
 
 int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin,
                         int Cout, cudaStream_t stream) {
   const long long P = (long long)B * H * W;
-  const int TWk = W >= 64 ? 64 : W, THk = 64 / TWk;
-  const int kblocks = (int)(P / 64);
+  int TWk = 64, THk = 1;
+  if (!conv_wgrad_kblock(H, W, &TWk, &THk)) {
+    s4_set_error("conv3x3_wgrad_tc: unsupported spatial shape %dx%d", H, W);
+    return S4_ERR_UNSUPPORTED;
+  }
+  const int krows = TWk * THk;                     // pixels per k-block (64, or 48 / 40 / ... padded)
+  const int kblocks = (int)(P / krows);
   const int BN = Cin >= 256 ? 256 : (Cin >= 128 ? 128 : 64);
   // CTA pairs: both 128-row halves of dy^T share the x window, each CTA stages half of it
   const int CT = (env_pair_mode() != 0 && BN >= 128 && Cout % 256 == 0) ? 2 : 1;
@@ -1124,7 +1156,7 @@ int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, 
     // A = dy^T, MN-major: inner = Cout, outer = pixels
     const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)P, 1, 1};
     const uint64_t str[3] = {(uint64_t)Cout, (uint64_t)Cout * 8, (uint64_t)Cout * 8};
-    const uint32_t box[4] = {64, (uint32_t)BK, 1, 1};
+    const uint32_t box[4] = {64, (uint32_t)krows, 1, 1};
     if ((rc = s4_make_tmap_bf16(&ta, dy, dims, str, box))) return rc;
   }
   {
@@ -1153,6 +1185,7 @@ int s4_conv3x3_wgrad_tc(const void* x, const void* dy, float* dw, int B, int H, 
   p.a_mode = OP_MNMAJOR; p.b_mode = OP_CONV_MN;
   p.cH = H; p.cW = W; p.cTW = TWk; p.cTH = THk; p.cblocks = 1;
   p.rows_valid = BM; p.row_pitch = BM; p.a_nobatch = 1;
+  p.k_rows = krows;
   p.c = dw;
   p.c_sm = (long long)Cin * 9; p.c_sn = 9; p.c_b1 = 0; p.c_b2 = 1;   // z2 = tap
   p.alpha = 1.f; p.c_f32 = 1; p.atomic = 1; p.accumulate = 1;

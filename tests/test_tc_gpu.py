@@ -194,7 +194,8 @@ def test_tc_gemm_fused_colsum():
         assert float((p.grad - want).abs().max()) < 4e-3 * scale, float((p.grad - want).abs().max()) / scale
 
 
-@pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 32, 32, 128, 64), (1, 64, 64, 64, 256), (2, 128, 128, 256, 256)])
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 32, 32, 128, 64), (1, 64, 64, 64, 256), (2, 128, 128, 256, 256),
+                                            (2, 48, 48, 128, 256), (1, 96, 96, 64, 64), (1, 40, 40, 64, 128)])
 def test_tc_conv3x3_wgrad(B, H, W, Cin, Cout, pair_mode):
     x, dy, wf, wd, xr, wr, yr, st = _conv_case(B, H, W, Cin, Cout)
     dw = torch.zeros(Cout, Cin, 3, 3, device=DEV)
