@@ -428,22 +428,29 @@ class EncoderDecoder(BaseSegmentor):
             ops.bump_generation(t)
         ops.mark_shadows_fresh(table.targets)
 
+    def _set_mode(self, ema, training):
+        """`.train(mode)` of the student (or EMA) sub-models.  The module list is cached and the
+        flag written straight into each module's ``__dict__``: ``nn.Module.train`` re-walks ~400
+        modules through ``nn.Module.__setattr__`` and was ~2 ms of host time per step for the two
+        teacher toggles (reference encoder_decoder.py:524,539)."""
+        cache = self.__dict__.setdefault('_s4_mode_lists', {})
+        mods = cache.get(bool(ema))
+        if mods is None:
+            roots = [self.backbone_ema, self.decode_head_ema] if ema else \
+                [self.backbone, self.decode_head] + ([self.auxiliary_head] if self.with_auxiliary_head else [])
+            mods = [m for r in roots for m in r.modules()]
+            # VisionTransformer.train keeps its LayerNorms in eval mode under norm_eval (vit.py:416-445)
+            frozen = [m for r in roots if getattr(r, 'norm_eval', False)
+                      for m in r.modules() if isinstance(m, torch.nn.LayerNorm)]
+            mods = (mods, frozen)
+            cache[bool(ema)] = mods
+        for m in mods[0]:
+            m.__dict__['training'] = training
+        for m in mods[1]:
+            m.__dict__['training'] = False
+
     def set_eval(self, ema=False):
-        if not ema:
-            self.backbone.eval()
-            self.decode_head.eval()
-            if self.with_auxiliary_head:
-                self.auxiliary_head.eval()
-        else:
-            self.backbone_ema.eval()
-            self.decode_head_ema.eval()
+        self._set_mode(ema, False)
 
     def set_train(self, ema=False):
-        if not ema:
-            self.backbone.train()
-            self.decode_head.train()
-            if self.with_auxiliary_head:
-                self.auxiliary_head.train()
-        else:
-            self.backbone_ema.train()
-            self.decode_head_ema.train()
+        self._set_mode(ema, True)
