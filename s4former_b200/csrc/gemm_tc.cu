@@ -404,6 +404,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // written into a 64B-swizzled 32x32 box in smem -> one lane issues the TMA store (or
     // reduce-add).  Residual / GELU' inputs arrive the same way in the other direction,
     // prefetched one chunk ahead.  TMA clips rows >= M and columns >= N.
+    // the elected lane (always the same one: the warp is converged at every use) issues the TMA /
+    // bulk-group instructions; coordinates are warp-uniform, so no per-instruction elect loop
+    const bool el = tc::elect_one();
     const int ew = warp - 4;
     const int quad = warp & 3;
     const int half = ew >> 2;
@@ -425,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
       const int row0 = (t.m0 / BM) * p.row_pitch + quad * 32;
       const bool rows_ok = quad * 32 < p.rows_valid && row0 < p.M;
-      if (xload && rows_ok && lane == 0 && t.n0 + c_begin * 32 < p.N && c_begin < c_end) {
+      if (xload && rows_ok && el && t.n0 + c_begin * 32 < p.N && c_begin < c_end) {
         tc::mbar_expect_tx(xbar(ew, xi & 1), 2048);
         tc::tma_load_4d(x_buf(xi & 1), &tmX, xbar(ew, xi & 1), t.n0 + c_begin * 32, row0, t.z2, t.z1);
       }
@@ -445,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (xload) {
           // prefetch the next chunk's operand into the other buffer (its readers are done: syncwarp)
           __syncwarp();
-          if (lane == 0 && chunk + 1 < c_end && col0 + 32 < p.N) {
+          if (el && chunk + 1 < c_end && col0 + 32 < p.N) {
             tc::mbar_expect_tx(xbar(ew, (xi + 1) & 1), 2048);
             tc::tma_load_4d(x_buf((xi + 1) & 1), &tmX, xbar(ew, (xi + 1) & 1), col0 + 32, row0, t.z2, t.z1);
           }
@@ -474,7 +477,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ++xi;
         }
         // staging buffers of the chunk before last must have been read by their stores
-        if (lane == 0) {
+        if (el) {
           if (p.c_f32) tc::bulk_wait_read<0>();
           else tc::bulk_wait_read<1>();
         }
@@ -544,7 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (el) {
           if (p.c_f32) {
             if (p.accumulate) {
               tc::tma_reduce_add_4d(&tmC, out_buf(0), col0, row0, t.z2, t.z1);
@@ -563,13 +566,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) {
+      if (el) {
         if (PAIR) tc::mbar_arrive_leader(tempty_bar(acc));
         else tc::mbar_arrive(tempty_bar(acc));
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (lane == 0) tc::bulk_wait<0>();
+    if (el) tc::bulk_wait<0>();
   } else if (warp >= 4) {
     // ================================ epilogue (direct stores) ==============================
     const int ew = warp - 4;
