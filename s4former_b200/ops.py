@@ -663,6 +663,17 @@ class ConvBNReLUClsUpFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 # losses / pseudo labels / augmentation / EMA
 # ----------------------------------------------------------------------------------------------
+_zero_scalars = {}
+
+
+def _zero_scalar(device):
+    z = _zero_scalars.get(device)
+    if z is None:
+        z = torch.zeros((), dtype=torch.float32, device=device)
+        _zero_scalars[device] = z
+    return z
+
+
 class CeNcrFn(torch.autograd.Function):
     """(loss_ce, loss_ncr) = (w_ce/P * sum_valid nll, w_ncr/P * sum_valid ||p_s - p_t + eps||).
 
@@ -679,6 +690,7 @@ class CeNcrFn(torch.autograd.Function):
         label = label.reshape(B, H, W).contiguous()
         if logits_t is not None:
             logits_t = logits_t.contiguous()
+        ctx.set_materialize_grads(False)     # unused outputs: no zero-filled gradient tensors
         out = torch.empty(3, dtype=torch.float32, device=logits_s.device)
         nbytes = L.load().s4_ce_ncr_workspace(B, H, W)
         ws = workspace(nbytes, logits_s.device, 'loss')
@@ -700,8 +712,10 @@ class CeNcrFn(torch.autograd.Function):
         if dz is None:
             raise RuntimeError('CeNcrFn.backward called twice (the saved gradient buffer is consumed)')
         ctx.dz = None
-        gs = torch.stack([g_ce if g_ce is not None else torch.zeros((), device=dev),
-                          g_ncr if g_ncr is not None else torch.zeros((), device=dev)]).float().contiguous()
+        zero = _zero_scalar(dev)
+        gs = torch.stack([g_ce if g_ce is not None else zero, g_ncr if g_ncr is not None else zero])
+        if gs.dtype != torch.float32:
+            gs = gs.float()
         L.call('s4_ce_ncr_grad_fixup', _p(logits_s), _p(logits_t), _p(label), _p(dz), _p(gs), B, Cc, H, W,
                ce_w, ncr_w, ignore_index, _st())
         return dz, None, None, None, None, None

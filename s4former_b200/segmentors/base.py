@@ -15,6 +15,9 @@ import torch.distributed as dist
 import torch.nn as nn
 
 
+_pending_key_checks = []      # deferred cross-rank key-count checks of _parse_losses(sync=False)
+
+
 class BaseSegmentor(nn.Module, metaclass=ABCMeta):
     def __init__(self, init_cfg=None):
         super().__init__()
@@ -65,11 +68,13 @@ class BaseSegmentor(nn.Module, metaclass=ABCMeta):
     @staticmethod
     def _parse_losses(losses, sync=True):
         log_vars = OrderedDict()
+        def _mean(t):                      # the path's losses are already scalars: no launch for them
+            return t if t.dim() == 0 else t.mean()
         for loss_name, loss_value in losses.items():
             if isinstance(loss_value, torch.Tensor):
-                log_vars[loss_name] = loss_value.mean()
+                log_vars[loss_name] = _mean(loss_value)
             elif isinstance(loss_value, list):
-                log_vars[loss_name] = sum(_loss.mean() for _loss in loss_value)
+                log_vars[loss_name] = sum(_mean(_loss) for _loss in loss_value)
             else:
                 raise TypeError(f'{loss_name} is not a tensor or list of tensors')
         loss = sum(_value for _key, _value in log_vars.items() if 'loss' in _key)
@@ -81,8 +86,16 @@ class BaseSegmentor(nn.Module, metaclass=ABCMeta):
             packed = torch.cat([packed, n])
             dist.all_reduce(packed)
             ws = dist.get_world_size()
-            assert int(round(float(packed[-1]))) == len(names) * ws, \
-                'loss log variables are different across GPUs!\n' + ','.join(names)
+            # the reference's cross-rank key-count assertion (base.py:263).  Reading the count is a
+            # device->host sync: with sync=False it is checked one call LATE (the value is long
+            # since final by then), so the host keeps enqueueing instead of stalling mid-step
+            check = (packed[-1], len(names) * ws, ','.join(names))
+            todo = [check] if sync else _pending_key_checks[:]
+            if not sync:
+                _pending_key_checks[:] = [check]
+            for cnt, want, nm in todo:
+                assert int(round(float(cnt))) == want, \
+                    'loss log variables are different across GPUs!\n' + nm
             packed = packed[:-1] / ws
         if sync:
             vals = packed.tolist()        # ONE device->host copy
