@@ -36,10 +36,15 @@ def backend():
     return _cfg['backend']
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def _st():
     # raw handle of the current stream (torch.cuda.current_stream() builds a Stream object and
     # re-resolves the device on every call: a quarter of the step's host time at ~3000 calls)
-    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
 def _p(t):

@@ -212,6 +212,91 @@ def test_parse_losses_two_ranks_gloo():
     assert abs(v0['mask_ratio'] - 0.375) < 1e-6
 
 
+def _parse_deferred_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from s4former_b200.segmentors import base
+    ok = {'decode.loss_ce': torch.tensor(1.0 + rank), 'mask_ratio': torch.tensor(0.5)}
+    out = []
+    # sync=False: values stay tensors, the cross-rank key-count assertion runs one call late
+    _, lv = base.BaseSegmentor._parse_losses(dict(ok), sync=False)
+    out.append(float(lv['decode.loss_ce']))
+    assert len(base._pending_key_checks) == 1
+    # a mismatch recorded by one call (here: forged, a real one would hang gloo's all_reduce) is
+    # raised by the NEXT call
+    cnt, want, names = base._pending_key_checks[0]
+    base._pending_key_checks[0] = (cnt, want + 1, names)
+    err = None
+    try:
+        base.BaseSegmentor._parse_losses(dict(ok), sync=False)
+    except AssertionError:
+        err = 'late'
+    # and the queue keeps exactly one (fresh, good) entry afterwards
+    base._pending_key_checks[:] = []
+    base.BaseSegmentor._parse_losses(dict(ok), sync=False)
+    base.BaseSegmentor._parse_losses(dict(ok), sync=False)
+    assert len(base._pending_key_checks) == 1
+    q.put((rank, out, err))
+    try:
+        dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+def test_parse_losses_deferred_key_check_two_ranks_gloo():
+    """sync=False must not read the all-reduced key count in the same call (that is a mid-step
+    host sync at N > 1) but must still catch a cross-rank mismatch, one call late."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_parse_deferred_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        if p.is_alive():
+            p.terminate()
+    for rank, out, err in res:
+        assert abs(out[0] - 1.5) < 1e-6
+        assert err == 'late', (rank, err)
+
+
+def test_step_arena_and_bn_grad_add():
+    """Host helpers behind the per-step scratch: arena_zeros hands out disjoint zeroed slices, a
+    reset re-zeroes what was used; _add_bn_grads takes the one-launch path when weight.grad and
+    bias.grad are adjacent in the flat gradient buffer and the two-add path otherwise."""
+    from s4former_b200 import ops
+    from s4former_b200.optim import FlatGrads
+    dev = torch.device('cpu')
+    ops._arena.pop(dev, None)
+    a = ops.arena_zeros((2, 8), dev)
+    b = ops.arena_zeros((3,), dev)
+    assert float(a.abs().sum()) == 0 and float(b.abs().sum()) == 0
+    a.fill_(1.0)
+    b.fill_(2.0)
+    assert a.data_ptr() != b.data_ptr() and float(a.sum()) == 16.0 and float(b.sum()) == 6.0
+    ops.reset_arena()
+    c = ops.arena_zeros((2, 8), dev)
+    assert c.data_ptr() == a.data_ptr() and float(c.abs().sum()) == 0
+    big = ops.arena_zeros((ops._ARENA_CHUNK + 5,), dev)       # larger than a chunk: own allocation
+    assert big.numel() == ops._ARENA_CHUNK + 5 and float(big.abs().sum()) == 0
+    ops._arena.pop(dev, None)
+
+    bn = torch.nn.BatchNorm2d(4)
+    FlatGrads(list(bn.parameters()))                          # weight.grad, bias.grad adjacent views
+    sums = torch.arange(8, dtype=torch.float32).view(2, 4)    # [dgamma; dbeta]
+    ops._add_bn_grads(bn, sums)
+    ops._add_bn_grads(bn, sums)
+    assert torch.equal(bn.weight.grad, 2 * sums[0]) and torch.equal(bn.bias.grad, 2 * sums[1])
+    bn2 = torch.nn.BatchNorm2d(4)                             # separate gradient tensors: fallback
+    ops._add_bn_grads(bn2, sums)
+    assert torch.equal(bn2.weight.grad, sums[0]) and torch.equal(bn2.bias.grad, sums[1])
+
+
 def test_parse_losses_single_process():
     from s4former_b200.segmentors.base import BaseSegmentor
     loss, lv = BaseSegmentor._parse_losses({'a.loss_ce': torch.tensor([1., 3.]), 'x': torch.tensor(5.)})
