@@ -297,6 +297,38 @@ def test_step_arena_and_bn_grad_add():
     assert torch.equal(bn2.weight.grad, sums[0]) and torch.equal(bn2.bias.grad, sums[1])
 
 
+def test_init_weights_statistics():
+    """Random-init path used by the parity tests and the bench (reference
+    vit.py:369-414, setr_up_head.py:34-40, mmcv ConvModule default): trunc-normal(0.02) Linear /
+    pos / cls, FFN biases ~ N(0, 1e-6), LayerNorm 1/0, conv_seg ~ N(0, 0.01), kaiming convs."""
+    import s4former_b200 as s4
+    from s4former_b200 import configs
+    torch.manual_seed(3)
+    m = s4.build_segmentor(configs.setr_pup_deit_base('ours', 512, 21, norm='BN'))
+    m.init_weights()
+    bb, head = m.backbone, m.decode_head
+    lyr = bb.layers[3]
+    # in_proj_weight is a bare Parameter of nn.MultiheadAttention (not an nn.Linear): the reference's
+    # init loop never touches it, it keeps torch's xavier_uniform (bound sqrt(6 / (768 + 2304)))
+    w = lyr.attn.attn.in_proj_weight
+    bound = (6.0 / (768 + 2304)) ** 0.5
+    assert float(w.abs().max()) <= bound + 1e-6 and abs(float(w.std()) - bound / 3 ** 0.5) < 1e-3
+    wo = lyr.attn.attn.out_proj.weight                                               # an nn.Linear: trunc-normal
+    assert abs(float(wo.std()) - 0.02) < 2e-3 and float(wo.abs().max()) <= 2.0   # cut at +-2 ABSOLUTE, as mmcv
+    assert abs(float(bb.pos_embed.std()) - 0.02) < 2e-3
+    fc1 = lyr.ffn.layers[0][0]
+    assert abs(float(fc1.weight.std()) - 0.02) < 2e-3
+    assert 0 < float(fc1.bias.abs().max()) < 1e-5                                      # N(0, 1e-6)
+    assert float(lyr.attn.attn.out_proj.bias.abs().max()) == 0.0
+    assert torch.equal(lyr.ln1.weight, torch.ones_like(lyr.ln1.weight)) and float(lyr.ln1.bias.abs().max()) == 0
+    pe = bb.patch_embed.projection.weight                                             # kaiming, fan_in = 3*16*16
+    assert abs(float(pe.std()) - (2.0 / (3 * 16 * 16)) ** 0.5) < 5e-3
+    assert abs(float(head.conv_seg.weight.std()) - 0.01) < 2e-3 and float(head.conv_seg.bias.abs().max()) == 0
+    c0 = head.up_convs[0][0].conv.weight                                              # kaiming, fan_out = 256*9
+    assert abs(float(c0.std()) - (2.0 / (256 * 9)) ** 0.5) < 2e-3
+    assert torch.equal(head.up_convs[0][0].bn.weight, torch.ones(256))
+
+
 def test_parse_losses_single_process():
     from s4former_b200.segmentors.base import BaseSegmentor
     loss, lv = BaseSegmentor._parse_losses({'a.loss_ce': torch.tensor([1., 3.]), 'x': torch.tensor(5.)})
