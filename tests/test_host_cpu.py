@@ -56,6 +56,30 @@ def test_library_is_sm100a_only():
     assert archs == {'100a'}, archs
 
 
+def test_sass_has_tcgen05_tma_and_no_serialised_mma_issue():
+    """The hot kernels really are tcgen05 / TMEM / TMA code (SASS: UTCHMMA = tcgen05.mma, UTCBAR =
+    tcgen05.commit, LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG / UTMAREDG = TMA load / store /
+    reduce), the GEMM uses CTA pairs (.2CTA), and no tcgen05.mma sits inside one of ptxas'
+    per-instruction elect loops (BRA.U.ANY right after it: what a `lane == 0` issue branch produces
+    and what cost ~100 clk per MMA before the issue warps were made warp-uniform)."""
+    import shutil
+    lib = os.path.join(ROOT, 's4former_b200', 'libs4former_b200.so')
+    if shutil.which('cuobjdump') is None or not os.path.exists(lib):
+        pytest.skip('cuobjdump or the built library is not available')
+    sass = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
+    for mnem in ('UTCHMMA', 'UTCHMMA.2CTA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAREDG',
+                 'UBLKRED'):
+        assert mnem in sass, mnem
+    lines = [ln for ln in sass.splitlines() if '/*' in ln and ';' in ln]
+    bad = 0
+    for i, ln in enumerate(lines):
+        if 'UTCHMMA' in ln:
+            nxt = ' '.join(lines[i + 1:i + 3])
+            if 'BRA.U.ANY' in nxt:
+                bad += 1
+    assert bad == 0, f'{bad} tcgen05.mma instructions are wrapped in serialising elect loops'
+
+
 def test_product_package_never_imports_oracle():
     for dp, _dn, fns in os.walk(os.path.join(ROOT, 's4former_b200')):
         for fn in fns:
