@@ -326,6 +326,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FwdParams p) {
         u0s[i] = v;
         nz |= (v != 0.f) ? 1u : 0u;
       }
+      // the peeled key L-1 is not part of the staged row but counts for "has a bias"
+      if (p.peel && t256 == 0) nz |= (ub[p.L - 1] != 0.f) ? 1u : 0u;
       uint32_t any;
       asm volatile(
           "{\n"
