@@ -38,6 +38,12 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-prof', action='store_true')
     ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='reference arm wall budget')
+    ap.add_argument('--cpu-threads', type=int, default=0, help='reference arm threads (0 = all host cores)')
+    ap.add_argument('--no-gpu-eager', action='store_true',
+                    help='skip the PyTorch-eager-on-this-GPU leg (the oracle math on cuBLAS/cuDNN kernels)')
+    ap.add_argument('--no-extra-configs', action='store_true',
+                    help='skip the short runs of BASELINE configs 1/2/4 (sup-only, MT, 768x768/19)')
+    ap.add_argument('--no-parity', action='store_true', help='skip the in-bench parity block')
     return ap.parse_args()
 
 
@@ -110,6 +116,11 @@ def cpu_reference_steps(a, n_sup, n_unsup, max_steps, warmup, budget_s):
     BOUNDED sample (n_sup labeled + n_unsup unlabeled crops).  Returns (seconds/step, steps, threads)."""
     import copy
     import torch
+    # The launcher's environment must not decide the baseline's speed: torch.distributed.run
+    # exports OMP_NUM_THREADS=1, which would time the reference on ONE core.  Always use all the
+    # host cores (or --cpu-threads) and report the count.
+    threads = a.cpu_threads or (os.cpu_count() or 1)
+    torch.set_num_threads(threads)
     from oracle import s4former_oracle as O            # checker / CPU baseline only
     from s4former_b200 import configs
     from s4former_b200.utils.synthetic import make_batch, fresh_metas
@@ -142,25 +153,33 @@ def cpu_reference_steps(a, n_sup, n_unsup, max_steps, warmup, budget_s):
         if times and (time.perf_counter() - t_start) + dt > budget_s:
             break
     times.sort()
-    return times[len(times) // 2], len(times), torch.get_num_threads()
+    return times[len(times) // 2], len(times), threads
 
 
 def reference_arm(a):
+    """``--impl reference``: the reference's own algorithm (the oracle port, pinned to the reference
+    by tests/golden) on the host cores.  One "step" of this arm is a BOUNDED SAMPLE of the workload
+    (2 labeled + 2 unlabeled crops = 1/4 of the 8L+8U batch): ``steps`` / ``ms_per_step`` describe the
+    sample steps actually timed; ``value`` is the metric (full 8L+8U steps/s) = sample_fraction /
+    seconds-per-sample-step, with the extrapolation spelled out in ``config``."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    s_sup, s_unsup = 1, (1 if a.variant != 'sup' else 0)
+    s_sup = min(2, a.sup)
+    s_unsup = min(2, a.unsup) if a.variant != 'sup' else 0
     sec, n, threads = cpu_reference_steps(a, s_sup, s_unsup, max(1, a.steps), min(a.warmup, 1), a.cpu_budget_s)
-    frac = s_sup / a.sup                      # the sample is 1/8 of the per-GPU batch
+    frac = s_sup / a.sup
     value = frac / sec                        # full (8L+8U) steps per second
     unit = 'steps/s'
-    sample = (f'{s_sup} labeled + {s_unsup} unlabeled {a.size}x{a.size} crops per step (1/{a.sup} of the '
-              f'{a.sup}L+{a.unsup}U batch; value scaled by 1/{a.sup}), fp32, PyTorch CPU kernels, oracle port of the '
-              f'reference path; median of {n} timed step(s)')
+    sample = (f'{s_sup} labeled + {s_unsup} unlabeled {a.size}x{a.size} crops per sample step '
+              f'({frac:.3g} of the {a.sup}L+{a.unsup}U batch), fp32, PyTorch CPU kernels on {threads} threads, '
+              f'oracle port of the reference path; median of {n} timed sample step(s)')
     out = dict(impl='reference', metric='train_steps_per_s', value=value, unit=unit, n_gpus=a.gpus,
-               steps=n, warmup=min(a.warmup, 1), ms_per_step=sec * 1e3 / frac, higher_is_better=True,
+               gpus_used=0, steps=n, warmup=min(a.warmup, 1), ms_per_step=sec * 1e3, higher_is_better=True,
                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-               config=dict(workload=workload_name(a), sample=sample),
+               config=dict(workload=workload_name(a), sample=sample, sample_fraction=frac,
+                           ms_per_full_step_extrapolated=sec * 1e3 / frac,
+                           note='GPU-over-CPU context, not a kernel-quality claim; ms_per_step is one SAMPLE step'),
                cpu_baseline=dict(value=value, unit=unit, cores=threads, kind='port', sample=sample),
                e2e=dict(value=value, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)

@@ -64,10 +64,10 @@ def tiny_cfg(variant='ours'):
     return model
 
 
-def seeded_state_dict(template, seed=5):
+def seeded_state_dict(template, seed=5, ema_cls_std=6.0):
     """Deterministic weights for every key of ``template`` (shapes/dtypes kept).
-    conv_seg of the EMA head is scaled up so that a useful fraction of pixels clears
-    the 0.95 confidence threshold."""
+    conv_seg of the EMA head is scaled up (``ema_cls_std``) so that a useful fraction of pixels
+    clears the 0.95 confidence threshold."""
     g = torch.Generator().manual_seed(seed)
     out = {}
     for k in sorted(template.keys()):
@@ -84,7 +84,7 @@ def seeded_state_dict(template, seed=5):
         elif k.endswith('bias'):
             t = 0.02 * torch.randn(v.shape, generator=g)
         elif 'conv_seg.weight' in k:
-            t = torch.randn(v.shape, generator=g) * (6.0 if 'ema' in k else 0.1)
+            t = torch.randn(v.shape, generator=g) * (ema_cls_std if 'ema' in k else 0.1)
         elif v.dim() >= 2:
             fan_in = v[0].numel()
             t = torch.randn(v.shape, generator=g) * (1.0 / fan_in ** 0.5)
@@ -102,3 +102,60 @@ def tiny_batch(variant='ours', seed=1999):
     from oracle.s4former_oracle import synthetic_batch
     n_unsup = 0 if variant == 'sup' else 2
     return synthetic_batch(2, n_unsup, TINY['img'], TINY['classes'], seed=seed, grid=16)
+
+
+# ----------------------------------------------------------------------------------------
+# full-size fixtures (BASELINE shapes): oracle/make_golden_full.py, tests/test_full_parity_gpu.py
+# ----------------------------------------------------------------------------------------
+FULL = dict(
+    full512=dict(size=512, classes=21, n_sup=2, n_unsup=2, wseed=5, ema_cls_std=2.0, seed=1999),
+    full768=dict(size=768, classes=19, n_sup=1, n_unsup=1, wseed=6, ema_cls_std=2.0, seed=2024),
+)
+
+
+def full_cfg(shape='full512', variant='ours', norm='SyncBN'):
+    """The shipped ``_MT_w_ours`` model dict at a BASELINE shape (DeiT-B, SETR-PUP)."""
+    from s4former_b200 import configs
+    f = FULL[shape]
+    return configs.setr_pup_deit_base(variant, f['size'], f['classes'], norm=norm)
+
+
+def full_batch(shape='full512'):
+    from oracle.s4former_oracle import synthetic_batch
+    f = FULL[shape]
+    return synthetic_batch(f['n_sup'], f['n_unsup'], f['size'], f['classes'], seed=f['seed'], grid=32)
+
+
+def strided_sample(t, n):
+    """<= n elements of ``t`` at evenly spaced flat positions (the whole tensor if it is smaller)."""
+    flat = t.detach().reshape(-1)
+    if flat.numel() <= n:
+        return flat.clone().cpu()
+    idx = (torch.arange(n, dtype=torch.int64) * flat.numel()) // n
+    return flat[idx.to(flat.device)].clone().cpu()
+
+
+def full_grad_keys(names):
+    """Parameters whose gradient samples are stored: the tiny-fixture keys mapped to DeiT-B depth
+    plus one tensor of every kind in every part of the model."""
+    want = [
+        'backbone.cls_token', 'backbone.pos_embed', 'backbone.patch_embed.projection.weight',
+        'backbone.patch_embed.projection.bias',
+        'backbone.layers.0.ln1.weight', 'backbone.layers.0.ln1.bias',
+        'backbone.layers.0.attn.attn.in_proj_weight', 'backbone.layers.0.attn.attn.in_proj_bias',
+        'backbone.layers.0.attn.attn.out_proj.weight', 'backbone.layers.0.ffn.layers.0.0.weight',
+        'backbone.layers.5.attn.attn.in_proj_weight', 'backbone.layers.5.attn.attn.out_proj.bias',
+        'backbone.layers.5.ffn.layers.0.0.bias', 'backbone.layers.5.ffn.layers.1.weight',
+        'backbone.layers.5.ln2.weight',
+        'backbone.layers.11.attn.attn.in_proj_bias', 'backbone.layers.11.attn.attn.out_proj.weight',
+        'backbone.layers.11.ffn.layers.0.0.weight', 'backbone.layers.11.ffn.layers.1.bias',
+        'decode_head.norm.weight', 'decode_head.norm.bias',
+        'decode_head.up_convs.0.0.conv.weight', 'decode_head.up_convs.0.0.bn.weight',
+        'decode_head.up_convs.1.0.conv.weight', 'decode_head.up_convs.2.0.bn.bias',
+        'decode_head.up_convs.3.0.conv.weight', 'decode_head.up_convs.3.0.bn.weight',
+        'decode_head.conv_seg.weight', 'decode_head.conv_seg.bias',
+        'auxiliary_head.0.norm.weight', 'auxiliary_head.0.up_convs.1.0.conv.weight',
+        'auxiliary_head.1.up_convs.0.0.conv.weight', 'auxiliary_head.2.conv_seg.bias',
+        'auxiliary_head.3.up_convs.1.0.bn.weight', 'auxiliary_head.3.conv_seg.weight',
+    ]
+    return [k for k in want if k in names]

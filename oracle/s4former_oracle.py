@@ -199,7 +199,7 @@ def pasa_gate_u0(u, adaptive=True, topk_idx=None):
     if adaptive:
         if topk_idx is None:
             topk_idx = torch.topk(flat, int(0.5 * flat.shape[-1]), dim=-1, largest=False)[1]
-        gate[torch.arange(b).unsqueeze(1), topk_idx + 1] = 0
+        gate[torch.arange(b, device=gate.device).unsqueeze(1), topk_idx.to(gate.device) + 1] = 0
     return u0, gate
 
 
@@ -476,8 +476,12 @@ class OracleEncoderDecoder(nn.Module):
                                                    teacher['hard_seg_label'])
         return out
 
-    def forward_train(self, img, img_metas, gt_semantic_seg, topk_idx=None, record=None):
-        """Returns the reference's loss dict.  ``record`` (a dict) receives intermediates."""
+    def forward_train(self, img, img_metas, gt_semantic_seg, topk_idx=None, record=None,
+                      teacher_override=None):
+        """Returns the reference's loss dict.  ``record`` (a dict) receives intermediates.
+        ``teacher_override`` = dict(seg_logits, hard_seg_label, conf_mask): parity tests pin the
+        teacher outputs (e.g. to the ones the CUDA path produced) so that the student-side
+        arithmetic is compared given IDENTICAL pseudo labels."""
         tags = [m['tag'] for m in img_metas]
         groups = {}
         for t in dict.fromkeys(tags):
@@ -497,14 +501,16 @@ class OracleEncoderDecoder(nn.Module):
             losses['decode.loss_ce'] = dec['loss_ce']
         if 'unsup_student' in groups and self.unsup_weight != 0:   # :488-512
             un = self.forward_unsup_train(groups['unsup_teacher'], groups['unsup_student'],
-                                          topk_idx=topk_idx, record=record)
+                                          topk_idx=topk_idx, record=record,
+                                          teacher_override=teacher_override)
             for k in un:
                 if 'loss' in k:   # structual_utils.py:132-154
                     un[k] = un[k] * self.unsup_weight
             losses.update(un)
         return losses
 
-    def forward_unsup_train(self, teacher_data, student_data, topk_idx=None, record=None):
+    def forward_unsup_train(self, teacher_data, student_data, topk_idx=None, record=None,
+                            teacher_override=None):
         loss_unsup = {}
         tnames = [m['filename'] for m in teacher_data['metas']]
         snames = [m['filename'] for m in student_data['metas']]
@@ -518,6 +524,10 @@ class OracleEncoderDecoder(nn.Module):
             hard, conf, _ = pseudo_label(z_t, self.unsup_confidence)
             self.backbone_ema.train()
             self.decode_head_ema.train()
+        if teacher_override is not None:
+            z_t = teacher_override['seg_logits']
+            hard = teacher_override['hard_seg_label'].clone()
+            conf = teacher_override['conf_mask']
         teacher = dict(seg_logits=z_t, hard_seg_label=hard, conf_mask=conf)
         simg = student_data['img']
         smetas = student_data['metas']

@@ -66,7 +66,7 @@ class TransformerEncoderLayer(nn.Module):
         self.num_heads = num_heads
 
     def forward(self, x2d, B, L, u0=None, gate=None, w=0.0):
-        return ops.EncoderLayerFn.apply(x2d, self, B, L, u0, gate, float(w))
+        return ops.EncoderLayerFn.apply(x2d, self, B, L, u0, gate, float(w), self.ln1.weight)
 
 
 class _PatchEmbed(nn.Module):
@@ -107,6 +107,9 @@ class VisionTransformer(nn.Module):
                            (w_PatchRelativeAttention, 'w_PatchRelativeAttention')):
             if flag:
                 raise NotImplementedError(f'{name} is not used by any S4Former config (out of the hot path)')
+        if drop_path_rate:
+            raise NotImplementedError('drop_path_rate != 0 (stochastic depth) is not used by any S4Former '
+                                      'config; refusing to train silently without it')
         self.init_cfg = init_cfg
         self.img_size, self.patch_size = tuple(img_size), patch_size
         self.interpolate_mode, self.norm_eval, self.with_cp = interpolate_mode, norm_eval, with_cp
@@ -176,6 +179,8 @@ class VisionTransformer(nn.Module):
         u0 = torch.cat((torch.zeros(b, 1, device=flat.device), flat), -1).contiguous()
         gate = None
         if adaptive_attn_mask:
+            if callable(topk_idx):      # parity tests: e.g. the reference's CPU torch.topk on this u
+                topk_idx = topk_idx(flat)
             if topk_idx is None:
                 topk_idx = torch.topk(flat, int(0.5 * flat.size(-1)), dim=-1, largest=False)[1]
             gate = torch.ones_like(u0)

@@ -132,7 +132,7 @@ class SETRUPHead(BaseDecodeHead):
             has_cls = False
         row_map = self._row_map(B, g, has_cls, x2d.device, PatchMix_N, PatchMixIndex, b0)
         Ltok = g * g + 1
-        y = ops.HeadLNFn.apply(x2d, self, row_map, B, Ltok)
+        y = ops.HeadLNFn.apply(x2d, self, row_map, B, Ltok, self.norm.weight)
         H = W = g
         s = self.up_scale
         gi = self._group_info()

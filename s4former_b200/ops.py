@@ -196,6 +196,37 @@ def _add_bn_grads(bn, dgamma_dbeta):
         gb.add_(dgamma_dbeta[1])
 
 
+# Modules that run as ONE autograd node count their pending backward passes (three student passes
+# share the weights); the data-parallel reducer is told when the count returns to zero.  The
+# counters are re-armed at the start of every step (``reset_pending``): a grad-enabled forward
+# whose output feeds no loss, or an exception in the middle of backward, must not leave them
+# above zero for good (every bucket would silently fall back to ``GradReducer.finalize``).
+_pending_mods = {}
+
+
+def _pending_inc(mod):
+    mod._s4_pending = getattr(mod, '_s4_pending', 0) + 1
+    _pending_mods[id(mod)] = mod
+
+
+def _pending_dec(mod):
+    mod._s4_pending -= 1
+    if mod._s4_pending == 0:
+        hook = getattr(mod, '_s4_grad_ready_hook', None)
+        if hook is not None:
+            hook(mod)
+
+
+def reset_pending():
+    """Returns how many modules still had a pending count (0 in a healthy step)."""
+    stale = 0
+    for mod in _pending_mods.values():
+        if getattr(mod, '_s4_pending', 0):
+            stale += 1
+            mod._s4_pending = 0
+    return stale
+
+
 def grad_buffer(p):
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
@@ -351,7 +382,10 @@ class EncoderLayerFn(torch.autograd.Function):
     """x + OutProj(Attn(LN1(x))) then + FFN(LN2(.)); ``layer`` supplies the parameters."""
 
     @staticmethod
-    def forward(ctx, x, layer, B, Ltok, u0, gate, w):
+    def forward(ctx, x, layer, B, Ltok, u0, gate, w, _param_probe=None):
+        # ``_param_probe`` (one of the layer's parameters) makes ``needs_input_grad`` reflect the
+        # parameters too: a trainable layer behind a frozen / non-differentiable input still
+        # takes the training path (its weights are not autograd inputs, see the module docstring)
         M, D = x.shape
         H = layer.num_heads
         hd = D // H
@@ -363,7 +397,7 @@ class EncoderLayerFn(torch.autograd.Function):
         att, lse = attention_fwd(qkv, B, Ltok, H, hd, u0, gate, w)
         xm = linear_fwd(att, lowp(mha.out_proj.weight), mha.out_proj.bias, res=x)
         xl2, mean2, rstd2 = layernorm_fwd(xm, layer.ln2.weight, layer.ln2.bias, eps)
-        if not ctx.needs_input_grad[0]:
+        if not any(ctx.needs_input_grad):
             # no-grad pass (the EMA teacher): the pre-activation copy (one extra [M, 4D] store) and
             # the saved activations are only needed by backward
             h = linear_fwd(xl2, lowp(fc1.weight), fc1.bias, act=L.ACT_GELU)
@@ -372,7 +406,7 @@ class EncoderLayerFn(torch.autograd.Function):
         y = linear_fwd(h, lowp(fc2.weight), fc2.bias, res=xm)
         ctx.layer, ctx.dims, ctx.w = layer, (B, Ltok, H, hd), w
         ctx.save_for_backward(x, xl1, mean1, rstd1, qkv, att, lse, xm, xl2, mean2, rstd2, pre, h, u0, gate)
-        layer._s4_pending = getattr(layer, '_s4_pending', 0) + 1
+        _pending_inc(layer)
         return y
 
     @staticmethod
@@ -397,12 +431,8 @@ class EncoderLayerFn(torch.autograd.Function):
         dxl1 = linear_dgrad(dqkv, lowp(mha.in_proj_weight))
         linear_wgrad(dqkv, xl1, mha.in_proj_weight, mha.in_proj_bias)
         dx = layernorm_bwd(dxl1, x, layer.ln1.weight, layer.ln1.bias, mean1, rstd1, dres=dxm)
-        layer._s4_pending -= 1
-        if layer._s4_pending == 0:
-            hook = getattr(layer, '_s4_grad_ready_hook', None)
-            if hook is not None:
-                hook(layer)
-        return dx, None, None, None, None, None, None
+        _pending_dec(layer)
+        return dx, None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -427,7 +457,8 @@ class PatchEmbedFn(torch.autograd.Function):
                B, Ltok, D, _code(dt), _st())
         ctx.bb, ctx.dims = bb, (B, Ltok, D)
         ctx.save_for_backward(a)
-        bb._s4_pending = getattr(bb, '_s4_pending', 0) + 1
+        if any(ctx.needs_input_grad):       # all False under no_grad: no backward will come
+            _pending_inc(bb)
         return x
 
     @staticmethod
@@ -437,17 +468,16 @@ class PatchEmbedFn(torch.autograd.Function):
         B, Ltok, D = ctx.dims
         dx = dx.contiguous()
         dtok = torch.empty((B * (Ltok - 1), D), dtype=dx.dtype, device=dx.device)
-        gcls = torch.zeros_like(bb.cls_token)
-        L.call('s4_assemble_tokens_bwd', _p(dx), _p(dtok), _p(gcls), _p(grad_buffer(bb.pos_embed)),
-               B, Ltok, D, _code(dx.dtype), _st())
+        # cls_token / pos_embed gradients are accumulated straight into their gradient buffers
+        # (like every other parameter): returning the cls gradient to autograd instead would let
+        # AccumulateGrad add it AFTER the grad-ready hook below has handed the bucket holding
+        # cls_token to the asynchronous all-reduce (a data race at N > 1).
+        L.call('s4_assemble_tokens_bwd', _p(dx), _p(dtok), _p(grad_buffer(bb.cls_token)),
+               _p(grad_buffer(bb.pos_embed)), B, Ltok, D, _code(dx.dtype), _st())
         proj = bb.patch_embed.projection
         linear_wgrad(dtok, a, proj.weight, proj.bias)
-        bb._s4_pending -= 1
-        if bb._s4_pending == 0:
-            hook = getattr(bb, '_s4_grad_ready_hook', None)
-            if hook is not None:
-                hook(bb)
-        return gcls, None, None
+        _pending_dec(bb)
+        return None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -466,14 +496,15 @@ class HeadLNFn(torch.autograd.Function):
     (reference setr_up_head.py:96-104, decode_head.py:186-212)."""
 
     @staticmethod
-    def forward(ctx, x_tokens, head, row_map, B, Ltok):
+    def forward(ctx, x_tokens, head, row_map, B, Ltok, _param_probe=None):
         D = x_tokens.shape[1]
         rows = B * (Ltok - 1)
         y, mean, rstd = layernorm_fwd(x_tokens, head.norm.weight, head.norm.bias, head.norm.eps,
                                       row_map=row_map, out_rows=rows)
         ctx.head = head
         ctx.save_for_backward(x_tokens, mean, rstd, row_map)
-        head._s4_pending = getattr(head, '_s4_pending', 0) + 1
+        if any(ctx.needs_input_grad):
+            _pending_inc(head)
         return y
 
     @staticmethod
@@ -482,12 +513,8 @@ class HeadLNFn(torch.autograd.Function):
         head = ctx.head
         dx = layernorm_bwd(dy.contiguous(), x_tokens, head.norm.weight, head.norm.bias, mean, rstd,
                            row_map=row_map)
-        head._s4_pending -= 1
-        if head._s4_pending == 0:      # the LayerNorm is the last node of the head's backward
-            hook = getattr(head, '_s4_grad_ready_hook', None)
-            if hook is not None:
-                hook(head)
-        return dx, None, None, None, None
+        _pending_dec(head)                 # the LayerNorm is the last node of the head's backward
+        return dx, None, None, None, None, None
 
 
 def _conv_fwd(stage, x, B, H, W, Cin, Cout, training):

@@ -93,9 +93,16 @@ class GradReducer:
     def finalize(self):
         """Reduce whatever has not been launched, wait for everything, and re-arm."""
         if self.world > 1:
-            for b in range(len(self.buckets)):
-                if not self.launched[b]:
-                    self._launch(b)
+            late = [b for b in range(len(self.buckets)) if not self.launched[b]]
+            self.late_buckets = len(late)
+            if late and not getattr(self, '_warned_late', False):
+                import warnings
+                warnings.warn(f'GradReducer: {len(late)} of {len(self.buckets)} gradient buckets were not '
+                              'signalled ready during backward and are all-reduced without overlap '
+                              '(a student pass that fed no loss?)')
+                self._warned_late = True
+            for b in late:
+                self._launch(b)
             for w in self.works:
                 if isinstance(w, tuple):
                     w[0].wait()

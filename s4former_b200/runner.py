@@ -32,6 +32,7 @@ class TrainStep:
         ``sync=False`` the log variables stay device tensors (no host synchronisation)."""
         self.optimizer.zero_grad()
         ops.reset_arena()
+        self.stale_pending = ops.reset_pending()      # 0 in a healthy step (see ops._pending_inc)
         losses = self.model(img, img_metas, return_loss=True, gt_semantic_seg=gt_semantic_seg, iter=it)
         loss, log_vars = self.model._parse_losses(losses, sync=False)
         loss.backward()

@@ -336,10 +336,14 @@ class EncoderDecoder(BaseSegmentor):
         if not self.attn_mask_seperate_head:
             # Mean-Teacher config as shipped (:650-670): a PASA student pass whose features feed
             # no loss (hazard 4) -- executed for fidelity of the as-shipped step.
+            # Its output reaches no loss, so it is run without autograd bookkeeping: same values,
+            # no saved activations, and the pending-backward counters of the gradient reducer
+            # (ops._pending_inc) are not armed for a backward that never comes.
             attn_mask = self._patch_unconfidence(teacher_info, student_info)
-            unlabled_feat = self.extract_feat(
-                student_info['img'], attn_mask=attn_mask, attn_mask_weight=self.attn_mask_weight,
-                adaptive_attn_mask=self.adaptive_attn_mask)
+            with torch.no_grad():
+                unlabled_feat = self.extract_feat(
+                    student_info['img'], attn_mask=attn_mask, attn_mask_weight=self.attn_mask_weight,
+                    adaptive_attn_mask=self.adaptive_attn_mask)
         else:
             unlabled_feat = self.extract_feat(student_info['img'])
         student_info['backbone_feature'] = unlabled_feat
