@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument('--no-extra-configs', action='store_true',
                     help='skip the short runs of BASELINE configs 1/2/4 (sup-only, MT, 768x768/19)')
     ap.add_argument('--no-parity', action='store_true', help='skip the in-bench parity block')
+    ap.add_argument('--no-graph', action='store_true',
+                    help='launch every kernel from the host each step instead of replaying the captured CUDA graph')
     return ap.parse_args()
 
 
@@ -273,7 +275,7 @@ def main():
     model.backbone_ema.load_state_dict(model.backbone.state_dict())
     model.decode_head_ema.load_state_dict(model.decode_head.state_dict())
     model = model.to(dev).train()
-    step = TrainStep(model)
+    step = TrainStep(model, cuda_graph=not a.no_graph, graph_warmup=2)
 
     img, gt, metas = make_batch(a.sup, n_unsup, a.size, a.classes, seed=1999 + rank)
     img_h, gt_h = img.pin_memory(), gt.pin_memory()
@@ -344,9 +346,14 @@ def main():
     if rank == 0:
         clocks.start()
     l0 = lib.s4_launch_count()
+    r0 = step.replays
     ms = timed(run_resident, a.steps)
     host_enqueue_ms = host_ms[0]
-    launches = (lib.s4_launch_count() - l0) // a.steps
+    graph_replays = step.replays - r0
+    if graph_replays == a.steps:      # kernel nodes of the captured step (counted while capturing)
+        launches = step.graph_kernel_launches
+    else:
+        launches = (lib.s4_launch_count() - l0) // a.steps
     run_e2e(0)
     drain_e2e()
     ms_e2e = timed(lambda i: run_e2e(i, a.steps), a.steps, after=drain_e2e)
@@ -357,11 +364,13 @@ def main():
     # ---- roofline leg: per-kernel-family device time, measured live with CUDA events ---------
     kinds = []
     if not a.no_prof:
+        use_graph, step.cuda_graph = step.cuda_graph, False     # per-launch event pairs need host launches
         lib.s4_prof_enable(1)
         nprof = 2
         for i in range(nprof):
             run_resident(i)
         torch.cuda.synchronize()
+        step.cuda_graph = use_graph
         import ctypes as C
         for i in range(lib.s4_prof_num_kinds()):
             name = C.create_string_buffer(64)
@@ -423,6 +432,8 @@ def main():
                         d2h_bytes_per_step=4 * len(last)),
                gpu_launches=int(launches) * a.steps, gpu_launches_per_step=int(launches),
                host_enqueue_ms_per_step=host_enqueue_ms,
+               cuda_graph=dict(enabled=not a.no_graph, replays_in_timed_region=int(graph_replays),
+                               kernel_nodes_per_replay=getattr(step, 'graph_kernel_launches', None)),
                clocks=clk, roofline=roofline,
                kernels=sorted(kinds, key=lambda k: -k["ms_per_step"])[:40])
     if world == 1 and not a.no_cpu_baseline:

@@ -30,6 +30,17 @@ int s4_cls_upsample_fwd(const float* z, float* logits, int B, int H, int W, int 
 int s4_cls_upsample_bwd(const float* dlogits, void* dz16, int B, int H, int W, int NC, int s, cudaStream_t st);
 #include "gemm_params.h"
 
+// head_stream.cu: second-generation streaming kernels (bf16); false = shape outside the fast path
+bool s4_stream_upsample_fwd(const void* x, const float* scale, const float* shift, void* out, int B, int H,
+                            int W, int C, int s, cudaStream_t st);
+bool s4_stream_upsample_bwd(const void* dout, const void* x, const float* scale, const float* shift,
+                            const float* mean, const float* invstd, void* dact, float* dsum, float* ddot,
+                            int B, int H, int W, int C, int s, cudaStream_t st);
+bool s4_stream_bn_bwd_apply(const void* dact, const void* x, const float* gamma, const float* mean,
+                            const float* invstd, const float* dsum, const float* ddot, double count,
+                            void* dy, long long rows, int C, cudaStream_t st);
+bool s4_stream_pack_conv_weight(const float* w, void* wf, void* wd, int Cin, int Cout, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------
 // 3x3 convolution as implicit GEMM on CUDA cores (fp32 accumulate)
 //   fwd  : M = B*H*W pixels, N = Cout, K = 9*Cin ; A gathered from x, B = w_packed [N][K]
@@ -265,6 +276,8 @@ extern "C" int s4_pack_conv3x3_weight(const float* w, void* w_fwd, void* w_dgrad
   S4ProfScope prof_("pack_conv3x3_weight", 0.0, 1, stream);
   const int total = Cout * Cin * 9;
   if (total == 0) return S4_OK;
+  if (dtype == S4_BF16 && s4_stream_pack_conv_weight(w, w_fwd, w_dgrad, Cin, Cout, stream))
+    return s4_check_launch("pack_conv3x3_weight");
   const int grid = min((total + 255) / 256, s4_num_sms() * 8);
   if (dtype == S4_BF16)
     pack_conv_weight_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad, Cin, Cout);
@@ -477,6 +490,8 @@ extern "C" int s4_bn_relu_upsample_fwd(const void* x, const float* scale, const 
   S4_REQUIRE(C % vn == 0 && s >= 1, "bn_relu_upsample: C=%d must be a multiple of %d", C, vn);
   const size_t total = (size_t)B * H * s * W * s * (C / vn);
   if (total == 0) return S4_OK;
+  if (dtype == S4_BF16 && s4_stream_upsample_fwd(x, scale, shift, out, B, H, W, C, s, stream))
+    return s4_check_launch("bn_relu_upsample_fwd");
   const bool done = dtype == S4_BF16
                         ? bn_relu_upsample_fwd_blk<__nv_bfloat16>(x, scale, shift, out, B, H, W, C, s, stream)
                         : bn_relu_upsample_fwd_blk<float>(x, scale, shift, out, B, H, W, C, s, stream);
@@ -686,6 +701,9 @@ extern "C" int s4_bn_relu_upsample_bwd(const void* dout, const void* x, const fl
   S4_REQUIRE(C % vn == 0 && s >= 1, "bn_relu_upsample_bwd: C=%d must be a multiple of %d", C, vn);
   const size_t total = (size_t)B * H * W * (C / vn);
   if (total == 0) return S4_OK;
+  if (dtype == S4_BF16 &&
+      s4_stream_upsample_bwd(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, s, stream))
+    return s4_check_launch("bn_relu_upsample_bwd");
   const bool done =
       dtype == S4_BF16
           ? bn_relu_upsample_bwd_blk<__nv_bfloat16>(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, s, stream)
@@ -753,6 +771,9 @@ extern "C" int s4_bn_bwd_apply(const void* dact, const void* x, const float* gam
   S4_REQUIRE(C % vn == 0, "bn_bwd_apply: C=%d must be a multiple of %d", C, vn);
   const size_t total = (size_t)rows * (C / vn);
   if (total == 0) return S4_OK;
+  if (dtype == S4_BF16 &&
+      s4_stream_bn_bwd_apply(dact, x, gamma, mean, invstd, dsum, ddot, count, dy, rows, C, stream))
+    return s4_check_launch("bn_bwd_apply");
   const int grid = (int)min((total + 255) / 256, (size_t)s4_num_sms() * 32);
   const float inv_n = (float)(1.0 / count);
   if (dtype == S4_BF16)

@@ -53,7 +53,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // lanes = 64 contiguous bytes per row): channel(step s, mma m, slot) = 32 s + 8 t + 4 m + slot.
 // ---------------------------------------------------------------------------------------------
 template <int STEPS, int NT>   // C = 32 * STEPS, NC <= 8 * NT
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, STEPS <= 8 ? 2 : 1)
 cls_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                const float* __restrict__ shift, const float* __restrict__ w,
                const float* __restrict__ bias, float* __restrict__ z, long long rows, int NC) {
@@ -75,15 +75,27 @@ cls_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ sc
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long nblk = (rows + 15) / 16;
+  // register double buffering: the loads of the warp's NEXT 16-row block are issued before the
+  // current block's BN + ReLU + MMAs (v1 was latency-bound: 11 long-scoreboard stall cycles per
+  // issue at 21 % issue utilisation)
+  uint4 na[STEPS], nb[STEPS];
+  auto fetch = [&](long long blk) {
+    const long long ra = blk * 16 + g, rb = ra + 8;
+    const bool oka = blk < nblk && ra < rows, okb = blk < nblk && rb < rows;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      na[s] = oka ? __ldg(reinterpret_cast<const uint4*>(y + ra * C + 32 * s + 8 * t)) : make_uint4(0, 0, 0, 0);
+      nb[s] = okb ? __ldg(reinterpret_cast<const uint4*>(y + rb * C + 32 * s + 8 * t)) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  fetch(warp0);
   for (long long blk = warp0; blk < nblk; blk += nwarps) {
     const long long ra = blk * 16 + g, rb = ra + 8;
     const bool oka = ra < rows, okb = rb < rows;
     uint4 xa[STEPS], xb[STEPS];
 #pragma unroll
-    for (int s = 0; s < STEPS; ++s) {
-      xa[s] = oka ? __ldg(reinterpret_cast<const uint4*>(y + ra * C + 32 * s + 8 * t)) : make_uint4(0, 0, 0, 0);
-      xb[s] = okb ? __ldg(reinterpret_cast<const uint4*>(y + rb * C + 32 * s + 8 * t)) : make_uint4(0, 0, 0, 0);
-    }
+    for (int s = 0; s < STEPS; ++s) { xa[s] = na[s]; xb[s] = nb[s]; }
+    fetch(blk + nwarps);
     float acc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
@@ -144,7 +156,12 @@ __device__ __forceinline__ int grp_channel(int nt, int j) {
   return idx < 8 ? 8 * tt + idx : 32 + 8 * tt + (idx - 8);
 }
 
-template <int GROUPS>   // C = 64 * GROUPS
+// v2: gamma*invstd is folded into the B fragments (W[j,c] * A[c] before the bf16 rounding), so
+//   dy = mask * (dz @ (W A)) - y * (A E) - A F
+// needs ONE float4 of per-channel constants (scale, shift, A E, A F); a warp iteration covers
+// RB 16-row blocks so each constant load serves 2 RB outputs (v1: short-scoreboard stalls of 18
+// cycles per issue on three smem loads per output pair).
+template <int GROUPS, int RB>   // C = 64 * GROUPS
 __global__ void __launch_bounds__(256)
 cls_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz16, const __nv_bfloat16* __restrict__ y,
                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -154,83 +171,100 @@ cls_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz16, const __nv_bfloat16
                      __nv_bfloat16* __restrict__ dy, long long rows, int NC) {
   constexpr int C = 64 * GROUPS;
   extern __shared__ __align__(16) uint8_t smem[];
-  float4* t1 = reinterpret_cast<float4*>(smem);                       // [C] scale, shift, E, F
-  float* t2 = reinterpret_cast<float*>(smem + C * sizeof(float4));    // [C] A = gamma * invstd
-  uint2* bfr = reinterpret_cast<uint2*>(smem + C * (sizeof(float4) + sizeof(float)));   // [GROUPS][8][2][32]
+  float4* t1 = reinterpret_cast<float4*>(smem);                       // [C] scale, shift, A*E, A*F
+  uint2* bfr = reinterpret_cast<uint2*>(smem + C * sizeof(float4));   // [GROUPS][8][2][32]
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float is = invstd[c];
+    const float A = gamma[c] * is;
     const float E = is * ddot[c] * inv_n;                    // xhat*ddot/n = (y - mean) * E
     const float F = dsum[c] * inv_n - mean[c] * E;
-    t1[c] = make_float4(scale[c], shift[c], E, F);
-    t2[c] = gamma[c] * is;
+    t1[c] = make_float4(scale[c], shift[c], A * E, A * F);
   }
   for (int i = threadIdx.x; i < GROUPS * 8 * 2 * 32; i += blockDim.x) {
     const int ln = i & 31, ks = (i >> 5) & 1, nt = (i >> 6) & 7, gq = i >> 9;
     const int ch = 64 * gq + grp_channel(nt, ln >> 2);
     const int k = 16 * ks + 2 * (ln & 3);
-    auto wv = [&](int kk) { return kk < NC ? w[(size_t)kk * C + ch] : 0.f; };
+    const float A = gamma[ch] * invstd[ch];
+    auto wv = [&](int kk) { return kk < NC ? w[(size_t)kk * C + ch] * A : 0.f; };
     bfr[i] = make_uint2(pack2(wv(k), wv(k + 1)), pack2(wv(k + 8), wv(k + 9)));
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long nblk = (rows + 15) / 16;
+  const long long nblk = (rows + 16 * RB - 1) / (16 * RB);
   for (long long blk = warp0; blk < nblk; blk += nwarps) {
-    const long long ra = blk * 16 + g, rb = ra + 8;
-    const bool oka = ra < rows, okb = rb < rows;
-    uint32_t a[2][4];
-    {
-      const uint32_t* pa = reinterpret_cast<const uint32_t*>(dz16 + ra * 32);
-      const uint32_t* pb = reinterpret_cast<const uint32_t*>(dz16 + rb * 32);
+    long long rr[RB][2];
+    bool ok[RB][2];
+    uint32_t a[RB][2][4];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) {
+      rr[rb][0] = (blk * RB + rb) * 16 + g;
+      rr[rb][1] = rr[rb][0] + 8;
+      ok[rb][0] = rr[rb][0] < rows;
+      ok[rb][1] = rr[rb][1] < rows;
+      const uint32_t* pa = reinterpret_cast<const uint32_t*>(dz16 + rr[rb][0] * 32);
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(dz16 + rr[rb][1] * 32);
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        a[ks][0] = oka ? __ldg(pa + 8 * ks + t) : 0u;
-        a[ks][1] = okb ? __ldg(pb + 8 * ks + t) : 0u;
-        a[ks][2] = oka ? __ldg(pa + 8 * ks + 4 + t) : 0u;
-        a[ks][3] = okb ? __ldg(pb + 8 * ks + 4 + t) : 0u;
+        a[rb][ks][0] = ok[rb][0] ? __ldg(pa + 8 * ks + t) : 0u;
+        a[rb][ks][1] = ok[rb][1] ? __ldg(pb + 8 * ks + t) : 0u;
+        a[rb][ks][2] = ok[rb][0] ? __ldg(pa + 8 * ks + 4 + t) : 0u;
+        a[rb][ks][3] = ok[rb][1] ? __ldg(pb + 8 * ks + 4 + t) : 0u;
       }
     }
 #pragma unroll 1
     for (int gq = 0; gq < GROUPS; ++gq) {
       const int cb = 64 * gq;
-      uint4 ya[2], yb[2];
+      uint4 yv[RB][2][2];     // [row block][row a/b][half of the 64-channel group]
 #pragma unroll
-      for (int hc = 0; hc < 2; ++hc) {
-        ya[hc] = oka ? __ldg(reinterpret_cast<const uint4*>(y + ra * C + cb + 32 * hc + 8 * t)) : make_uint4(0, 0, 0, 0);
-        yb[hc] = okb ? __ldg(reinterpret_cast<const uint4*>(y + rb * C + cb + 32 * hc + 8 * t)) : make_uint4(0, 0, 0, 0);
-      }
-      float acc[8][4];
+      for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+        for (int ab = 0; ab < 2; ++ab)
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc)
+            yv[rb][ab][hc] = ok[rb][ab] ? __ldg(reinterpret_cast<const uint4*>(y + rr[rb][ab] * C + cb + 32 * hc + 8 * t))
+                                        : make_uint4(0, 0, 0, 0);
+      float acc[RB][8][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
         const uint2 b0 = bfr[((gq * 8 + nt) * 2 + 0) * 32 + lane];
         const uint2 b1 = bfr[((gq * 8 + nt) * 2 + 1) * 32 + lane];
-        mma_bf16_16816(acc[nt], a[0], b0.x, b0.y);
-        mma_bf16_16816(acc[nt], a[1], b1.x, b1.y);
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[rb][nt][e] = 0.f;
+          mma_bf16_16816(acc[rb][nt], a[rb][0], b0.x, b0.y);
+          mma_bf16_16816(acc[rb][nt], a[rb][1], b1.x, b1.y);
+        }
       }
 #pragma unroll
       for (int hc = 0; hc < 2; ++hc) {
-        const uint32_t wa[4] = {ya[hc].x, ya[hc].y, ya[hc].z, ya[hc].w};
-        const uint32_t wb[4] = {yb[hc].x, yb[hc].y, yb[hc].z, yb[hc].w};
-        uint32_t oa[4], ob[4];
+        uint32_t oo[RB][2][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {   // channels cb + 32 hc + 8 t + 2q (+1)  <->  n-tile 4 hc + q
           const int nt = 4 * hc + q;
           const int ch = cb + 32 * hc + 8 * t + 2 * q;
           const float4 k0 = t1[ch], k1 = t1[ch + 1];
-          const float A0 = t2[ch], A1 = t2[ch + 1];
-          const float2 va = unpack2(wa[q]), vb = unpack2(wb[q]);
-          const float da00 = fmaf(va.x, k0.x, k0.y) > 0.f ? acc[nt][0] : 0.f;
-          const float da01 = fmaf(va.y, k1.x, k1.y) > 0.f ? acc[nt][1] : 0.f;
-          const float da10 = fmaf(vb.x, k0.x, k0.y) > 0.f ? acc[nt][2] : 0.f;
-          const float da11 = fmaf(vb.y, k1.x, k1.y) > 0.f ? acc[nt][3] : 0.f;
-          oa[q] = pack2(A0 * (da00 - fmaf(va.x, k0.z, k0.w)), A1 * (da01 - fmaf(va.y, k1.z, k1.w)));
-          ob[q] = pack2(A0 * (da10 - fmaf(vb.x, k0.z, k0.w)), A1 * (da11 - fmaf(vb.y, k1.z, k1.w)));
+#pragma unroll
+          for (int rb = 0; rb < RB; ++rb) {
+            const uint32_t wa = (&yv[rb][0][hc].x)[q], wb = (&yv[rb][1][hc].x)[q];
+            const float2 va = unpack2(wa), vb = unpack2(wb);
+            const float da00 = fmaf(va.x, k0.x, k0.y) > 0.f ? acc[rb][nt][0] : 0.f;
+            const float da01 = fmaf(va.y, k1.x, k1.y) > 0.f ? acc[rb][nt][1] : 0.f;
+            const float da10 = fmaf(vb.x, k0.x, k0.y) > 0.f ? acc[rb][nt][2] : 0.f;
+            const float da11 = fmaf(vb.y, k1.x, k1.y) > 0.f ? acc[rb][nt][3] : 0.f;
+            oo[rb][0][q] = pack2(da00 - fmaf(va.x, k0.z, k0.w), da01 - fmaf(va.y, k1.z, k1.w));
+            oo[rb][1][q] = pack2(da10 - fmaf(vb.x, k0.z, k0.w), da11 - fmaf(vb.y, k1.z, k1.w));
+          }
         }
-        if (oka) *reinterpret_cast<uint4*>(dy + ra * C + cb + 32 * hc + 8 * t) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
-        if (okb) *reinterpret_cast<uint4*>(dy + rb * C + cb + 32 * hc + 8 * t) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+          for (int ab = 0; ab < 2; ++ab)
+            if (ok[rb][ab])
+              *reinterpret_cast<uint4*>(dy + rr[rb][ab] * C + cb + 32 * hc + 8 * t) =
+                  make_uint4(oo[rb][ab][0], oo[rb][ab][1], oo[rb][ab][2], oo[rb][ab][3]);
       }
     }
   }
@@ -481,6 +515,84 @@ cls_upsample_fwd_kernel(const float* __restrict__ z, float* __restrict__ out, in
   }
 }
 
+// v2: one block per (image, strip of P source rows) = S*P output rows.  Every source row is read
+// from global memory once per strip (cp.async into a 3-row smem ring, the next row in flight under
+// the current row's outputs) instead of once per output row by its own block; v1 ran at 2.0 TB/s
+// with 15 long-scoreboard stall cycles per issue (load phase and store phase serialised per block).
+template <int S>
+__global__ void __launch_bounds__(256)
+cls_upsample_fwd_strip_kernel(const float* __restrict__ z, float* __restrict__ out, int H, int W, int NC, int P) {
+  extern __shared__ __align__(16) float zs[];   // [3][n] ring, [n] blended row, [OW] (x0 | x1<<16), [OW] lx
+  const int OH = H * S, OW = W * S;
+  const int n = W * NC;                         // floats per source row (host checks n % 4 == 0)
+  float* vb = zs + 3 * n;
+  int* xi = reinterpret_cast<int*>(vb + n);
+  float* xl = vb + n + OW;
+  const int strips = (H + P - 1) / P;
+  const int strip = blockIdx.x % strips, b = blockIdx.x / strips;
+  const int r0 = strip * P, r1 = min(r0 + P, H);
+  const float* zb = z + (size_t)b * H * n;
+  auto fetch = [&](int r) {                     // source row r (clamped) -> ring slot (r + 1) % 3
+    const float* src = zb + (size_t)min(max(r, 0), H - 1) * n;
+    float* dst = zs + ((r + 1) % 3) * n;
+    for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) cp_async16(smem_addr(dst + i), src + i, true);
+    cp_async_commit();
+  };
+  fetch(r0 - 1);
+  fetch(r0);
+  for (int ox = threadIdx.x; ox < OW; ox += blockDim.x) {
+    int x0, x1;
+    float lx;
+    bl_src(ox, S, W, x0, x1, lx);
+    xi[ox] = x0 | (x1 << 16);
+    xl[ox] = lx;
+  }
+  float* ob = out + (size_t)b * NC * OH * OW;
+  for (int r = r0; r < r1; ++r) {
+    fetch(r + 1);                               // rows r-1, r resident or in flight; r+1 prefetched
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* up = zs + ((r + 0) % 3) * n;   // slot of row r-1
+    const float* mid = zs + ((r + 1) % 3) * n;  // row r
+    const float* dn = zs + ((r + 2) % 3) * n;   // row r+1 (complete only for the lower half: waited below)
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      const int oy = S * r + j;
+      // output row oy: source = r + (j + 0.5)/S - 0.5 -> rows (r-1, r) for j < S/2, (r, r+1) below
+      const float ly = (j + 0.5f) / S - 0.5f + (j < S / 2 ? 1.f : 0.f);
+      if (j == S / 2) {                         // the lower half needs row r+1
+        cp_async_wait<0>();
+        __syncthreads();
+      }
+      const float* a0 = j < S / 2 ? up : mid;
+      const float* a1 = j < S / 2 ? mid : dn;
+      for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
+        const float4 p = *reinterpret_cast<const float4*>(a0 + i), q = *reinterpret_cast<const float4*>(a1 + i);
+        float4 o;
+        o.x = fmaf(ly, q.x - p.x, p.x); o.y = fmaf(ly, q.y - p.y, p.y);
+        o.z = fmaf(ly, q.z - p.z, p.z); o.w = fmaf(ly, q.w - p.w, p.w);
+        *reinterpret_cast<float4*>(vb + i) = o;
+      }
+      __syncthreads();
+      for (int cls = threadIdx.x / 32; cls < NC; cls += blockDim.x / 32) {     // one warp per class row
+        float* orow = ob + ((size_t)cls * OH + oy) * OW;
+        for (int ox = (threadIdx.x & 31) * 4; ox < OW; ox += 128) {
+          const int4 pk = *reinterpret_cast<const int4*>(xi + ox);
+          const float4 lx = *reinterpret_cast<const float4*>(xl + ox);
+          float4 o;
+          o.x = (1.f - lx.x) * vb[(pk.x & 0xffff) * NC + cls] + lx.x * vb[(pk.x >> 16) * NC + cls];
+          o.y = (1.f - lx.y) * vb[(pk.y & 0xffff) * NC + cls] + lx.y * vb[(pk.y >> 16) * NC + cls];
+          o.z = (1.f - lx.z) * vb[(pk.z & 0xffff) * NC + cls] + lx.z * vb[(pk.z >> 16) * NC + cls];
+          o.w = (1.f - lx.w) * vb[(pk.w & 0xffff) * NC + cls] + lx.w * vb[(pk.w >> 16) * NC + cls];
+          *reinterpret_cast<float4*>(orow + ox) = o;
+        }
+      }
+      __syncthreads();                          // vb is rewritten by the next output row
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // transpose of the above into the padded bf16 layout the backward MMAs read: dz16 [B*H*W, 32].
 // One block per (image, source row).  Exactly 2S output rows / columns carry weight for a source
 // row / column (S*i - S/2 .. S*i + 3S/2 - 1).  Phase 1 streams the 2S output rows of every class
@@ -614,14 +726,14 @@ int s4_cls_bwd_apply_tc(const void* dz16, const void* y, const float* scale, con
                         const float* mean, const float* invstd, const float* gamma, const float* w,
                         const float* dsum, const float* ddot, double count, void* dy, long long rows,
                         int C, int NC, cudaStream_t st) {
-  const size_t smem = (size_t)C * 20 + (size_t)(C / 64) * 8 * 2 * 32 * 8;
-  const int grid = (int)std::min<long long>((rows + 127) / 128, (long long)s4_num_sms() * 4);
+  const size_t smem = (size_t)C * 16 + (size_t)(C / 64) * 8 * 2 * 32 * 8;
+  const int grid = (int)std::min<long long>((rows + 255) / 256, (long long)s4_num_sms() * 4);
   const float inv_n = (float)(1.0 / count);
   int rc;
 #define S4_CLS_APP(GROUPS)                                                                         \
   {                                                                                                \
-    if ((rc = set_smem(cls_bwd_apply_kernel<GROUPS>, smem, "cls_bwd_apply"))) return rc;           \
-    cls_bwd_apply_kernel<GROUPS><<<grid, 256, smem, st>>>(                                         \
+    if ((rc = set_smem(cls_bwd_apply_kernel<GROUPS, 2>, smem, "cls_bwd_apply"))) return rc;        \
+    cls_bwd_apply_kernel<GROUPS, 2><<<grid, 256, smem, st>>>(                                       \
         (const __nv_bfloat16*)dz16, (const __nv_bfloat16*)y, scale, shift, mean, invstd, gamma, w, \
         dsum, ddot, inv_n, (__nv_bfloat16*)dy, rows, NC);                                          \
   }
@@ -634,8 +746,25 @@ int s4_cls_bwd_apply_tc(const void* dz16, const void* y, const float* scale, con
 }
 
 int s4_cls_upsample_fwd(const float* z, float* logits, int B, int H, int W, int NC, int s, cudaStream_t st) {
-  const size_t smem = (size_t)2 * W * NC * 4 + (size_t)2 * W * s * 4;
   int rc;
+  const size_t n = (size_t)W * NC;
+  const size_t smem2 = 4 * n * 4 + (size_t)2 * W * s * 4;
+  if ((s == 2 || s == 4) && n % 4 == 0 && (W * s) % 4 == 0 && smem2 <= 200 * 1024 &&
+      (((uintptr_t)z | (uintptr_t)logits) & 15) == 0) {
+    // strip height: >= 2 blocks per SM in flight (two fit by shared memory), at most 8 rows
+    // strip height: ONE wave of blocks (two fit per SM by shared memory), as many as possible
+    const int P = (int)std::max<long long>(2, ((long long)B * H + 2 * s4_num_sms() - 1) / (2 * s4_num_sms()));
+    const int grid = B * ((H + P - 1) / P);
+    if (s == 2) {
+      if ((rc = set_smem(cls_upsample_fwd_strip_kernel<2>, smem2, "cls_upsample_fwd"))) return rc;
+      cls_upsample_fwd_strip_kernel<2><<<grid, 256, smem2, st>>>(z, logits, H, W, NC, P);
+    } else {
+      if ((rc = set_smem(cls_upsample_fwd_strip_kernel<4>, smem2, "cls_upsample_fwd"))) return rc;
+      cls_upsample_fwd_strip_kernel<4><<<grid, 256, smem2, st>>>(z, logits, H, W, NC, P);
+    }
+    return s4_check_launch("cls_upsample_fwd");
+  }
+  const size_t smem = (size_t)2 * W * NC * 4 + (size_t)2 * W * s * 4;
   if ((rc = set_smem(cls_upsample_fwd_kernel, smem, "cls_upsample_fwd"))) return rc;
   cls_upsample_fwd_kernel<<<B * H * s, 256, smem, st>>>(z, logits, H, W, NC, s);
   return s4_check_launch("cls_upsample_fwd");

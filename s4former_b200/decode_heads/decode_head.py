@@ -54,6 +54,9 @@ class BaseDecodeHead(nn.Module, metaclass=ABCMeta):
 
     @staticmethod
     def _patchmix_index(img_metas):
+        dev = img_metas[0].get('_s4_perms_dev')
+        if dev is not None:           # resident copy of the same permutations (no host round trip)
+            return dev, img_metas[-1]['PatchMix_N']
         idx = torch.stack([torch.as_tensor(m['PatchMixIndex']) for m in img_metas])
         return idx, img_metas[-1]['PatchMix_N']
 

@@ -94,15 +94,28 @@ class SETRUPHead(BaseDecodeHead):
             return m
         n = int(PatchMix_N)
         gb = g // n
-        perm = torch.as_tensor(PatchMixIndex).to('cpu', torch.int64).reshape(B, gb * gb)
+        perm = torch.as_tensor(PatchMixIndex)
+        # the index arithmetic runs where the permutation lives: on the host for the reference's
+        # per-meta tensors, on the device (a dozen tiny launches, no host round trip -> CUDA-graph
+        # capturable) for the resident copy of a pre-drawn step
+        pdev = perm.device if perm.is_cuda else torch.device('cpu')
+        perm = perm.to(torch.int64).reshape(B, gb * gb)
+        key = ('grid', B, g, n, has_cls, b0, str(pdev))
+        grid = self._row_maps.get(key)
+        if grid is None:
+            ty, tx = torch.meshgrid(torch.arange(g), torch.arange(g), indexing='ij')
+            qb = ((ty // n) * gb + (tx // n)).reshape(-1)                   # destination block of each token
+            grid = (qb.to(pdev), (ty % n).reshape(1, -1).to(pdev), (tx % n).reshape(1, -1).to(pdev),
+                    torch.arange(gb * gb, dtype=torch.int64, device=pdev).expand(B, -1).contiguous(),
+                    (torch.arange(B, dtype=torch.int64, device=pdev).view(B, 1) * Ls + off))
+            self._row_maps[key] = grid
+        qb, ry, rx, ar, base = grid
         inv = torch.empty_like(perm)
-        inv.scatter_(1, perm, torch.arange(gb * gb, dtype=torch.int64).expand(B, -1))
-        ty, tx = torch.meshgrid(torch.arange(g), torch.arange(g), indexing='ij')
-        qb = (ty // n) * gb + (tx // n)                      # destination block of each token
-        src_blk = inv[:, qb.reshape(-1)]                     # [B, g*g] source block
-        sy = (src_blk // gb) * n + (ty % n).reshape(1, -1)
-        sx = (src_blk % gb) * n + (tx % n).reshape(1, -1)
-        m = torch.arange(B, dtype=torch.int64).view(B, 1) * Ls + off + sy * g + sx
+        inv.scatter_(1, perm, ar)
+        src_blk = inv[:, qb]                                 # [B, g*g] source block
+        sy = (src_blk // gb) * n + ry
+        sx = (src_blk % gb) * n + rx
+        m = base + sy * g + sx
         return m.reshape(-1).to(torch.int32).to(device, non_blocking=True)
 
     def _group_info(self):

@@ -64,13 +64,22 @@ def _require_cuda(*ts):
 # ----------------------------------------------------------------------------------------------
 # low-precision / repacked weight cache
 # ----------------------------------------------------------------------------------------------
+_global_gen = [0]
+
+
 def bump_generation(p):
     """Call after a raw-pointer kernel (EMA / SGD) has modified ``p`` in place."""
     p._s4_gen = getattr(p, '_s4_gen', 0) + 1
 
 
+def bump_all_generations():
+    """Every parameter may have changed behind the host's back (a CUDA-graph replay of the whole
+    step): one counter that is part of every cache tag."""
+    _global_gen[0] += 1
+
+
 def _cache(p, key, make):
-    tag = (p._version, getattr(p, '_s4_gen', 0), p.data_ptr(), compute_dtype())
+    tag = (p._version, getattr(p, '_s4_gen', 0), _global_gen[0], p.data_ptr(), compute_dtype())
     store = p.__dict__.setdefault('_s4_cache', {})
     hit = store.get(key)
     if hit is not None and hit[0] == tag:
@@ -99,7 +108,8 @@ def transpose2d(x):
 
 
 def _param_tag(p):
-    return (p._version, getattr(p, '_s4_gen', 0), p.data_ptr())
+    return (p._version, getattr(p, '_s4_gen', 0), p.data_ptr())     # (shadows are refreshed by the
+    # EMA / SGD kernels themselves, also inside a graph replay: no global generation here)
 
 
 def lowp(p):
@@ -148,6 +158,71 @@ def conv_packed(p):
         L.call('s4_pack_conv3x3_weight', _p(p.detach()), _p(wf), _p(wd), cin, cout, _code(dt), _st())
         return wf, wd
     return _cache(p, 'conv', make)
+
+
+# ----------------------------------------------------------------------------------------------
+# host-drawn per-step parameters (augmentation boxes / permutations, learning rates)
+# ----------------------------------------------------------------------------------------------
+class StepParams:
+    """Everything the HOST decides per training step (CutMix boxes, PatchShuffle permutations --
+    host RNG, reference call order -- and the poly-LR table) lives in ONE persistent device buffer
+    refreshed by ONE small host->device copy before the step's first kernel.  The device program
+    of a step then depends on the host only through this buffer, which is what allows the whole
+    step to be captured in a CUDA graph and replayed (runner.TrainStep).
+
+    The staging side is a ring of pinned slots: a slot is rewritten only after the copy that read
+    it has completed on the device (the host may run a step or two ahead of the GPU)."""
+
+    def __init__(self, device, nbytes=1 << 16, slots=4):
+        self.device = torch.device(device)
+        self.dev = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self.host = [torch.zeros(nbytes, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.events = [None] * slots
+        self.k = -1
+        self.fields = {}
+        self.off = 0
+
+    def _field(self, name, shape, dtype):
+        f = self.fields.get(name)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        if f is None or f[1] != tuple(shape) or f[2] != dtype:
+            off = (self.off + 15) // 16 * 16
+            if off + nbytes > self.dev.numel():
+                raise RuntimeError('StepParams buffer exhausted')
+            self.off = off + nbytes
+            f = (off, tuple(shape), dtype, nbytes)
+            self.fields[name] = f
+        return f
+
+    def view(self, name, shape=None, dtype=None):
+        """Device view of a field (stable address for the lifetime of this object)."""
+        off, shp, dt, nbytes = self.fields[name] if shape is None else self._field(name, shape, dtype)
+        return self.dev[off:off + nbytes].view(dt).view(shp)
+
+    def begin(self):
+        self.k = (self.k + 1) % len(self.host)
+        ev = self.events[self.k]
+        if ev is not None:
+            ev.synchronize()
+
+    def set(self, name, value):
+        """Write a CPU tensor into the current staging slot; returns the device view."""
+        value = value.contiguous()
+        off, shp, dt, nbytes = self._field(name, value.shape, value.dtype)
+        self.host[self.k][off:off + nbytes].view(dt).view(shp).copy_(value)
+        return self.dev[off:off + nbytes].view(dt).view(shp)
+
+    def commit(self):
+        """One async H2D copy of the used prefix on the current stream."""
+        n = (self.off + 15) // 16 * 16
+        if n:
+            self.dev[:n].copy_(self.host[self.k][:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[self.k] = ev
 
 
 # ----------------------------------------------------------------------------------------------
@@ -775,7 +850,10 @@ def cutmix(img, label, boxes):
     """boxes: list of (y0, y1, x0, x1) from the host RNG."""
     _require_cuda(img)
     B, Cc, H, W = img.shape
-    bx = torch.tensor(boxes, dtype=torch.int32).reshape(B, 4).to(img.device, non_blocking=True)
+    if torch.is_tensor(boxes) and boxes.is_cuda:
+        bx = boxes                       # [B, 4] int32, already resident (ops.StepParams)
+    else:
+        bx = torch.as_tensor(boxes, dtype=torch.int32).reshape(B, 4).to(img.device, non_blocking=True)
     out_img = torch.empty_like(img)
     out_lab = torch.empty_like(label) if label is not None else None
     L.call('s4_cutmix', _p(img.contiguous()), _p(label.contiguous() if label is not None else None),
@@ -811,7 +889,10 @@ class TensorTable:
         self.chunk_tensor = torch.tensor(ct, dtype=torch.int32).to(device)
         self.chunk_off = torch.tensor(co, dtype=torch.int64).to(device)
         self.n_chunks = len(ct)
-        self.lrs = None if lrs is None else torch.tensor(lrs, dtype=torch.float32).to(device)
+        if torch.is_tensor(lrs):
+            self.lrs = lrs                    # a resident float32 table owned by the caller
+        else:
+            self.lrs = None if lrs is None else torch.tensor(lrs, dtype=torch.float32).to(device)
         self.key = tuple(0 if t is None else t.data_ptr() for lst in lists for t in lst)
         self.keep = lists
 
@@ -828,6 +909,8 @@ def ema_update(table, momentum):
 
 
 def sgd_step(table, momentum, weight_decay, first_step, lrs=None):
+    """``lrs``: host list -> copied into the table now; None -> the table's ``lrs`` tensor (e.g. a
+    ``StepParams`` view refreshed by the step's parameter upload) is used as it is."""
     if lrs is not None:
         table.lrs.copy_(torch.tensor(lrs, dtype=torch.float32), non_blocking=True)
     shadow = table.ptrs[3] if len(table.ptrs) > 3 else None

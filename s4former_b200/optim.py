@@ -75,17 +75,31 @@ class FusedSGD:
         # mmcv applies the schedule to each group's own initial lr (base*mult), min_lr is absolute
         return [poly_lr(self.base_lr * m, it, self.max_iters, self.power, self.min_lr) for m in self.lr_mult]
 
+    def attach_step_params(self, sp):
+        """Read the per-step learning rates from ``sp`` (ops.StepParams, field 'lrs') instead of
+        copying a fresh host table inside ``step``: the step's device program then has no host
+        dependency of its own (CUDA-graph capture)."""
+        self._sp = sp
+        self._sp_view = sp.view('lrs', (len(self.params),), torch.float32)
+        self._table = None
+
+    def write_lrs(self, it=None):
+        """Stage this step's learning rates (call between ``sp.begin()`` and ``sp.commit()``)."""
+        self._sp.set('lrs', torch.tensor(self.current_lrs(it), dtype=torch.float32))
+
     def step(self, it=None):
+        sp_view = getattr(self, '_sp_view', None)
         shadows = ops.shadow_list(self.params)      # bf16 weight copies the GEMMs read
         skey = tuple(0 if s is None else s.data_ptr() for s in shadows)
         if self._table is None or self._shadow_key != skey:
             dev = self.params[0].device
             self._table = ops.TensorTable([[p.data for p in self.params], [p.grad for p in self.params],
-                                           self.bufs, shadows], dev, lrs=self.current_lrs(it))
+                                           self.bufs, shadows], dev,
+                                          lrs=sp_view if sp_view is not None else self.current_lrs(it))
             self._table.targets = self.params
             self._shadow_key = skey
         ops.sgd_step(self._table, self.momentum, self.weight_decay, first_step=(self.steps == 0),
-                     lrs=self.current_lrs(it))
+                     lrs=None if sp_view is not None else self.current_lrs(it))
         for p in self.params:
             ops.bump_generation(p)                  # repacked conv weights are rebuilt lazily
         ops.mark_shadows_fresh(self.params)         # ... the bf16 shadows were refreshed in the same pass

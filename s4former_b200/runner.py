@@ -4,6 +4,8 @@ all-reduce -> ``optimizer.step()`` (mmcv ``OptimizerHook.after_train_iter`` + DD
 the poly LR schedule.  ``TrainStep`` is the call a user makes per iteration; everything it does
 on the device runs in the CUDA library.
 """
+from collections import OrderedDict
+
 import torch
 import torch.distributed as dist
 
@@ -13,7 +15,16 @@ from .parallel import GradReducer
 
 
 class TrainStep:
-    def __init__(self, model, optimizer_cfg=None, lr_cfg=None, max_iters=configs.MAX_ITERS):
+    """``cuda_graph=True``: after ``graph_warmup`` eager iterations the WHOLE step (EMA, teacher,
+    student passes, losses, backward, gradient all-reduce, SGD) is captured in one CUDA graph and
+    replayed; per-step host work shrinks to the augmentation RNG draws, one small parameter upload
+    (``ops.StepParams``) and one graph launch.  The eager path runs the very same device program
+    (same code, same parameter buffer), so a replay is bit-identical to the eager step it replaces
+    up to the order of fp32 atomics.  A batch whose shape / tag layout differs from the captured
+    one falls back to the eager path."""
+
+    def __init__(self, model, optimizer_cfg=None, lr_cfg=None, max_iters=configs.MAX_ITERS, cuda_graph=False,
+                 graph_warmup=3):
         ocfg = dict(configs.OPTIMIZER if optimizer_cfg is None else optimizer_cfg)
         lcfg = dict(configs.LR_CONFIG if lr_cfg is None else lr_cfg)
         assert ocfg.get('type', 'SGD') == 'SGD' and lcfg.get('policy', 'poly') == 'poly'
@@ -26,19 +37,106 @@ class TrainStep:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.reducer = GradReducer(model, self.optimizer.grads) if self.world > 1 else None
         self.device = next(model.parameters()).device
+        self.params = ops.StepParams(self.device, nbytes=max(1 << 16, 8 * len(self.optimizer.params) + (1 << 14)))
+        self.optimizer.attach_step_params(self.params)
+        self.cuda_graph, self.graph_warmup = bool(cuda_graph), int(graph_warmup)
+        self._graph = None
+        self._calls = 0
+        self.replays = 0
 
-    def __call__(self, img, img_metas, gt_semantic_seg, it, sync=True):
-        """Device-resident batch -> one optimisation step.  Returns ``(loss, log_vars)``; with
-        ``sync=False`` the log variables stay device tensors (no host synchronisation)."""
+    # ---- host side of a step: RNG draws (reference order) + learning rates -> one H2D copy ------
+    def _prepare(self, img, img_metas, it):
+        tags = [m['tag'] for m in img_metas]
+        n_unsup = sum(1 for t in tags if t == 'unsup_student')
+        draw = getattr(self.model, 'draw_aug_params', None)
+        aug = draw(n_unsup, int(img.shape[2]), int(img.shape[3])) if draw is not None else dict(cutmix=[], perms=None)
+        sp = self.params
+        sp.begin()
+        self.optimizer.write_lrs(it)
+        staged = dict(cutmix=[sp.set(f'cutmix{i}', b) for i, b in enumerate(aug['cutmix'])], next_cutmix=0,
+                      perms=aug['perms'], perms_dev=None)
+        if aug['perms'] is not None:
+            staged['perms_dev'] = sp.set('perms', aug['perms'])
+        sp.commit()
+        return staged
+
+    def _device_step(self, img, img_metas, gt_semantic_seg, it, staged):
+        """The device program of one step (eager, or under CUDA-graph capture)."""
         self.optimizer.zero_grad()
         ops.reset_arena()
         self.stale_pending = ops.reset_pending()      # 0 in a healthy step (see ops._pending_inc)
-        losses = self.model(img, img_metas, return_loss=True, gt_semantic_seg=gt_semantic_seg, iter=it)
+        self.model._step_aug = staged
+        try:
+            losses = self.model(img, img_metas, return_loss=True, gt_semantic_seg=gt_semantic_seg, iter=it)
+        finally:
+            self.model._step_aug = None
         loss, log_vars = self.model._parse_losses(losses, sync=False)
         loss.backward()
         if self.reducer is not None:
             self.reducer.finalize()
         self.optimizer.step(it)
+        return loss, log_vars
+
+    def _signature(self, img, img_metas, gt):
+        names = [m['filename'] for m in img_metas]
+        return (tuple(img.shape), tuple(gt.shape), img.dtype, tuple(m['tag'] for m in img_metas),
+                tuple(names.index(n) for n in names), self.model.training, ops.compute_dtype())
+
+    def _capture(self, img, img_metas, gt, it):
+        g = self.__dict__
+        g['_static_img'], g['_static_gt'] = torch.empty_like(img), torch.empty_like(gt)
+        self._static_img.copy_(img)
+        self._static_gt.copy_(gt)
+        staged = self._prepare(img, img_metas, it)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        steps0 = self.optimizer.steps
+        from . import _lib
+        l0 = _lib.load().s4_launch_count()
+        with torch.cuda.graph(graph):
+            loss, log_vars = self._device_step(self._static_img, [dict(m) for m in img_metas], self._static_gt,
+                                               it, staged)
+            packed = torch.stack([v.detach().float().reshape(()) for v in log_vars.values()])
+        self.graph_kernel_launches = int(_lib.load().s4_launch_count() - l0)   # library kernel nodes per replay
+        self.optimizer.steps = steps0          # capture launched nothing; the replay below is the step
+        self._graph = graph
+        self._graph_sig = self._signature(img, img_metas, gt)
+        self._graph_out = (loss, list(log_vars.keys()), packed)
+        self._graph_ntok = (tuple(img.shape), len(staged['cutmix']), staged['perms'] is not None)
+
+    def _replay(self, img, img_metas, gt, it, sync, prepared=None):
+        if img.data_ptr() != self._static_img.data_ptr():
+            self._static_img.copy_(img, non_blocking=True)
+            self._static_gt.copy_(gt, non_blocking=True)
+        staged = prepared if prepared is not None else self._prepare(img, img_metas, it)
+        if staged['perms'] is not None:      # the reference writes the permutation into the metas
+            st = [m for m in img_metas if m['tag'] == 'unsup_student']
+            for m, p in zip(st, staged['perms']):
+                m['PatchMixIndex'] = p
+                m['PatchMix_N'] = self.model.PatchMix_N
+        self._graph.replay()
+        self.replays += 1
+        self.optimizer.steps += 1
+        ops.bump_all_generations()             # weights changed behind the host-side caches
+        loss, keys, packed = self._graph_out
+        if sync:
+            return loss, OrderedDict(zip(keys, packed.tolist()))
+        return loss, OrderedDict(zip(keys, packed.unbind(0)))
+
+    def __call__(self, img, img_metas, gt_semantic_seg, it, sync=True):
+        """Device-resident batch -> one optimisation step.  Returns ``(loss, log_vars)``; with
+        ``sync=False`` the log variables stay device tensors (no host synchronisation)."""
+        self._calls += 1
+        if self.cuda_graph:
+            if self._graph is not None and self._signature(img, img_metas, gt_semantic_seg) == self._graph_sig:
+                return self._replay(img, img_metas, gt_semantic_seg, it, sync)
+            if self._graph is None and self._calls > self.graph_warmup:
+                self._capture(img, img_metas, gt_semantic_seg, it)
+                # the capture consumed this step's RNG draws and staged them: replay with those
+                staged = dict(cutmix=None, perms=None)
+                return self._replay(self._static_img, img_metas, self._static_gt, it, sync, prepared=staged)
+        staged = self._prepare(img, img_metas, it)
+        loss, log_vars = self._device_step(img, img_metas, gt_semantic_seg, it, staged)
         if sync:
             packed = torch.stack(list(log_vars.values())).tolist()     # one device->host copy
             log_vars = type(log_vars)(zip(log_vars.keys(), packed))

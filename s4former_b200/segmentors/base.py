@@ -82,17 +82,22 @@ class BaseSegmentor(nn.Module, metaclass=ABCMeta):
         names = list(log_vars.keys())
         packed = torch.stack([v.detach().float().reshape(()) for v in log_vars.values()])
         if dist.is_available() and dist.is_initialized():
-            n = torch.tensor([float(len(names))], device=packed.device)
-            packed = torch.cat([packed, n])
+            n = packed.new_full((1,), float(len(names)))     # (a fill, not a host->device copy:
+            packed = torch.cat([packed, n])                  #  the step may be under graph capture)
             dist.all_reduce(packed)
             ws = dist.get_world_size()
+            capturing = packed.is_cuda and torch.cuda.is_current_stream_capturing()
             # the reference's cross-rank key-count assertion (base.py:263).  Reading the count is a
             # device->host sync: with sync=False it is checked one call LATE (the value is long
             # since final by then), so the host keeps enqueueing instead of stalling mid-step
             check = (packed[-1], len(names) * ws, ','.join(names))
-            todo = [check] if sync else _pending_key_checks[:]
-            if not sync:
-                _pending_key_checks[:] = [check]
+            if capturing:       # no host read inside a capture; a replayed step has static keys
+                todo = []
+                _pending_key_checks[:] = []
+            else:
+                todo = [check] if sync else _pending_key_checks[:]
+                if not sync:
+                    _pending_key_checks[:] = [check]
             for cnt, want, nm in todo:
                 assert int(round(float(cnt))) == want, \
                     'loss log variables are different across GPUs!\n' + nm

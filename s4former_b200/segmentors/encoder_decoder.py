@@ -20,7 +20,8 @@ import torch.nn as nn
 
 from .. import builder, ops
 from ..builder import SEGMENTORS
-from ..utils.generate_unsup_data import generate_unsup_cutmix_data, generate_unsup_patchmix_data
+from ..utils.generate_unsup_data import (draw_patchmix_perms, generate_cutout_box, generate_unsup_cutmix_data,
+                                          generate_unsup_patchmix_data)
 from ..utils.structual_utils import add_prefix, dict_split, weighted_loss
 from .base import BaseSegmentor
 
@@ -100,6 +101,7 @@ class EncoderDecoder(BaseSegmentor):
         # PatchShuffle) as ONE batched pass (see _forward_train_batched).  False keeps the
         # reference's pass-by-pass order.
         self.batch_student_passes = True
+        self._step_aug = None        # pre-drawn augmentation parameters of the current step (TrainStep)
 
     # ------------------------------------------------------------------ construction (:164-246)
     def _init_ema_model(self, pretrained, backbone_ema, decode_head_ema):
@@ -250,7 +252,7 @@ class EncoderDecoder(BaseSegmentor):
             self.set_eval(self.ema)
             timg = teacher_data['img']
             if tidx != list(range(len(tidx))):
-                timg = timg[torch.tensor(tidx, device=timg.device)]
+                timg = timg[self._index_tensor(tidx, timg.device)]
             tmetas = [teacher_data['img_metas'][idx] for idx in tidx]
             teacher_info = self.extract_teacher_info_ema(timg, tmetas)
             self.set_train(self.ema)
@@ -260,11 +262,8 @@ class EncoderDecoder(BaseSegmentor):
         pasa_student = dict(student_info, img_metas=[dict(m) for m in student_info['img_metas']])
         pasa_teacher = dict(teacher_info)
         # ---- strong augmentation of the third pass (:633-638); host RNG order as the reference ----
-        if np.random.uniform(0, 1) < self.strong_aug_prob:
-            teacher_info, student_info = generate_unsup_cutmix_data(
-                teacher_info, student_info, ratio=self.cutout_area, patchwise=False)
-        student_info, teacher_info = generate_unsup_patchmix_data(
-            student_info, teacher_info, PatchMix_N=self.PatchMix_N, patchmix_ratio=self.patchmix_ratio)
+        teacher_info, student_info = self._cutmix(teacher_info, student_info)
+        student_info, teacher_info = self._patchmix(student_info, teacher_info)
         # ---- one backbone pass ----
         ns, nu = sup_imgs.shape[0], student_info['img'].shape[0]
         imgs = torch.cat([sup_imgs, pasa_student['img'], student_info['img']], 0)
@@ -300,7 +299,7 @@ class EncoderDecoder(BaseSegmentor):
             self.set_eval(self.ema)
             timg = teacher_data['img']
             if tidx != list(range(len(tidx))):
-                timg = timg[torch.tensor(tidx, device=timg.device)]
+                timg = timg[self._index_tensor(tidx, timg.device)]
             tmetas = [teacher_data['img_metas'][idx] for idx in tidx]
             if not self.ema:
                 teacher_info = self.extract_teacher_info(timg, tmetas)
@@ -321,17 +320,11 @@ class EncoderDecoder(BaseSegmentor):
                 self.compute_pseudo_loss(student_info, teacher_info, want_ncr=False)['loss_seg_unsup'] * 0.5
 
         if self.use_CutMix:
-            if np.random.uniform(0, 1) < self.strong_aug_prob:
-                teacher_info, student_info = generate_unsup_cutmix_data(
-                    teacher_info, student_info, ratio=self.cutout_area, patchwise=False)
+            teacher_info, student_info = self._cutmix(teacher_info, student_info)
 
         if self.use_PatchShuffle_w_Cutmix:
-            if np.random.uniform(0, 1) < self.strong_aug_prob:
-                teacher_info, student_info = generate_unsup_cutmix_data(
-                    teacher_info, student_info, ratio=self.cutout_area, patchwise=False)
-            student_info, teacher_info = generate_unsup_patchmix_data(
-                student_info, teacher_info, PatchMix_N=self.PatchMix_N,
-                patchmix_ratio=self.patchmix_ratio)
+            teacher_info, student_info = self._cutmix(teacher_info, student_info)
+            student_info, teacher_info = self._patchmix(student_info, teacher_info)
 
         if not self.attn_mask_seperate_head:
             # Mean-Teacher config as shipped (:650-670): a PASA student pass whose features feed
@@ -354,6 +347,61 @@ class EncoderDecoder(BaseSegmentor):
                 loss_unsup['loss_ncr_unsup'] = losses['loss_ncr_unsup'] * 0.5
             loss_unsup['loss_seg_unsup'] = losses['loss_seg_unsup'] * self.fdrop_loss_weight
         return loss_unsup
+
+    # ------------------------------------------------------------------ strong augmentation
+    def draw_aug_params(self, n_unsup, height, width):
+        """ALL host RNG draws of one step, up front and in the reference's call order
+        (encoder_decoder.py:604-607 CutMix, :633-638 CutMix + PatchShuffle; generate_unsup_data.py
+        :7-26 three ``np.random.randint`` per box, :737-819 ``np.random.rand`` then
+        ``torch.randperm`` per image).  A CutMix the coin rejects becomes all-zero boxes (the kernel
+        then copies the images unchanged), so the step's device program is the same either way.
+        Returns dict(cutmix=[int32 [n,4] ...], perms=int64 [n,num] or None) of CPU tensors."""
+        out = dict(cutmix=[], perms=None)
+        if n_unsup == 0 or self.unsup_weight == 0:
+            return out
+
+        def one_cutmix():
+            if np.random.uniform(0, 1) < self.strong_aug_prob:
+                boxes = [generate_cutout_box([height, width], ratio=self.cutout_area) for _ in range(n_unsup)]
+            else:
+                boxes = [(0, 0, 0, 0)] * n_unsup
+            out['cutmix'].append(torch.tensor(boxes, dtype=torch.int32).reshape(n_unsup, 4))
+        if self.use_CutMix:
+            one_cutmix()
+        if self.use_PatchShuffle_w_Cutmix:
+            one_cutmix()
+            out['perms'] = draw_patchmix_perms(n_unsup, height, width, self.patchmix_ratio, 16, self.PatchMix_N)
+        return out
+
+    def _cutmix(self, teacher_info, student_info):
+        pre = self._step_aug
+        if pre is not None:       # pre-drawn (resident) boxes: no host decision inside the step
+            boxes = pre['cutmix'][pre['next_cutmix']]
+            pre['next_cutmix'] += 1
+            return generate_unsup_cutmix_data(teacher_info, student_info, ratio=self.cutout_area,
+                                              patchwise=False, boxes=boxes)
+        if np.random.uniform(0, 1) < self.strong_aug_prob:
+            return generate_unsup_cutmix_data(teacher_info, student_info, ratio=self.cutout_area, patchwise=False)
+        return teacher_info, student_info
+
+    def _patchmix(self, student_info, teacher_info):
+        pre = self._step_aug
+        if pre is not None:
+            return generate_unsup_patchmix_data(student_info, teacher_info, PatchMix_N=self.PatchMix_N,
+                                                patchmix_ratio=self.patchmix_ratio, perms=pre['perms'],
+                                                perms_dev=pre['perms_dev'])
+        return generate_unsup_patchmix_data(student_info, teacher_info, PatchMix_N=self.PatchMix_N,
+                                            patchmix_ratio=self.patchmix_ratio)
+
+    def _index_tensor(self, idx, device):
+        """Cached device copy of a host index list (no per-step host->device copy)."""
+        cache = self.__dict__.setdefault('_s4_index_cache', {})
+        key = (tuple(idx), str(device))
+        t = cache.get(key)
+        if t is None:
+            t = torch.tensor(idx, device=device)
+            cache[key] = t
+        return t
 
     def _patch_unconfidence(self, teacher_info, student_info):
         """(:547-555) u = mean over each patch of (1 - conf); produced by the pseudo-label kernel."""
