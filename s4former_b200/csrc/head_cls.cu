@@ -156,11 +156,11 @@ __device__ __forceinline__ int grp_channel(int nt, int j) {
   return idx < 8 ? 8 * tt + idx : 32 + 8 * tt + (idx - 8);
 }
 
-// v2: gamma*invstd is folded into the B fragments (W[j,c] * A[c] before the bf16 rounding), so
-//   dy = mask * (dz @ (W A)) - y * (A E) - A F
-// needs ONE float4 of per-channel constants (scale, shift, A E, A F); a warp iteration covers
-// RB 16-row blocks so each constant load serves 2 RB outputs (v1: short-scoreboard stalls of 18
-// cycles per issue on three smem loads per output pair).
+// v2: a warp iteration covers RB 16-row blocks so each per-channel constant load serves 2 RB
+// outputs (v1: short-scoreboard stalls of 18 cycles per issue on three smem loads per output pair).
+// (Folding gamma*invstd into the bf16 B fragments saves one more load but makes the recomputed
+// da differ from the one cls_bwd_reduce summed; after BatchNorm's mean / xhat projection that
+// inconsistency showed up as +45 % gradient error on the stage's conv weight -- not done.)
 template <int GROUPS, int RB>   // C = 64 * GROUPS
 __global__ void __launch_bounds__(256)
 cls_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz16, const __nv_bfloat16* __restrict__ y,
@@ -171,21 +171,21 @@ cls_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz16, const __nv_bfloat16
                      __nv_bfloat16* __restrict__ dy, long long rows, int NC) {
   constexpr int C = 64 * GROUPS;
   extern __shared__ __align__(16) uint8_t smem[];
-  float4* t1 = reinterpret_cast<float4*>(smem);                       // [C] scale, shift, A*E, A*F
-  uint2* bfr = reinterpret_cast<uint2*>(smem + C * sizeof(float4));   // [GROUPS][8][2][32]
+  float4* t1 = reinterpret_cast<float4*>(smem);                       // [C] scale, shift, E, F
+  float* t2 = reinterpret_cast<float*>(smem + C * sizeof(float4));    // [C] A = gamma * invstd
+  uint2* bfr = reinterpret_cast<uint2*>(smem + C * (sizeof(float4) + sizeof(float)));   // [GROUPS][8][2][32]
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float is = invstd[c];
-    const float A = gamma[c] * is;
     const float E = is * ddot[c] * inv_n;                    // xhat*ddot/n = (y - mean) * E
     const float F = dsum[c] * inv_n - mean[c] * E;
-    t1[c] = make_float4(scale[c], shift[c], A * E, A * F);
+    t1[c] = make_float4(scale[c], shift[c], E, F);
+    t2[c] = gamma[c] * is;
   }
   for (int i = threadIdx.x; i < GROUPS * 8 * 2 * 32; i += blockDim.x) {
     const int ln = i & 31, ks = (i >> 5) & 1, nt = (i >> 6) & 7, gq = i >> 9;
     const int ch = 64 * gq + grp_channel(nt, ln >> 2);
     const int k = 16 * ks + 2 * (ln & 3);
-    const float A = gamma[ch] * invstd[ch];
-    auto wv = [&](int kk) { return kk < NC ? w[(size_t)kk * C + ch] * A : 0.f; };
+    auto wv = [&](int kk) { return kk < NC ? w[(size_t)kk * C + ch] : 0.f; };
     bfr[i] = make_uint2(pack2(wv(k), wv(k + 1)), pack2(wv(k + 8), wv(k + 9)));
   }
   __syncthreads();
@@ -246,6 +246,8 @@ cls_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz16, const __nv_bfloat16
           const int nt = 4 * hc + q;
           const int ch = cb + 32 * hc + 8 * t + 2 * q;
           const float4 k0 = t1[ch], k1 = t1[ch + 1];
+          const float2 A01 = *reinterpret_cast<const float2*>(t2 + ch);
+          const float A0 = A01.x, A1 = A01.y;
 #pragma unroll
           for (int rb = 0; rb < RB; ++rb) {
             const uint32_t wa = (&yv[rb][0][hc].x)[q], wb = (&yv[rb][1][hc].x)[q];
@@ -254,8 +256,8 @@ cls_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz16, const __nv_bfloat16
             const float da01 = fmaf(va.y, k1.x, k1.y) > 0.f ? acc[rb][nt][1] : 0.f;
             const float da10 = fmaf(vb.x, k0.x, k0.y) > 0.f ? acc[rb][nt][2] : 0.f;
             const float da11 = fmaf(vb.y, k1.x, k1.y) > 0.f ? acc[rb][nt][3] : 0.f;
-            oo[rb][0][q] = pack2(da00 - fmaf(va.x, k0.z, k0.w), da01 - fmaf(va.y, k1.z, k1.w));
-            oo[rb][1][q] = pack2(da10 - fmaf(vb.x, k0.z, k0.w), da11 - fmaf(vb.y, k1.z, k1.w));
+            oo[rb][0][q] = pack2(A0 * (da00 - fmaf(va.x, k0.z, k0.w)), A1 * (da01 - fmaf(va.y, k1.z, k1.w)));
+            oo[rb][1][q] = pack2(A0 * (da10 - fmaf(vb.x, k0.z, k0.w)), A1 * (da11 - fmaf(vb.y, k1.z, k1.w)));
           }
         }
 #pragma unroll
@@ -726,7 +728,7 @@ int s4_cls_bwd_apply_tc(const void* dz16, const void* y, const float* scale, con
                         const float* mean, const float* invstd, const float* gamma, const float* w,
                         const float* dsum, const float* ddot, double count, void* dy, long long rows,
                         int C, int NC, cudaStream_t st) {
-  const size_t smem = (size_t)C * 16 + (size_t)(C / 64) * 8 * 2 * 32 * 8;
+  const size_t smem = (size_t)C * 20 + (size_t)(C / 64) * 8 * 2 * 32 * 8;
   const int grid = (int)std::min<long long>((rows + 255) / 256, (long long)s4_num_sms() * 4);
   const float inv_n = (float)(1.0 / count);
   int rc;

@@ -75,7 +75,9 @@ class TrainStep:
         if self.reducer is not None:
             self.reducer.finalize()
         self.optimizer.step(it)
-        return loss, log_vars
+        # (detached: the step is complete, nothing differentiates through the returned loss; a
+        # caller holding the previous step's autograd graph alive broke the next capture)
+        return loss.detach(), log_vars
 
     def _signature(self, img, img_metas, gt):
         names = [m['filename'] for m in img_metas]
@@ -93,13 +95,28 @@ class TrainStep:
         steps0 = self.optimizer.steps
         from . import _lib
         l0 = _lib.load().s4_launch_count()
-        with torch.cuda.graph(graph):
-            loss, log_vars = self._device_step(self._static_img, [dict(m) for m in img_metas], self._static_gt,
-                                               it, staged)
-            packed = torch.stack([v.detach().float().reshape(()) for v in log_vars.values()])
+        # No garbage collection while capturing: a collection may free pinned staging buffers /
+        # events of an older TrainStep, and the host allocator's event queries invalidate a
+        # capture in progress (cudaErrorStreamCaptureInvalidated).
+        import gc
+        gc.collect()
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            # 'thread_local': backward runs on autograd's device thread, whose allocations may have
+            # to grow the graph's private pool (cudaMalloc) -- legal, but a capture in the default
+            # 'global' mode is invalidated by such a call from any other thread
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                loss, log_vars = self._device_step(self._static_img, [dict(m) for m in img_metas],
+                                                   self._static_gt, it, staged)
+                packed = torch.stack([v.detach().float().reshape(()) for v in log_vars.values()])
+        finally:
+            if gc_was_enabled:
+                gc.enable()
         self.graph_kernel_launches = int(_lib.load().s4_launch_count() - l0)   # library kernel nodes per replay
         self.optimizer.steps = steps0          # capture launched nothing; the replay below is the step
         self._graph = graph
+        self._capture_staged = staged
         self._graph_sig = self._signature(img, img_metas, gt)
         self._graph_out = (loss, list(log_vars.keys()), packed)
         self._graph_ntok = (tuple(img.shape), len(staged['cutmix']), staged['perms'] is not None)
@@ -133,8 +150,8 @@ class TrainStep:
             if self._graph is None and self._calls > self.graph_warmup:
                 self._capture(img, img_metas, gt_semantic_seg, it)
                 # the capture consumed this step's RNG draws and staged them: replay with those
-                staged = dict(cutmix=None, perms=None)
-                return self._replay(self._static_img, img_metas, self._static_gt, it, sync, prepared=staged)
+                return self._replay(self._static_img, img_metas, self._static_gt, it, sync,
+                                    prepared=self._capture_staged)
         staged = self._prepare(img, img_metas, it)
         loss, log_vars = self._device_step(img, img_metas, gt_semantic_seg, it, staged)
         if sync:
