@@ -381,9 +381,23 @@ def main():
                               launches_per_step=n.value / nprof))
         lib.s4_prof_enable(0)
 
-    if rank != 0:
+    def teardown():
+        """Captured NCCL collectives keep the communicator busy: destroying the process group
+        with a live CUDA graph hung the N > 1 run at exit.  Drop the graph, drain, and leave
+        without the collective teardown."""
+        step._graph = None
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            if _REAL_STDOUT is not None:
+                _REAL_STDOUT.flush()
+            os._exit(0)
+
+    if rank != 0:
+        teardown()
         return
 
     peaks = {}
@@ -444,8 +458,7 @@ def main():
             sample=f'{s_sup} labeled + {s_unsup} unlabeled {a.size}x{a.size} crops, one oracle step '
                    f'({csec:.1f} s), scaled by 1/{a.sup} to the {a.sup}L+{a.unsup}U step')
     emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 if __name__ == '__main__':
