@@ -276,6 +276,15 @@ int s4_sgd_multi_tensor(void* const* params, void* const* grads, void* const* bu
                         void* const* bf16_shadow, const long long* sizes, const float* lrs,
                         const int* chunk_tensor, const long long* chunk_off, int n_chunks,
                         float momentum, float weight_decay, int first_step, cudaStream_t stream);
+/* SGD-momentum step fused with the EMA-teacher update of the same parameters (SURVEY.md section
+ * 8(f) rank 1: mmcv SGD + encoder_decoder.py:416-423, 1044-1066 in one sweep).  ema_params[i] may
+ * be NULL (parameter without a teacher copy); ema_momentum[i] is that tensor's EMA momentum. */
+int s4_sgd_ema_multi_tensor(void* const* params, void* const* grads, void* const* bufs,
+                            void* const* bf16_shadow, void* const* ema_params,
+                            void* const* ema_bf16_shadow, const float* ema_momentum,
+                            const long long* sizes, const float* lrs, const int* chunk_tensor,
+                            const long long* chunk_off, int n_chunks, float momentum,
+                            float weight_decay, int first_step, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

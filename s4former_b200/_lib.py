@@ -87,6 +87,7 @@ _SPEC = {
     's4_chunk_elems': (_I, []),
     's4_ema_multi_tensor': (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _P]),
     's4_sgd_multi_tensor': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P]),
+    's4_sgd_ema_multi_tensor': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SPEC)

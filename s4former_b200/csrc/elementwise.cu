@@ -484,6 +484,93 @@ extern "C" int s4_sgd_multi_tensor(void* const* params, void* const* grads, void
   return s4_check_launch("sgd_multi_tensor");
 }
 
+// SGD-momentum step AND the EMA-teacher update in ONE sweep.
+// The reference runs update_ema_variables at the START of step t+1 on the weights SGD wrote at
+// step t (encoder_decoder.py:416-423, 1044-1066): applying t <- m t + (1-m) s right after the SGD
+// write of s is the same arithmetic on the same values, one step earlier in program order and
+// with nothing reading the teacher in between.  Reads grad / momentum / weight / teacher once:
+// 4+4+4+4 B read, 4+4+4 B written (+2+2 B bf16 shadows) per parameter instead of two sweeps.
+// ema[ti] == null: a parameter without a teacher copy (auxiliary heads).
+__global__ void __launch_bounds__(256)
+sgd_ema_multi_kernel(S4TensorTable t, void* const* shadow, void* const* ema, void* const* ema_shadow,
+                     const float* __restrict__ ema_m, float mu, float wd, int first_step) {
+  const int ti = t.chunk_tensor[blockIdx.x];
+  const long long off = t.chunk_off[blockIdx.x];
+  const long long n = min((long long)S4_CHUNK, t.size[ti] - off);
+  float* p = (float*)t.a[ti] + off;
+  const float* g = (const float*)t.b[ti] + off;
+  float* buf = (float*)t.c[ti] + off;
+  __nv_bfloat16* sh = (shadow && shadow[ti]) ? (__nv_bfloat16*)shadow[ti] + off : nullptr;
+  float* e = ema[ti] ? (float*)ema[ti] + off : nullptr;
+  __nv_bfloat16* esh = (e && ema_shadow && ema_shadow[ti]) ? (__nv_bfloat16*)ema_shadow[ti] + off : nullptr;
+  const float lr = t.scalar[ti];
+  const float m = e ? ema_m[ti] : 0.f, om = 1.f - m;
+  auto upd = [&](float gi, float& pi, float& bi) {
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    bi = first_step ? gi : fmaf(mu, bi, gi);
+    pi = fmaf(-lr, bi, pi);
+  };
+  auto pack4 = [](const float4& v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    return o;
+  };
+  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)buf) | ((uintptr_t)e)) & 15) == 0 &&
+                   ((((uintptr_t)sh) | ((uintptr_t)esh)) & 7) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 bv = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(buf)[i];
+    float4 ev = e ? reinterpret_cast<float4*>(e)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    upd(gv.x, pv.x, bv.x);
+    upd(gv.y, pv.y, bv.y);
+    upd(gv.z, pv.z, bv.z);
+    upd(gv.w, pv.w, bv.w);
+    reinterpret_cast<float4*>(buf)[i] = bv;
+    reinterpret_cast<float4*>(p)[i] = pv;
+    if (sh) reinterpret_cast<uint2*>(sh)[i] = pack4(pv);
+    if (e) {
+      ev.x = fmaf(pv.x, om, ev.x * m);
+      ev.y = fmaf(pv.y, om, ev.y * m);
+      ev.z = fmaf(pv.z, om, ev.z * m);
+      ev.w = fmaf(pv.w, om, ev.w * m);
+      reinterpret_cast<float4*>(e)[i] = ev;
+      if (esh) reinterpret_cast<uint2*>(esh)[i] = pack4(ev);
+    }
+  }
+  for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+    float pi = p[i];
+    float bi = first_step ? 0.f : buf[i];
+    upd(g[i], pi, bi);
+    buf[i] = bi;
+    p[i] = pi;
+    if (sh) sh[i] = __float2bfloat16_rn(pi);
+    if (e) {
+      const float ei = fmaf(pi, om, e[i] * m);
+      e[i] = ei;
+      if (esh) esh[i] = __float2bfloat16_rn(ei);
+    }
+  }
+}
+
+extern "C" int s4_sgd_ema_multi_tensor(void* const* params, void* const* grads, void* const* bufs,
+                                       void* const* bf16_shadow, void* const* ema_params,
+                                       void* const* ema_bf16_shadow, const float* ema_momentum,
+                                       const long long* sizes, const float* lrs, const int* chunk_tensor,
+                                       const long long* chunk_off, int n_chunks, float momentum,
+                                       float weight_decay, int first_step, cudaStream_t stream) {
+  S4ProfScope prof_("sgd_ema_multi_tensor", 0.0, 1, stream);
+  if (n_chunks == 0) return S4_OK;
+  S4_REQUIRE(ema_params != nullptr && ema_momentum != nullptr, "sgd_ema: null EMA table");
+  S4TensorTable t{params, grads, bufs, sizes, lrs, chunk_tensor, chunk_off};
+  sgd_ema_multi_kernel<<<n_chunks, 256, 0, stream>>>(t, bf16_shadow, ema_params, ema_bf16_shadow, ema_momentum,
+                                                     momentum, weight_decay, first_step);
+  return s4_check_launch("sgd_ema_multi_tensor");
+}
+
 extern "C" int s4_chunk_elems() { return S4_CHUNK; }
 
 // ------------------------------------------------------------------------------------------

@@ -138,7 +138,7 @@ def lowp(p):
 
 def shadow_list(params):
     """bf16 shadow buffers (or None) of ``params``, for the multi-tensor kernels."""
-    return [getattr(p, '_s4_shadow', None) for p in params]
+    return [None if p is None else getattr(p, '_s4_shadow', None) for p in params]
 
 
 def mark_shadows_fresh(params):
@@ -919,3 +919,20 @@ def sgd_step(table, momentum, weight_decay, first_step, lrs=None):
            float(momentum), float(weight_decay), int(first_step), _st())
     for t in table.keep[0]:
         bump_generation(t)
+
+
+def sgd_ema_step(table, momentum, weight_decay, first_step, lrs=None):
+    """SGD-momentum + EMA-teacher update in one sweep (``s4_sgd_ema_multi_tensor``).  Table lists:
+    [params, grads, momentum buffers, bf16 shadows, ema params, ema bf16 shadows]; ``table.ema_m``
+    holds the per-tensor EMA momentum."""
+    if lrs is not None:
+        table.lrs.copy_(torch.tensor(lrs, dtype=torch.float32), non_blocking=True)
+    L.call('s4_sgd_ema_multi_tensor', _p(table.ptrs[0]), _p(table.ptrs[1]), _p(table.ptrs[2]), _p(table.ptrs[3]),
+           _p(table.ptrs[4]), _p(table.ptrs[5]), _p(table.ema_m), _p(table.sizes), _p(table.lrs),
+           _p(table.chunk_tensor), _p(table.chunk_off), table.n_chunks, float(momentum), float(weight_decay),
+           int(first_step), _st())
+    for t in table.keep[0]:
+        bump_generation(t)
+    for t in table.keep[4]:
+        if t is not None:
+            bump_generation(t)

@@ -87,20 +87,39 @@ class FusedSGD:
         """Stage this step's learning rates (call between ``sp.begin()`` and ``sp.commit()``)."""
         self._sp.set('lrs', torch.tensor(self.current_lrs(it), dtype=torch.float32))
 
+    def attach_ema(self, pairs):
+        """``pairs``: {id(student_param): (teacher_param, ema_momentum)}.  From now on ``step``
+        also applies teacher <- m teacher + (1-m) student for those parameters in the SAME sweep
+        (the reference does it at the start of the next iteration on exactly these values:
+        encoder_decoder.py:416-423, 1044-1066)."""
+        self._ema_pairs = dict(pairs)
+        self._table = None
+
     def step(self, it=None):
         sp_view = getattr(self, '_sp_view', None)
+        pairs = getattr(self, '_ema_pairs', None)
         shadows = ops.shadow_list(self.params)      # bf16 weight copies the GEMMs read
-        skey = tuple(0 if s is None else s.data_ptr() for s in shadows)
+        ema = [pairs.get(id(p), (None, 0.0))[0] for p in self.params] if pairs else None
+        ema_sh = ops.shadow_list([e for e in ema]) if pairs else []
+        skey = tuple(0 if s is None else s.data_ptr() for s in list(shadows) + list(ema_sh))
         if self._table is None or self._shadow_key != skey:
             dev = self.params[0].device
-            self._table = ops.TensorTable([[p.data for p in self.params], [p.grad for p in self.params],
-                                           self.bufs, shadows], dev,
-                                          lrs=sp_view if sp_view is not None else self.current_lrs(it))
+            lists = [[p.data for p in self.params], [p.grad for p in self.params], self.bufs, shadows]
+            if pairs:
+                lists += [[None if e is None else e.data for e in ema], ema_sh]
+            self._table = ops.TensorTable(lists, dev, lrs=sp_view if sp_view is not None else self.current_lrs(it))
             self._table.targets = self.params
+            if pairs:
+                self._table.ema_m = torch.tensor([pairs.get(id(p), (None, 0.0))[1] for p in self.params],
+                                                 dtype=torch.float32).to(dev)
+                self._ema_targets = [e for e in ema if e is not None]
             self._shadow_key = skey
-        ops.sgd_step(self._table, self.momentum, self.weight_decay, first_step=(self.steps == 0),
-                     lrs=None if sp_view is not None else self.current_lrs(it))
+        fn = ops.sgd_ema_step if pairs else ops.sgd_step
+        fn(self._table, self.momentum, self.weight_decay, first_step=(self.steps == 0),
+           lrs=None if sp_view is not None else self.current_lrs(it))
         for p in self.params:
             ops.bump_generation(p)                  # repacked conv weights are rebuilt lazily
         ops.mark_shadows_fresh(self.params)         # ... the bf16 shadows were refreshed in the same pass
+        if pairs:
+            ops.mark_shadows_fresh(self._ema_targets)
         self.steps += 1

@@ -24,7 +24,7 @@ class TrainStep:
     one falls back to the eager path."""
 
     def __init__(self, model, optimizer_cfg=None, lr_cfg=None, max_iters=configs.MAX_ITERS, cuda_graph=False,
-                 graph_warmup=3):
+                 graph_warmup=3, fused_ema=True):
         ocfg = dict(configs.OPTIMIZER if optimizer_cfg is None else optimizer_cfg)
         lcfg = dict(configs.LR_CONFIG if lr_cfg is None else lr_cfg)
         assert ocfg.get('type', 'SGD') == 'SGD' and lcfg.get('policy', 'poly') == 'poly'
@@ -39,6 +39,11 @@ class TrainStep:
         self.device = next(model.parameters()).device
         self.params = ops.StepParams(self.device, nbytes=max(1 << 16, 8 * len(self.optimizer.params) + (1 << 14)))
         self.optimizer.attach_step_params(self.params)
+        # f1: the EMA-teacher update rides in the SGD sweep (one pass over grad / momentum / weight
+        # / teacher); the model then only EMAs its BatchNorm buffers at the start of a step
+        self.fused_ema = bool(fused_ema) and bool(getattr(model, 'ema', False)) and hasattr(model, 'ema_pairs')
+        if self.fused_ema:
+            self.optimizer.attach_ema(model.ema_pairs())
         self.cuda_graph, self.graph_warmup = bool(cuda_graph), int(graph_warmup)
         self._graph = None
         self._calls = 0
@@ -75,6 +80,8 @@ class TrainStep:
         if self.reducer is not None:
             self.reducer.finalize()
         self.optimizer.step(it)
+        if self.fused_ema:
+            self.model._ema_fused_primed = True     # the next forward_train skips the parameter EMA
         # (detached: the step is complete, nothing differentiates through the returned loss; a
         # caller holding the previous step's autograd graph alive broke the next capture)
         return loss.detach(), log_vars

@@ -178,9 +178,15 @@ class EncoderDecoder(BaseSegmentor):
 
         self.losses = dict()
         if self.ema:
+            # ``_ema_fused_primed``: the optimizer applied this EMA to every parameter in the same
+            # sweep as the previous SGD step (optim.FusedSGD.attach_ema) -- only the BatchNorm
+            # running statistics (buffers, not optimizer state) are left to do here.
+            params_done = bool(getattr(self, '_ema_fused_primed', False))
             with torch.no_grad():
-                self.update_ema_variables(self.backbone, self.backbone_ema, self.momentum_backbone)
-                self.update_ema_variables(self.decode_head, self.decode_head_ema, self.momentum_head)
+                self.update_ema_variables(self.backbone, self.backbone_ema, self.momentum_backbone,
+                                          buffers_only=params_done)
+                self.update_ema_variables(self.decode_head, self.decode_head_ema, self.momentum_head,
+                                          buffers_only=params_done)
 
         if self._can_batch_student_passes(data_groups, current_iter):
             self.losses.update(self._forward_train_batched(data_groups))
@@ -277,15 +283,20 @@ class EncoderDecoder(BaseSegmentor):
         if self.with_auxiliary_head:
             losses.update(self._auxiliary_head_forward_train(labeled_features, sup['img_metas'], sup_gts))
         losses.update(loss_decode_sup)
+        # The branch weights (0.5 / fdrop_loss_weight, :567, :684-685) and unsup_weight
+        # (weighted_loss, :488-512) are handed to the loss kernel, so the upstream gradient of every
+        # term is 1 and the fused forward+gradient launch needs no rescale pass over dz.
+        w = float(self.unsup_weight)
         pasa_student['backbone_feature'] = self._feature_group(feats, ns, nu)
         loss_unsup['loss_seg_unsup_attn_mask'] = \
-            self.compute_pseudo_loss(pasa_student, pasa_teacher, want_ncr=False)['loss_seg_unsup'] * 0.5
+            self.compute_pseudo_loss(pasa_student, pasa_teacher, want_ncr=False, ce_scale=0.5 * w)['loss_seg_unsup']
         student_info['backbone_feature'] = self._feature_group(feats, ns + nu, nu)
-        mixed = self.compute_pseudo_loss(student_info, teacher_info)
+        mixed = self.compute_pseudo_loss(student_info, teacher_info, ce_scale=self.fdrop_loss_weight * w,
+                                         ncr_scale=0.5 * w)
         if self.negative_class_ranking:
-            loss_unsup['loss_ncr_unsup'] = mixed['loss_ncr_unsup'] * 0.5
-        loss_unsup['loss_seg_unsup'] = mixed['loss_seg_unsup'] * self.fdrop_loss_weight
-        losses.update(weighted_loss(loss_unsup, weight=self.unsup_weight))
+            loss_unsup['loss_ncr_unsup'] = mixed['loss_ncr_unsup']
+        loss_unsup['loss_seg_unsup'] = mixed['loss_seg_unsup']
+        losses.update(loss_unsup)
         return losses
 
     # ------------------------------------------------------------------ unsup branch (:516-687)
@@ -438,9 +449,10 @@ class EncoderDecoder(BaseSegmentor):
         return dict(backbone_feature=feat, seg_logits=seg_logits, hard_seg_label=hard, conf_mask=conf,
                     patch_unconf=u, img_metas=img_metas)
 
-    def compute_pseudo_loss(self, student_info, teacher_info, want_ncr=True):
+    def compute_pseudo_loss(self, student_info, teacher_info, want_ncr=True, ce_scale=1.0, ncr_scale=1.0):
         """(:906-954) masked CE (mean over ALL pixels) and, in 'unsup_only' mode, NCR.
-        ``want_ncr=False`` skips the NCR value the reference computes and discards (:567)."""
+        ``want_ncr=False`` skips the NCR value the reference computes and discards (:567);
+        ``ce_scale`` / ``ncr_scale`` multiply the two terms inside the kernel."""
         loss_unsup = {}
         students_prediction = self.decode_head.forward_get_logits(
             student_info['backbone_feature'], self.train_cfg, student_info['img_metas'])
@@ -448,24 +460,39 @@ class EncoderDecoder(BaseSegmentor):
             self.negative_class_ranking_mode in ('unsup_only', 'both')
         zt = teacher_info['seg_logits'] if ncr else None
         loss_ce, loss_ncr, _ = ops.CeNcrFn.apply(students_prediction, zt, teacher_info['hard_seg_label'],
-                                                 1.0, 1.0 if ncr else 0.0, 255)
+                                                 float(ce_scale), float(ncr_scale) if ncr else 0.0, 255)
         loss_unsup['loss_seg_unsup'] = loss_ce
         if ncr:
             loss_unsup['loss_ncr_unsup'] = loss_ncr
         return loss_unsup
 
     # ------------------------------------------------------------------ EMA (:1044-1066)
-    def update_ema_variables(self, model, ema_model, momentum=0.999, dropout=0.0, attn_frozen=False):
+    def ema_pairs(self):
+        """{id(student parameter): (teacher parameter, momentum)} in the reference's pairing order
+        (zip of named_parameters(), encoder_decoder.py:1049-1051) for the fused SGD + EMA sweep."""
+        out = {}
+        if not self.ema:
+            return out
+        for model, ema_model, m in ((self.backbone, self.backbone_ema, self.momentum_backbone),
+                                    (self.decode_head, self.decode_head_ema, self.momentum_head)):
+            for (_, sp_), (_, tp) in zip(model.named_parameters(), ema_model.named_parameters()):
+                out[id(sp_)] = (tp, float(m))
+        return out
+
+    def update_ema_variables(self, model, ema_model, momentum=0.999, dropout=0.0, attn_frozen=False,
+                             buffers_only=False):
         if dropout != 0 or attn_frozen:
             raise NotImplementedError('EMA dropout / attn_frozen are not used by the shipped configs')
-        key = (id(model), id(ema_model))
+        key = (id(model), id(ema_model), bool(buffers_only))
         table = self._ema_tables.get(key)
-        src = [p for _, p in model.named_parameters()]
-        dst = [p for _, p in ema_model.named_parameters()]
+        src = [] if buffers_only else [p for _, p in model.named_parameters()]
+        dst = [] if buffers_only else [p for _, p in ema_model.named_parameters()]
         for (sn, sb), (_, tb) in zip(model.named_buffers(), ema_model.named_buffers()):
             if 'bn' in sn and 'num_batches_tracked' not in sn:
                 src.append(sb)
                 dst.append(tb)
+        if not dst:
+            return
         shadows = ops.shadow_list(dst)      # bf16 copies of the teacher weights, refreshed in the same pass
         ptr_key = tuple(t.data_ptr() for t in dst) + tuple(t.data_ptr() for t in src) + \
             tuple(0 if s is None else s.data_ptr() for s in shadows)

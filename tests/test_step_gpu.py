@@ -286,3 +286,76 @@ def test_cuda_graph_replay_equals_eager_steps(variant):
         assert len(x) == len(y) and all(torch.equal(p, q) for p, q in zip(x, y))
     for k in wa:
         assert float((wa[k] - wb[k]).norm()) <= 2e-3 * float(wa[k].norm()) + 1e-6, k
+
+
+def test_fused_sgd_ema_sweep_equals_separate_updates():
+    """f1: TrainStep(fused_ema=True) applies the EMA-teacher update
+    inside the SGD sweep of the SAME step; the reference does it at the start of the next
+    iteration (encoder_decoder.py:416-423) on the same weights.  After n steps + the (n+1)-th
+    step's EMA, student, teacher and BatchNorm statistics of both schedules must agree."""
+    import copy as _copy
+    from s4former_b200.runner import TrainStep
+
+    def run(fused):
+        m, _ = _build('ours')
+        step = TrainStep(m, fused_ema=fused)
+        img, gt, metas = gc.tiny_batch('ours')
+        img_d, gt_d = img.to(DEV), gt.to(DEV)
+        O.seed_host_rng(1999)
+        logs = []
+        for it in range(3):
+            _, lv = step(img_d, _copy.deepcopy(metas), gt_d, it, sync=True)
+            logs.append(lv)
+        if not fused:      # bring the separate schedule to the same point: the next step's EMA
+            with torch.no_grad():
+                m.update_ema_variables(m.backbone, m.backbone_ema, m.momentum_backbone)
+                m.update_ema_variables(m.decode_head, m.decode_head_ema, m.momentum_head)
+        else:
+            with torch.no_grad():
+                m.update_ema_variables(m.backbone, m.backbone_ema, m.momentum_backbone, buffers_only=True)
+                m.update_ema_variables(m.decode_head, m.decode_head_ema, m.momentum_head, buffers_only=True)
+        torch.cuda.synchronize()
+        return logs, {k: v.detach().float().cpu().clone() for k, v in m.state_dict().items()}
+
+    la, sa = run(False)
+    lb, sb = run(True)
+    for i, (x, y) in enumerate(zip(la, lb)):
+        for k in x:
+            assert abs(x[k] - y[k]) <= (1e-3 if i == 0 else 5e-2) * abs(x[k]) + 1e-5, (i, k, x[k], y[k])
+    for k, v in sa.items():
+        if v.dtype.is_floating_point and 'num_batches' not in k:
+            tol = 2e-3 if 'ema' not in k else 1e-4      # the teacher moves by 1e-3 of the student's noise
+            assert float((v - sb[k]).norm()) <= tol * float(v.norm()) + 1e-6, k
+
+
+def test_sgd_ema_kernel_vs_torch_three_steps():
+    """s4_sgd_ema_multi_tensor against torch.optim.SGD(momentum) followed by t = m t + (1-m) s."""
+    from s4former_b200.optim import FusedSGD
+    g = torch.Generator().manual_seed(3)
+    shapes = [(300, 77), (5,), (16384 * 2 + 3,), (64, 3, 3, 3)]
+    ps = [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+    es = [torch.nn.Parameter(p.detach().clone() + 0.1, requires_grad=False) for p in ps[:3]]
+    ref_p = [p.detach().clone().requires_grad_(True) for p in ps]
+    ref_e = [e.detach().clone() for e in es]
+    opt = FusedSGD([(f'p{i}', p) for i, p in enumerate(ps)], lr=0.1, momentum=0.9)
+    opt.attach_ema({id(ps[i]): (es[i], 0.99 if i else 0.9) for i in range(3)})
+    ropt = torch.optim.SGD(ref_p, lr=0.1, momentum=0.9)
+    for it in range(3):
+        grads = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+        opt.zero_grad()
+        for p, rp, gr in zip(ps, ref_p, grads):
+            p.grad.copy_(gr)
+            rp.grad = gr.clone()
+        lrs = opt.current_lrs(it)
+        for grp in ropt.param_groups:
+            grp['lr'] = lrs[0]
+        opt.step(it)
+        ropt.step()
+        for i in range(3):
+            m = 0.99 if i else 0.9
+            ref_e[i].mul_(m).add_(ref_p[i].detach(), alpha=1 - m)
+    torch.cuda.synchronize()
+    for p, rp in zip(ps, ref_p):
+        assert torch.allclose(p.detach(), rp.detach(), rtol=1e-5, atol=1e-6)
+    for e, re_ in zip(es, ref_e):
+        assert torch.allclose(e.detach(), re_, rtol=1e-5, atol=1e-6)
