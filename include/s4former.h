@@ -286,6 +286,24 @@ int s4_sgd_ema_multi_tensor(void* const* params, void* const* grads, void* const
                             const long long* chunk_off, int n_chunks, float momentum,
                             float weight_decay, int first_step, cudaStream_t stream);
 
+/* ---- inference / validation -----------------------------------
+ * encoder_decoder.py:1068-1232 (slide / whole inference, rescale, softmax, flip, argmax) and
+ * mmseg/core/evaluation/metrics.py:26-131 (intersect_and_union), on the device. */
+/* mmseg/ops/wrappers.py:8-27 resize(mode='bilinear', align_corners=False), NCHW fp32, any scale */
+int s4_resize_bilinear_nchw(const float* in, float* out, int planes, int IH, int IW, int OH, int OW,
+                            cudaStream_t stream);
+/* F.softmax(dim=1) (+ flip: 0 none, 1 horizontal, 2 vertical; :1196-1204) and argmax(dim=1) (:1221);
+ * prob [B,C,H,W] and pred [B,H,W] int64 may each be NULL */
+int s4_softmax_argmax_nchw(const float* logits, float* prob, long long* pred, int B, int C, int H,
+                           int W, int flip, cudaStream_t stream);
+/* slide_inference :1089-1093: preds[:, :, y1:y1+ch, x1:x1+cw] += crop; count[...] += 1 */
+int s4_accumulate_crop(const float* crop, float* preds, float* count, int B, int C, int H, int W,
+                       int y1, int x1, int ch, int cw, cudaStream_t stream);
+/* metrics.py:26-91: hist3[0..C) intersect, [C..2C) prediction, [2C..3C) label counts (int64,
+ * ACCUMULATED) over pixels with label != ignore_index */
+int s4_intersect_union(const long long* pred, const long long* label, long long n, int num_classes,
+                       long long ignore_index, long long* hist3, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

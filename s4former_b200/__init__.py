@@ -16,10 +16,12 @@ from .decode_heads.setr_up_head import SETRUPHead
 from .losses.cross_entropy_loss import CrossEntropyLoss
 from .segmentors.encoder_decoder import EncoderDecoder
 from .ops import set_compute_dtype, set_backend
+from .parallel import S4DistributedDataParallel, register_ddp_into_mmseg
 
 __all__ = ['EncoderDecoder', 'VisionTransformer', 'SETRUPHead', 'CrossEntropyLoss', 'MODELS',
            'BACKBONES', 'HEADS', 'LOSSES', 'SEGMENTORS', 'build_backbone', 'build_head', 'build_loss',
-           'build_segmentor', 'set_compute_dtype', 'set_backend', 'register_into_mmseg', 'ops']
+           'build_segmentor', 'set_compute_dtype', 'set_backend', 'register_into_mmseg', 'ops',
+           'S4DistributedDataParallel', 'register_ddp_into_mmseg']
 
 
 def register_into_mmseg():

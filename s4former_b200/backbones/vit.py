@@ -143,10 +143,14 @@ class VisionTransformer(nn.Module):
         if isinstance(self.init_cfg, dict) and self.init_cfg.get('type') == 'Pretrained':
             checkpoint = torch.load(self.init_cfg['checkpoint'], map_location='cpu')
             state_dict = checkpoint['state_dict'] if 'state_dict' in checkpoint else checkpoint
+            state_dict = dict(state_dict)
             if 'pos_embed' in state_dict and self.pos_embed.shape != state_dict['pos_embed'].shape:
-                raise NotImplementedError(
-                    'pos_embed resize at checkpoint load (vit.py:381-392) is outside the train step; '
-                    'resize the checkpoint offline')
+                # vit.py:381-392: e.g. the DeiT-B/16 checkpoint (14 x 14 grid, 197 tokens) -> 32 x 32
+                h, w = self.img_size
+                pos_size = int(math.sqrt(state_dict['pos_embed'].shape[1] - 1))
+                state_dict['pos_embed'] = self.resize_pos_embed(
+                    state_dict['pos_embed'], (h // self.patch_size, w // self.patch_size),
+                    (pos_size, pos_size), self.interpolate_mode, self.no_pos_embed)
             self.load_state_dict(state_dict, strict=False)
             return
         nn.init.trunc_normal_(self.pos_embed, std=.02)
@@ -166,6 +170,44 @@ class VisionTransformer(nn.Module):
             elif isinstance(m, nn.LayerNorm):
                 nn.init.constant_(m.weight, 1.0)
                 nn.init.constant_(m.bias, 0.)
+
+    @staticmethod
+    def resize_pos_embed(pos_embed, input_shpae, pos_shape, mode, no_pos_embed=False):
+        """vit.py:447-477: cls row kept, the grid rows resized ([1, L, C] -> [1, 1 + h*w, C]).
+        CPU tensors (checkpoint load) go through ``F.interpolate``; CUDA tensors through the
+        library's bilinear resize."""
+        assert pos_embed.ndim == 3, 'shape of pos_embed must be [B, L, C]'
+        pos_h, pos_w = pos_shape
+        cls_token_weight = pos_embed[:, 0:1]
+        pos_embed_weight = pos_embed[:, (-1 * pos_h * pos_w):]
+        pos_embed_weight = pos_embed_weight.reshape(1, pos_h, pos_w, pos_embed.shape[2]).permute(0, 3, 1, 2)
+        if pos_embed_weight.is_cuda:
+            if mode != 'bilinear':
+                raise NotImplementedError(f'on-device pos_embed resize: bilinear only (got {mode})')
+            pos_embed_weight = ops.resize_bilinear(pos_embed_weight.float().contiguous(), input_shpae)
+        else:
+            import torch.nn.functional as F
+            pos_embed_weight = F.interpolate(pos_embed_weight, size=tuple(input_shpae), mode=mode,
+                                             align_corners=False)
+        pos_embed_weight = torch.flatten(pos_embed_weight, 2).transpose(1, 2)
+        if no_pos_embed:
+            pos_embed_weight = torch.zeros_like(pos_embed_weight)
+        return torch.cat((cls_token_weight, pos_embed_weight.to(cls_token_weight.dtype)), dim=1)
+
+    def _resized_pos_embed(self, gh, gw):
+        pos_h, pos_w = self.img_size[0] // self.patch_size, self.img_size[1] // self.patch_size
+        if self.pos_embed.shape[1] != pos_h * pos_w + 1:
+            raise ValueError('Unexpected shape of pos_embed, got {}.'.format(self.pos_embed.shape))
+        cache = self.__dict__.setdefault('_s4_pos_cache', {})
+        tag = (gh, gw, self.pos_embed._version, getattr(self.pos_embed, '_s4_gen', 0), ops._global_gen[0],
+               self.pos_embed.data_ptr())
+        hit = cache.get('pos')
+        if hit is None or hit[0] != tag:
+            with torch.no_grad():
+                val = self.resize_pos_embed(self.pos_embed.detach(), (gh, gw), (pos_h, pos_w),
+                                            self.interpolate_mode).contiguous()
+            cache['pos'] = hit = (tag, val)
+        return hit[1]
 
     @staticmethod
     def pasa_bias_vectors(attn_mask, adaptive_attn_mask, topk_idx=None):
@@ -202,10 +244,15 @@ class VisionTransformer(nn.Module):
         P = self.patch_size
         gh, gw = math.ceil(inputs.shape[2] / P), math.ceil(inputs.shape[3] / P)
         L = gh * gw + 1
+        pos_override = None
         if L != self.pos_embed.shape[1]:
-            raise NotImplementedError('on-the-fly pos_embed resize (vit.py:416-445) is off the hot path: '
-                                      f'got {L - 1} patches for a pos_embed of {self.pos_embed.shape[1] - 1}')
-        x = ops.PatchEmbedFn.apply(self.cls_token, self, inputs)
+            # vit.py:416-445 _pos_embeding: an input whose patch grid differs from the training grid
+            # (whole-image / sliding-window inference) gets a bilinearly resized position embedding
+            if torch.is_grad_enabled() and self.pos_embed.requires_grad:
+                raise NotImplementedError('training through a resized pos_embed is not on the S4Former path '
+                                          '(every shipped config trains at img_size); inference only')
+            pos_override = self._resized_pos_embed(gh, gw)
+        x = ops.PatchEmbedFn.apply(self.cls_token, self, inputs, pos_override)
         u0 = gate = None
         if attn_mask is not None:
             u0, gate = self.pasa_bias_vectors(attn_mask, adaptive_attn_mask, topk_idx)
@@ -225,6 +272,7 @@ class VisionTransformer(nn.Module):
             if i in self.out_indices:
                 out = x.view(B, L, -1)[:, 1:].unflatten(1, (gh, gw)).permute(0, 3, 1, 2)
                 out._s4_tokens = (x, B, L)
+                out._s4_hw = (gh, gw)
                 outs.append(out)
         self.multi_self_attn = [[], (gh, gw)]   # head-averaged weights are visualisation-only
         return tuple(outs)

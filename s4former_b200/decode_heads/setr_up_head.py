@@ -77,21 +77,24 @@ class SETRUPHead(BaseDecodeHead):
             nn.init.constant_(uc[0].bn.bias, 0.)
 
     # -- row map: dst token row -> src row of the backbone's [B*L, D] matrix ------------------
-    def _row_map(self, B, g, has_cls, device, PatchMix_N, PatchMixIndex, b0=0):
+    def _row_map(self, B, g, has_cls, device, PatchMix_N, PatchMixIndex, b0=0, gw=None):
         """Feature tap (+1 skips the cls row, vit.py:556-562) and, when PatchMix_N != 0, the
         inverse block permutation of decode_head.py:186-212: out_block[perm[p]] = in_block[p].
         ``b0``: index of this group's first image in the backbone's token matrix."""
-        Ls = g * g + (1 if has_cls else 0)
+        ntok = g * (g if gw is None else gw)           # (g, gw): rows x columns of the token grid
+        Ls = ntok + (1 if has_cls else 0)
         off = (1 if has_cls else 0) + b0 * Ls
         if PatchMix_N == 0:
-            key = (B, g, has_cls, str(device), b0)
+            key = (B, g, gw, has_cls, str(device), b0)
             m = self._row_maps.get(key)
             if m is None:
-                pos = torch.arange(g * g, dtype=torch.int64)
+                pos = torch.arange(ntok, dtype=torch.int64)
                 m = (torch.arange(B, dtype=torch.int64).view(B, 1) * Ls + off + pos.view(1, -1))
                 m = m.reshape(-1).to(torch.int32).to(device)
                 self._row_maps[key] = m
             return m
+        if gw is not None and gw != g:
+            raise NotImplementedError('PatchMix un-shuffle needs a square token grid (training crops are square)')
         n = int(PatchMix_N)
         gb = g // n
         perm = torch.as_tensor(PatchMixIndex)
@@ -135,18 +138,17 @@ class SETRUPHead(BaseDecodeHead):
         if tok is not None:
             x2d, B, L = tok[:3]
             b0 = tok[3] if len(tok) > 3 else 0
-            g = int(math.isqrt(L - 1))
+            gh, gw = getattr(x, '_s4_hw', None) or (int(math.isqrt(L - 1)),) * 2
+            assert gh * gw == L - 1
             has_cls = True
         else:   # a foreign NCHW tensor: flatten to tokens (copy) in the compute dtype
-            B, Cc, h, w = x.shape
-            assert h == w, 'square feature maps expected'
-            g = h
-            x2d = ops.cast(x.permute(0, 2, 3, 1).reshape(B * h * w, Cc).contiguous(), ops.compute_dtype())
+            B, Cc, gh, gw = x.shape
+            x2d = ops.cast(x.permute(0, 2, 3, 1).reshape(B * gh * gw, Cc).contiguous(), ops.compute_dtype())
             has_cls = False
-        row_map = self._row_map(B, g, has_cls, x2d.device, PatchMix_N, PatchMixIndex, b0)
-        Ltok = g * g + 1
+        row_map = self._row_map(B, gh, has_cls, x2d.device, PatchMix_N, PatchMixIndex, b0, gw=gw)
+        Ltok = gh * gw + 1
         y = ops.HeadLNFn.apply(x2d, self, row_map, B, Ltok, self.norm.weight)
-        H = W = g
+        H, W = gh, gw
         s = self.up_scale
         gi = self._group_info()
         n = len(self.up_convs)

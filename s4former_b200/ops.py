@@ -304,7 +304,11 @@ def reset_pending():
 
 def grad_buffer(p):
     if p.grad is None:
-        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        flat = getattr(p, '_s4_flat_view', None)     # a foreign zero_grad(set_to_none=True) dropped it:
+        if flat is not None:                         # re-attach the slice of the flat gradient buffer
+            p.grad = flat                            # (zeroed at the start of the step by its owner)
+        else:
+            p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
     return p.grad
 
 
@@ -515,7 +519,7 @@ class EncoderLayerFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 class PatchEmbedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, cls_token, bb, img):
+    def forward(ctx, cls_token, bb, img, pos_override=None):
         _require_cuda(img)
         B, Cin, Himg, Wimg = img.shape
         P = bb.patch_size
@@ -528,7 +532,8 @@ class PatchEmbedFn(torch.autograd.Function):
         tok = linear_fwd(a, lowp(proj.weight), proj.bias)
         Ltok = gh * gw + 1
         x = torch.empty((B * Ltok, D), dtype=dt, device=img.device)
-        L.call('s4_assemble_tokens', _p(tok), _p(cls_token.detach()), _p(bb.pos_embed.detach()), _p(x),
+        pos = bb.pos_embed.detach() if pos_override is None else pos_override
+        L.call('s4_assemble_tokens', _p(tok), _p(cls_token.detach()), _p(pos), _p(x),
                B, Ltok, D, _code(dt), _st())
         ctx.bb, ctx.dims = bb, (B, Ltok, D)
         ctx.save_for_backward(a)
@@ -552,7 +557,7 @@ class PatchEmbedFn(torch.autograd.Function):
         proj = bb.patch_embed.projection
         linear_wgrad(dtok, a, proj.weight, proj.bias)
         _pending_dec(bb)
-        return None, None, None
+        return None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -936,3 +941,50 @@ def sgd_ema_step(table, momentum, weight_decay, first_step, lrs=None):
     for t in table.keep[4]:
         if t is not None:
             bump_generation(t)
+
+
+# ----------------------------------------------------------------------------------------------
+# inference / validation (reference encoder_decoder.py:1068-1232, core/evaluation/metrics.py)
+# ----------------------------------------------------------------------------------------------
+def resize_bilinear(x, size):
+    """mmseg ``resize(x, size, mode='bilinear', align_corners=False)`` on NCHW fp32 (any scale)."""
+    _require_cuda(x)
+    B, Cc, IH, IW = x.shape
+    OH, OW = int(size[0]), int(size[1])
+    if (IH, IW) == (OH, OW):
+        return x
+    x = x.float().contiguous()
+    out = torch.empty((B, Cc, OH, OW), dtype=torch.float32, device=x.device)
+    L.call('s4_resize_bilinear_nchw', _p(x), _p(out), B * Cc, IH, IW, OH, OW, _st())
+    return out
+
+
+def softmax_argmax(logits, want_prob=True, want_pred=True, flip=None):
+    """(softmax over dim 1 [flipped], argmax over dim 1): (prob [B,C,H,W] f32 | None, pred [B,H,W] i64 | None)."""
+    _require_cuda(logits)
+    logits = logits.float().contiguous()
+    B, Cc, H, W = logits.shape
+    prob = torch.empty_like(logits) if want_prob else None
+    pred = torch.empty((B, H, W), dtype=torch.int64, device=logits.device) if want_pred else None
+    code = {None: 0, False: 0, 'horizontal': 1, 'vertical': 2}[flip]
+    L.call('s4_softmax_argmax_nchw', _p(logits), _p(prob), _p(pred), B, Cc, H, W, code, _st())
+    return prob, pred
+
+
+def accumulate_crop(preds, count, crop, y1, x1):
+    B, Cc, H, W = preds.shape
+    ch, cw = crop.shape[2], crop.shape[3]
+    L.call('s4_accumulate_crop', _p(crop.float().contiguous()), _p(preds), _p(count), B, Cc, H, W, int(y1), int(x1),
+           ch, cw, _st())
+
+
+def intersect_union_hist(pred, label, num_classes, ignore_index, hist=None):
+    """Accumulates the three class histograms of ``intersect_and_union`` into ``hist`` ([3, C] int64)."""
+    _require_cuda(pred, label)
+    pred = pred.to(torch.int64).contiguous()
+    label = label.to(device=pred.device, dtype=torch.int64).contiguous()
+    assert pred.numel() == label.numel()
+    if hist is None:
+        hist = torch.zeros((3, num_classes), dtype=torch.int64, device=pred.device)
+    L.call('s4_intersect_union', _p(pred), _p(label), pred.numel(), int(num_classes), int(ignore_index), _p(hist), _st())
+    return hist

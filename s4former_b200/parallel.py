@@ -110,3 +110,96 @@ class GradReducer:
                 else:
                     w.wait()
         self.reset()
+
+
+class S4DistributedDataParallel(torch.nn.Module):
+    """Drop-in for mmcv's ``MMDistributedDataParallel`` as built by ``mmseg.utils.util_distribution.
+    build_ddp`` (util_distribution.py:39-66, called from mmseg/apis/train.py:129-138 with
+    ``device_ids=[LOCAL_RANK], broadcast_buffers=False, find_unused_parameters=...``).
+
+    ``torch.nn.parallel.DistributedDataParallel`` cannot drive this model: the parameters are not
+    autograd inputs of the fused layer nodes (weight gradients are accumulated in place by the
+    wgrad kernels), so its per-parameter gradient hooks never fire.  This wrapper gives the
+    runner the same contract through the library's own reducer:
+
+      * construction broadcasts rank 0's parameters and buffers (DDP's initial sync);
+      * ``train_step`` / ``val_step`` / ``forward`` delegate to the wrapped segmentor (batch tensors
+        are moved to this rank's device, which is what ``MMDistributedDataParallel.scatter`` does
+        for the single-device case);
+      * every gradient lives in one flat buffer; buckets are all-reduced (average) as the modules
+        finish their backward, and whatever is left is reduced when ``loss.backward()`` ends (an
+        autograd-engine callback queued from a hook on the loss) -- so when mmcv's
+        ``OptimizerHook.after_train_iter`` reaches ``optimizer.step()`` the ``.grad`` tensors hold
+        the cross-rank mean, exactly as after DDP's backward.
+
+    The runner's ``optimizer.zero_grad()`` (set_to_none or not) is honoured: gradients are re-zeroed
+    here at the start of every ``train_step`` and ``ops.grad_buffer`` re-attaches a dropped
+    ``.grad`` to its slice of the flat buffer."""
+
+    def __init__(self, module, device_ids=None, dim=0, broadcast_buffers=False, find_unused_parameters=False,
+                 bucket_cap_mb=25, **kwargs):
+        super().__init__()
+        from .optim import FlatGrads
+        self.module = module
+        self.dim = dim
+        self.device_ids = device_ids
+        self.broadcast_buffers = broadcast_buffers
+        self.device = next(module.parameters()).device
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t.data, src=0)
+        self.grads = FlatGrads([p for p in module.parameters() if p.requires_grad])
+        for p in self.grads.params:
+            p._s4_flat_view = p.grad
+        self.reducer = GradReducer(module, self.grads, bucket_bytes=int(bucket_cap_mb) * 1024 * 1024) \
+            if self.world > 1 else None
+
+    def _to_device(self, obj):
+        if torch.is_tensor(obj):
+            return obj.to(self.device, non_blocking=True) if obj.device != self.device else obj
+        if hasattr(obj, '_data'):            # mmcv DataContainer: .data[0] is this rank's part
+            data = obj._data
+            return self._to_device(data[0] if isinstance(data, (list, tuple)) and len(data) == 1 else data)
+        if isinstance(obj, dict):
+            return {k: self._to_device(v) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._to_device(v) for v in obj)
+        return obj
+
+    def _arm(self, outputs):
+        """Reduce the gradients when the backward pass of ``outputs['loss']`` completes."""
+        loss = outputs.get('loss') if isinstance(outputs, dict) else None
+        if self.reducer is None or loss is None or not loss.requires_grad:
+            return outputs
+
+        def on_backward_start(grad):
+            torch.autograd.Variable._execution_engine.queue_callback(self.reducer.finalize)
+            return grad
+        loss.register_hook(on_backward_start)
+        return outputs
+
+    def train_step(self, *inputs, **kwargs):
+        from . import ops
+        self.grads.zero()
+        ops.reset_arena()
+        ops.reset_pending()
+        if self.reducer is not None:
+            self.reducer.reset()
+        inputs, kwargs = self._to_device(inputs), self._to_device(kwargs)
+        return self._arm(self.module.train_step(*inputs, **kwargs))
+
+    def val_step(self, *inputs, **kwargs):
+        inputs, kwargs = self._to_device(inputs), self._to_device(kwargs)
+        return self.module.val_step(*inputs, **kwargs)
+
+    def forward(self, *inputs, **kwargs):
+        inputs, kwargs = self._to_device(inputs), self._to_device(kwargs)
+        return self.module(*inputs, **kwargs)
+
+
+def register_ddp_into_mmseg():
+    """Make ``mmseg.utils.util_distribution.build_ddp`` (hence tools/train.py) build this wrapper."""
+    from mmseg.utils import util_distribution
+    util_distribution.ddp_factory['cuda'] = S4DistributedDataParallel

@@ -45,7 +45,22 @@ class BaseSegmentor(nn.Module, metaclass=ABCMeta):
         pass
 
     def forward_test(self, imgs, img_metas, **kwargs):
-        raise NotImplementedError('inference (simple_test / aug_test) is outside the train-step scope')
+        """base.py:65-99.  ``img_metas`` entries may be mmcv ``DataContainer``s (``._data[0]``, what the
+        shipped code assumes) or plain lists of dicts."""
+        for var, name in [(imgs, 'imgs'), (img_metas, 'img_metas')]:
+            if not isinstance(var, list):
+                raise TypeError(f'{name} must be a list, but got {type(var)}')
+        num_augs = len(imgs)
+        if num_augs != len(img_metas):
+            raise ValueError(f'num of augmentations ({len(imgs)}) != num of image meta ({len(img_metas)})')
+        metas = [m._data[0] if hasattr(m, '_data') else m for m in img_metas]
+        for img_meta in metas:
+            for key in ('ori_shape', 'img_shape', 'pad_shape'):
+                vals = [_[key] for _ in img_meta]
+                assert all(v == vals[0] for v in vals)
+        if num_augs == 1:
+            return self.simple_test(imgs[0], metas[0], **kwargs)
+        return self.aug_test(imgs, metas, **kwargs)
 
     def forward(self, img, img_metas, return_loss=True, **kwargs):
         if return_loss:

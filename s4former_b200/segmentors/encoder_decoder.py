@@ -146,9 +146,118 @@ class EncoderDecoder(BaseSegmentor):
     def extract_feat_ema(self, img):
         return self.backbone_ema(img)
 
+    # ------------------------------------------------------------------ inference (:270-308, :1068-1265)
     def encode_decode(self, img, img_metas, adaptive_attn_mask=False, return_last_feat=False):
-        raise NotImplementedError('inference is outside the train-step scope (and broken as shipped, '
-                                  'SURVEY.md section 2.3 hazard 5)')
+        """(:270-297) backbone + decode head + resize to the input size.  ``adaptive_attn_mask`` has
+        a default here: the shipped ``whole_inference`` / ``slide_inference`` call this method
+        without it and raise ``TypeError`` (SURVEY.md hazard 5); same signature otherwise."""
+        if return_last_feat:
+            raise NotImplementedError('return_last_feat (feature visualisation) is outside the hot path')
+        x = self.extract_feat(img)
+        out = self._decode_head_forward_test(x, img_metas)
+        return ops.resize_bilinear(out, img.shape[2:])
+
+    def encode_decode_ema(self, img, img_metas):
+        """(:298-308)"""
+        x = self.extract_feat_ema(img)
+        out = self._decode_head_forward_test_ema(x, img_metas)
+        return ops.resize_bilinear(out, img.shape[2:])
+
+    def _decode_head_forward_test(self, x, img_metas, return_last_feat=False):
+        return self.decode_head.forward_test(x, img_metas, self.test_cfg, return_last_feat)
+
+    def _decode_head_forward_test_ema(self, x, img_metas):
+        return self.decode_head_ema.forward_test(x, img_metas, self.test_cfg)
+
+    @staticmethod
+    def _cfg_get(cfg, key):
+        return cfg[key] if isinstance(cfg, dict) else getattr(cfg, key)
+
+    def slide_inference(self, img, img_meta, rescale):
+        """(:1068-1115) sliding window with overlap; window logits are accumulated on the device."""
+        h_stride, w_stride = self._cfg_get(self.test_cfg, 'stride')
+        h_crop, w_crop = self._cfg_get(self.test_cfg, 'crop_size')
+        batch_size, _, h_img, w_img = img.size()
+        h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
+        w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
+        preds = torch.zeros((batch_size, self.num_classes, h_img, w_img), dtype=torch.float32, device=img.device)
+        count_mat = torch.zeros((batch_size, 1, h_img, w_img), dtype=torch.float32, device=img.device)
+        for h_idx in range(h_grids):
+            for w_idx in range(w_grids):
+                y1 = h_idx * h_stride
+                x1 = w_idx * w_stride
+                y2 = min(y1 + h_crop, h_img)
+                x2 = min(x1 + w_crop, w_img)
+                y1 = max(y2 - h_crop, 0)
+                x1 = max(x2 - w_crop, 0)
+                crop_img = img[:, :, y1:y2, x1:x2].contiguous()
+                if self.ema_test:
+                    crop_seg_logit = self.encode_decode_ema(crop_img, img_meta)
+                else:
+                    crop_seg_logit = self.encode_decode(crop_img, img_meta)
+                ops.accumulate_crop(preds, count_mat, crop_seg_logit, y1, x1)
+        preds = preds / count_mat          # (every pixel is covered: the grid spans the image)
+        if rescale:
+            resize_shape = img_meta[0]['img_shape'][:2]
+            preds = preds[:, :, :resize_shape[0], :resize_shape[1]]
+            preds = ops.resize_bilinear(preds, img_meta[0]['ori_shape'][:2])
+        return preds
+
+    def whole_inference(self, img, img_meta, rescale, tde=False, return_last_feat=False, use_attn_mask=None):
+        """(:1117-1174)"""
+        if tde or return_last_feat or use_attn_mask is not None:
+            raise NotImplementedError('tde / return_last_feat / use_attn_mask are analysis paths')
+        if self.ema_test:
+            seg_logit = self.encode_decode_ema(img, img_meta)
+        else:
+            seg_logit = self.encode_decode(img, img_meta)
+        if rescale:
+            resize_shape = img_meta[0]['img_shape'][:2]
+            seg_logit = seg_logit[:, :, :resize_shape[0], :resize_shape[1]]
+            seg_logit = ops.resize_bilinear(seg_logit, img_meta[0]['ori_shape'][:2])
+        return seg_logit
+
+    def inference(self, img, img_meta, rescale, tde=False, return_last_feat=False, use_attn_mask=None,
+                  want_pred=False):
+        """(:1176-1212) softmax over classes of the whole / slide logits, flipped back when the test
+        pipeline flipped the image.  ``want_pred=True`` also returns the arg-max map computed in the
+        same kernel (``simple_test`` needs nothing else)."""
+        mode = self._cfg_get(self.test_cfg, 'mode')
+        assert mode in ['slide', 'whole']
+        ori_shape = img_meta[0]['ori_shape']
+        assert all(_['ori_shape'] == ori_shape for _ in img_meta)
+        with torch.no_grad():
+            if mode == 'slide':
+                seg_logit = self.slide_inference(img, img_meta, rescale)
+            else:
+                seg_logit = self.whole_inference(img, img_meta, rescale, tde, return_last_feat, use_attn_mask)
+            flip = img_meta[0].get('flip', False)
+            direction = None
+            if flip:
+                direction = img_meta[0]['flip_direction']
+                assert direction in ['horizontal', 'vertical']
+            output, pred = ops.softmax_argmax(seg_logit, want_prob=True, want_pred=want_pred, flip=direction)
+        return (output, pred) if want_pred else output
+
+    def simple_test(self, img, img_meta, rescale=True, tde=False, return_last_feat=False):
+        """(:1214-1232) -> list of per-image int64 label maps (numpy, like the reference)."""
+        _, seg_pred = self.inference(img, img_meta, rescale, tde, return_last_feat, want_pred=True)
+        return list(seg_pred.cpu().numpy())
+
+    def simple_test_device(self, img, img_meta, rescale=True):
+        """``simple_test`` without the device->host copy: [B, H, W] int64 on the device, ready for
+        ``core.evaluation.intersect_and_union``."""
+        return self.inference(img, img_meta, rescale, want_pred=True)[1]
+
+    def aug_test(self, imgs, img_metas, rescale=True):
+        """(:1257-1274) mean of the per-augmentation probabilities, then arg-max."""
+        assert rescale
+        seg_logit = self.inference(imgs[0], img_metas[0], rescale)
+        for i in range(1, len(imgs)):
+            seg_logit = seg_logit + self.inference(imgs[i], img_metas[i], rescale)
+        seg_logit = seg_logit / len(imgs)
+        seg_pred = seg_logit.argmax(dim=1)
+        return list(seg_pred.cpu().numpy())
 
     def _decode_head_forward_train(self, x, img_metas, gt_semantic_seg):
         loss_decode = self.decode_head.forward_train(x, img_metas, gt_semantic_seg, self.train_cfg)
@@ -234,6 +343,7 @@ class EncoderDecoder(BaseSegmentor):
             x2d, _, L = f._s4_tokens[:3]
             g = f[b0:b0 + nb]
             g._s4_tokens = (x2d, nb, L, b0)
+            g._s4_hw = getattr(f, '_s4_hw', None)
             outs.append(g)
         return tuple(outs)
 

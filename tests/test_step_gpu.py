@@ -359,3 +359,100 @@ def test_sgd_ema_kernel_vs_torch_three_steps():
         assert torch.allclose(p.detach(), rp.detach(), rtol=1e-5, atol=1e-6)
     for e, re_ in zip(es, ref_e):
         assert torch.allclose(e.detach(), re_, rtol=1e-5, atol=1e-6)
+
+
+def _data_batch(variant, it=0):
+    """The reference's ``data_batch`` layout after ``collate(flatten=True)`` + scatter
+    (datasets/builder.py:295-302): one dict of img / img_metas / gt_semantic_seg."""
+    img, gt, metas = gc.tiny_batch(variant)
+    return dict(img=img.to(DEV), img_metas=[dict(m) for m in metas], gt_semantic_seg=gt.to(DEV))
+
+
+def test_train_step_and_val_step_api():
+    """BaseSegmentor.train_step(data_batch, optimizer, iter=i) (base.py:155-206): returns
+    dict(loss, log_vars, num_samples) with host-float log variables whose 'loss' is the sum of the
+    entries containing 'loss'; val_step mirrors it."""
+    m, _ = _build('ours')
+    O.seed_host_rng(1999)
+    out = m.train_step(_data_batch('ours'), None, iter=3)
+    assert set(out) == {'loss', 'log_vars', 'num_samples'} and out['num_samples'] == 6
+    lv = out['log_vars']
+    assert all(isinstance(v, float) for v in lv.values())
+    want_keys = {'decode.loss_ce', 'aux_0.loss_ce', 'aux_1.loss_ce', 'aux_2.loss_ce', 'aux_3.loss_ce',
+                 'loss_seg_unsup_attn_mask', 'loss_ncr_unsup', 'loss_seg_unsup', 'loss'}
+    assert set(lv) == want_keys
+    assert abs(lv['loss'] - sum(v for k, v in lv.items() if 'loss' in k and k != 'loss')) < 1e-4 * abs(lv['loss'])
+    assert abs(float(out['loss']) - lv['loss']) < 1e-5 * abs(lv['loss'])
+    assert m.current_iter == 3
+    out['loss'].backward()
+    assert float(m.backbone.layers[0].ffn.layers[1].weight.grad.abs().sum()) > 0
+    # the same numbers as the golden step (same seeds / weights / batch)
+    G = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'step_ours.pt'), weights_only=False)
+    for k, v in G['losses'].items():
+        assert abs(lv[k] - float(v)) <= 3e-2 * abs(float(v)) + 1e-3, k
+    O.seed_host_rng(1999)
+    vout = m.val_step(dict(_data_batch('ours'), iter=4))
+    assert set(vout['log_vars']) == {k + '_val' for k in want_keys}
+
+
+def test_ddp_wrapper_world1_runner_contract():
+    """S4DistributedDataParallel under the runner's protocol (mmcv OptimizerHook.after_train_iter:
+    optimizer.zero_grad(); loss.backward(); optimizer.step()) with a stock torch.optim.SGD and
+    zero_grad(set_to_none=True): two iterations equal the un-wrapped model driven the same way."""
+    from s4former_b200.parallel import S4DistributedDataParallel
+
+    def run(wrap):
+        m, _ = _build('ours')
+        model = S4DistributedDataParallel(m, device_ids=[0], broadcast_buffers=False,
+                                          find_unused_parameters=False) if wrap else m
+        opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=1e-3, momentum=0.9)
+        O.seed_host_rng(1999)
+        logs = []
+        for it in range(2):
+            if not wrap:
+                opt.zero_grad(set_to_none=False)
+                ops.reset_arena()
+            out = model.train_step(_data_batch('ours'), opt, iter=it)
+            if wrap:
+                opt.zero_grad(set_to_none=True)          # after the forward, like the hook
+            out['loss'].backward()
+            opt.step()
+            logs.append(out['log_vars'])
+        torch.cuda.synchronize()
+        if wrap:      # gradients still live in the wrapper's flat buffer
+            fg = model.grads
+            for p in fg.params:
+                off, n = fg.offsets[id(p)]
+                assert p.grad.data_ptr() == fg.flat.data_ptr() + 4 * off
+        return logs, {n: p.detach().float().cpu().clone() for n, p in m.named_parameters()}
+
+    la, wa = run(False)
+    lb, wb = run(True)
+    for x, y in zip(la, lb):
+        for k in x:
+            assert abs(x[k] - y[k]) <= 2e-2 * abs(x[k]) + 1e-4, (k, x[k], y[k])
+    for k in wa:
+        assert float((wa[k] - wb[k]).norm()) <= 2e-3 * float(wa[k].norm()) + 1e-6, k
+
+
+def test_pasa_bias_only_on_peeled_key():
+    """Regression for the peeled-key detection (L = 128 k + 1: the last key is folded in on the CUDA
+    cores and is not part of the staged u0 row): a batch whose ONLY non-zero u0 entry is that last
+    key must still take the biased path."""
+    B, H, hd, L_ = 2, 2, 64, 257
+    g = torch.Generator().manual_seed(4)
+    qkv = (torch.randn(B * L_, 3 * H * hd, generator=g) * 0.5).to(DEV, torch.bfloat16)
+    u0 = torch.zeros(B, L_)
+    u0[0, L_ - 1] = 1.0                    # image 0: bias on the peeled key only; image 1: no bias at all
+    gate = torch.ones(B, L_)
+    gate[0, 5:40] = 0.0
+    w = 5.0
+    out, lse = ops.attention_fwd(qkv, B, L_, H, hd, u0.to(DEV), gate.to(DEV), w)
+    q, k, v = qkv.float().view(B, L_, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    s = q @ k.transpose(-1, -2) / hd ** 0.5 + (w * gate.to(DEV)[:, None, :, None] * u0.to(DEV)[:, None, None, :])
+    want = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * L_, H * hd)
+    assert float((out.float() - want).norm() / want.norm()) < 2e-2
+    # and it differs measurably from the unbiased result for image 0's gated-on rows
+    plain, _ = ops.attention_fwd(qkv, B, L_, H, hd, None, None, 0.0)
+    assert float((out.float()[:L_] - plain.float()[:L_]).norm()) > 1e-2 * float(plain.float()[:L_].norm())
+    assert float((out.float()[L_:] - plain.float()[L_:]).norm()) < 1e-3 * float(plain.float()[L_:].norm())
