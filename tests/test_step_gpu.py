@@ -325,6 +325,8 @@ def test_fused_sgd_ema_sweep_equals_separate_updates():
     for k, v in sa.items():
         if v.dtype.is_floating_point and 'num_batches' not in k:
             tol = 2e-3 if 'ema' not in k else 1e-4      # the teacher moves by 1e-3 of the student's noise
+            if 'running_' in k:                          # batch statistics of a tiny model amplify bf16 /
+                tol = 2e-2 if 'ema' not in k else 1e-3   # atomic-order noise between two runs
             assert float((v - sb[k]).norm()) <= tol * float(v.norm()) + 1e-6, k
 
 
