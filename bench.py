@@ -113,9 +113,14 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU reference path (the oracle: the reference's algorithm in plain PyTorch fp32)
 # --------------------------------------------------------------------------------------------
-def cpu_reference_steps(a, n_sup, n_unsup, max_steps, warmup, budget_s):
+EMA_CLS_SCALE = 50.0      # random-init conv_seg ~ N(0, 0.01): scale the teacher's so ~half the pixels clear 0.95
+
+
+def cpu_reference_steps(a, n_sup, n_unsup, max_steps, warmup, budget_s, keep=None):
     """Times the oracle's train step (forward_train + backward + SGD step) on the host cores for a
-    BOUNDED sample (n_sup labeled + n_unsup unlabeled crops).  Returns (seconds/step, steps, threads)."""
+    BOUNDED sample (n_sup labeled + n_unsup unlabeled crops).  Returns (seconds/step, steps, threads).
+    ``keep`` (a dict) receives the initial weights, the batch and the first step's losses / pseudo
+    labels for the in-bench parity block."""
     import copy
     import torch
     # The launcher's environment must not decide the baseline's speed: torch.distributed.run
@@ -133,17 +138,27 @@ def cpu_reference_steps(a, n_sup, n_unsup, max_steps, warmup, budget_s):
     if m.ema:
         m.backbone_ema.load_state_dict(m.backbone.state_dict())
         m.decode_head_ema.load_state_dict(m.decode_head.state_dict())
+        with torch.no_grad():
+            m.decode_head_ema.conv_seg.weight.mul_(EMA_CLS_SCALE)
+            m.decode_head_ema.conv_seg.bias.mul_(EMA_CLS_SCALE)
     m.train()
     params = [p for p in m.parameters() if p.requires_grad]
     opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9)
     img, gt, metas = make_batch(n_sup, n_unsup if a.variant != 'sup' else 0, a.size, a.classes, seed=1999)
+    if keep is not None:
+        keep.update(state_dict={k: v.detach().clone() for k, v in m.state_dict().items()}, img=img, gt=gt,
+                    metas=metas, cfg=cfg)
     O.seed_host_rng(1999)
     times = []
     t_start = time.perf_counter()
     for i in range(warmup + max_steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        losses = m.forward_train(img, fresh_metas(metas), gt)
+        rec = {} if (keep is not None and i == 0) else None
+        losses = m.forward_train(img, fresh_metas(metas), gt, record=rec)
+        if rec is not None:
+            keep.update(losses={k: float(v) for k, v in losses.items()},
+                        mask_ratio=float(rec['conf'].float().mean()) if 'conf' in rec else None)
         loss = O.parse_losses(losses)
         loss.backward()
         opt.step()
@@ -186,6 +201,120 @@ def reference_arm(a):
                e2e=dict(value=value, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
     emit(out)
+
+
+# --------------------------------------------------------------------------------------------
+# legs that put the headline number in context (rank 0, N = 1 only)
+# --------------------------------------------------------------------------------------------
+def parity_block(a, keep, dev):
+    """The GPU path (bf16 tcgen05 kernels) on the SAME weights / sample / host RNG seed as the
+    cpu_baseline's oracle step: the 8 losses side by side."""
+    import torch
+    import s4former_b200 as s4
+    from oracle import s4former_oracle as O
+    from s4former_b200.utils.synthetic import fresh_metas
+    cfg = dict(keep['cfg'])
+    m = s4.build_segmentor(cfg)
+    m.load_state_dict(keep['state_dict'])
+    m = m.to(dev).train()
+    m._topk_override = lambda flat: torch.topk(flat.detach().float().cpu(), int(0.5 * flat.size(-1)), dim=-1,
+                                               largest=False)[1]      # the reference's CPU tie order
+    O.seed_host_rng(1999)
+    with torch.no_grad():
+        pass
+    losses = m.forward_train(keep['img'].to(dev), fresh_metas(keep['metas']), gt_semantic_seg=keep['gt'].to(dev), iter=0)
+    got = {k: float(v) for k, v in losses.items()}
+    rel = {k: abs(got[k] - v) / max(abs(v), 1e-12) for k, v in keep['losses'].items()}
+    del m
+    torch.cuda.empty_cache()
+    return dict(what='losses of one step on the cpu_baseline sample: oracle fp32 on the host vs this repo in bf16 on the GPU '
+                     '(same weights, inputs and host RNG seed)',
+                oracle_cpu_fp32=keep['losses'], ours_gpu_bf16=got, max_rel_diff=max(rel.values()) if rel else None,
+                teacher_mask_ratio_oracle=keep.get('mask_ratio'), tolerance='2e-2 (north_star bf16 gate)',
+                ok=bool(rel) and max(rel.values()) <= 2e-2)
+
+
+def gpu_eager_leg(a, dev, n_sup, n_unsup, steps=3):
+    """SURVEY.md section 8(d) "the true bar": the reference path on THIS GPU -- the oracle port in
+    PyTorch eager (cuBLAS / cuDNN / ATen kernels), fp32 (TF32 off, the reference's arithmetic) and
+    under bf16 autocast, same batch, forward_train + backward + SGD step, CUDA events."""
+    import torch
+    from oracle import s4former_oracle as O            # baseline leg only: never the product path
+    from s4former_b200 import configs
+    from s4former_b200.utils.synthetic import make_batch, fresh_metas
+    out = dict(kind='oracle port of the reference path in PyTorch eager on this GPU (cuBLAS/cuDNN/ATen)',
+               steps=steps, workload=f'{n_sup} labeled + {n_unsup} unlabeled {a.size}x{a.size} crops')
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = configs.setr_pup_deit_base(a.variant, a.size, a.classes, norm='BN')
+    for mode in ('bf16_autocast', 'fp32'):
+        try:
+            torch.manual_seed(1999)
+            m = O.OracleEncoderDecoder(**{k: v for k, v in cfg.items() if k != 'type'})
+            m.init_weights()
+            if m.ema:
+                m.backbone_ema.load_state_dict(m.backbone.state_dict())
+                m.decode_head_ema.load_state_dict(m.decode_head.state_dict())
+                with torch.no_grad():
+                    m.decode_head_ema.conv_seg.weight.mul_(EMA_CLS_SCALE)
+                    m.decode_head_ema.conv_seg.bias.mul_(EMA_CLS_SCALE)
+            m = m.to(dev).train()
+            opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=1e-3, momentum=0.9)
+            img, gt, metas = make_batch(n_sup, n_unsup, a.size, a.classes, seed=1999)
+            img, gt = img.to(dev), gt.to(dev)
+            O.seed_host_rng(1999)
+
+            def one():
+                opt.zero_grad(set_to_none=True)
+                if mode == 'fp32':
+                    losses = m.forward_train(img, fresh_metas(metas), gt)
+                else:
+                    with torch.autocast('cuda', dtype=torch.bfloat16):
+                        losses = m.forward_train(img, fresh_metas(metas), gt)
+                O.parse_losses(losses).backward()
+                opt.step()
+            one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = dict(ms_per_step=ms, steps_per_s=1e3 / ms, peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+        except Exception as e:      # e.g. out of memory at the full batch: say so instead of dying
+            out[mode] = dict(error=f'{type(e).__name__}: {str(e)[:160]}')
+        finally:
+            m = opt = None
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats(dev)
+    return out
+
+
+def extra_config_runs(a):
+    """BASELINE.json configs 1 / 2 / 4 (supervised-only, Mean Teacher as shipped, 768x768 / 19 classes) as
+    short runs of this same script, so that they are driver-run numbers too."""
+    runs = {}
+    specs = dict(sup_only_config1=['--variant', 'sup'], mean_teacher_config2=['--variant', 'mt'],
+                 cityscapes_768_config4=['--size', '768', '--classes', '19'])
+    for name, extra in specs.items():
+        cmd = [sys.executable, os.path.abspath(__file__), '--steps', '5', '--warmup', '3', '--no-cpu-baseline',
+               '--no-gpu-eager', '--no-extra-configs', '--no-prof', '--no-parity'] + extra
+        if a.no_graph:
+            cmd.append('--no-graph')
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=240)
+            line = [ln for ln in r.stdout.decode().splitlines() if ln.startswith('{')][-1]
+            j = json.loads(line)
+            runs[name] = dict(workload=j['config']['workload'], ms_per_step=j['ms_per_step'], value=j['value'],
+                              unit=j['unit'], e2e_ms_per_step=j['e2e']['ms_per_step'], step_tc_frac=j['step_tc_frac'],
+                              step_tflops=j['step_tflops'], steps=j['steps'])
+        except Exception as e:
+            runs[name] = dict(error=f'{type(e).__name__}: {str(e)[:120]}')
+    return runs
 
 
 # --------------------------------------------------------------------------------------------
@@ -385,7 +514,8 @@ def main():
         """Captured NCCL collectives keep the communicator busy: destroying the process group
         with a live CUDA graph hung the N > 1 run at exit.  Drop the graph, drain, and leave
         without the collective teardown."""
-        step._graph = None
+        if step is not None:
+            step._graph = None
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -450,9 +580,30 @@ def main():
                                kernel_nodes_per_replay=getattr(step, 'graph_kernel_launches', None)),
                clocks=clk, roofline=roofline,
                kernels=sorted(kinds, key=lambda k: -k["ms_per_step"])[:40])
+    if world == 1 and not (a.no_gpu_eager and a.no_extra_configs and a.no_cpu_baseline):
+        # the comparison legs need the memory: drop this arm's model, graph and staging buffers
+        step._graph = None
+        step = model = img_d = gt_d = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    if world == 1 and not a.no_gpu_eager:
+        out['gpu_eager_baseline'] = gpu_eager_leg(a, dev, a.sup, n_unsup)
+        for mode in ('bf16_autocast', 'fp32'):
+            r = out['gpu_eager_baseline'].get(mode, {})
+            if 'ms_per_step' in r:
+                r['speedup_of_this_repo'] = r['ms_per_step'] / (sec * 1e3)
+    if world == 1 and not a.no_extra_configs:
+        out['extra_configs'] = extra_config_runs(a)
     if world == 1 and not a.no_cpu_baseline:
         s_sup, s_unsup = 1, (1 if n_unsup else 0)
-        csec, n, threads = cpu_reference_steps(a, s_sup, s_unsup, 1, 0, 40.0)
+        keep = {} if not a.no_parity else None
+        csec, n, threads = cpu_reference_steps(a, s_sup, s_unsup, 1, 0, 40.0, keep=keep)
+        if keep:
+            try:
+                out['parity'] = parity_block(a, keep, dev)
+            except Exception as e:
+                out['parity'] = dict(error=f'{type(e).__name__}: {str(e)[:160]}')
         out['cpu_baseline'] = dict(
             value=(s_sup / a.sup) / csec, unit='steps/s', cores=threads, kind='port',
             sample=f'{s_sup} labeled + {s_unsup} unlabeled {a.size}x{a.size} crops, one oracle step '
