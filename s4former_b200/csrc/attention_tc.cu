@@ -621,6 +621,7 @@ struct BwdParams {
   const float* gate;
   float w, scale;
   int B, H, L, q_tiles;
+  int kv_tiles;          // 128-key tiles walked by CTAs (q_tiles, or q_tiles - 1 when key L-1 is peeled)
   TraceCfg trace;
 };
 
@@ -670,7 +671,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   float* wgls = dlts + lpad;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv_tiles = p.q_tiles;
+  const int kv_tiles = p.kv_tiles;
   const int jt = blockIdx.x % kv_tiles;
   const int bh = blockIdx.x / kv_tiles;
   const int h = bh % p.H, b = bh / p.H;
@@ -1061,10 +1062,90 @@ attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat1
   delta[((size_t)b * H + hh) * L + q] = acc;
 }
 
+// PEELED KEY (L = 128 k + 1: a ViT's cls token + square patch grid).  Key L-1 would be a 128-key
+// tile of its own with ONE valid key: a CTA walking all query tiles with full-size MMAs for 1/128
+// of their rows (1 of 9 CTAs at L = 1025, 11 % of the kernel).  Its contribution is a rank-1 term
+// instead, computed on the CUDA cores by one small block per (batch, head):
+//   p[q]  = 2^(c1 Q_q.K_x + w gate_q u0_x log2e - lse_q log2e)   ds[q] = p[q] (dO_q.V_x - delta_q)
+//   dV_x  = sum_q p[q] dO_q     dK_x = scale sum_q ds[q] Q_q     dQ_q += ds[q] K_x  (added by the
+//   dq convert kernel from ds_peel[b,h,q])
+// p / ds are rounded to bf16 before they are used, as the tensor-core path rounds P^T / dS^T.
+__global__ void __launch_bounds__(256)
+attn_bwd_peel_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                     const float* __restrict__ lse, const float* __restrict__ delta,
+                     const float* __restrict__ u0, const float* __restrict__ gate, float w, float scale,
+                     __nv_bfloat16* __restrict__ dqkv, float* __restrict__ ds_peel, int B, int H, int L) {
+  extern __shared__ float psm[];            // [L] p, [L] ds, [64] K_x, [64] V_x, [4][128] partials
+  float* ps = psm;
+  float* dss = psm + L;
+  float* kx = dss + L;
+  float* vx = kx + 64;
+  float* part = vx + 64;
+  const int bh = blockIdx.x, h = bh % H, b = bh / H;
+  const int D3 = 3 * H * HD, D = H * HD;
+  const int x = L - 1;
+  const __nv_bfloat16* qkv_b = qkv + (size_t)b * L * D3;
+  const __nv_bfloat16* do_b = dout + (size_t)b * L * D;
+  if (threadIdx.x < 64) kx[threadIdx.x] = __bfloat162float(qkv_b[(size_t)x * D3 + (H + h) * HD + threadIdx.x]);
+  else if (threadIdx.x < 128) vx[threadIdx.x - 64] = __bfloat162float(qkv_b[(size_t)x * D3 + (2 * H + h) * HD + threadIdx.x - 64]);
+  __syncthreads();
+  const float c1 = scale * LOG2E;
+  const float u0x = u0 ? u0[(size_t)b * L + x] : 0.f;
+  const float* lse_b = lse + ((size_t)b * H + h) * L;
+  const float* dl_b = delta + ((size_t)b * H + h) * L;
+  for (int q = threadIdx.x; q < L; q += blockDim.x) {
+    const uint4* qr = reinterpret_cast<const uint4*>(qkv_b + (size_t)q * D3 + h * HD);
+    const uint4* dr = reinterpret_cast<const uint4*>(do_b + (size_t)q * D + h * HD);
+    float s = 0.f, dp = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 qa = __ldg(qr + c), da = __ldg(dr + c);
+      const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qa);
+      const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&da);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 qf = __bfloat1622float2(q2[e]), df = __bfloat1622float2(d2[e]);
+        s = fmaf(qf.x, kx[c * 8 + 2 * e], s);
+        s = fmaf(qf.y, kx[c * 8 + 2 * e + 1], s);
+        dp = fmaf(df.x, vx[c * 8 + 2 * e], dp);
+        dp = fmaf(df.y, vx[c * 8 + 2 * e + 1], dp);
+      }
+    }
+    float wg = 0.f;
+    if (u0) wg = w * LOG2E * (gate ? gate[(size_t)b * L + q] : 1.f);
+    const float pe = tc::ex2(fmaf(s, c1, fmaf(wg, u0x, -lse_b[q] * LOG2E)));
+    const float dsv = pe * (dp - dl_b[q]);
+    const float pr = __bfloat162float(__float2bfloat16_rn(pe));
+    const float dr_ = __bfloat162float(__float2bfloat16_rn(dsv));
+    ps[q] = pr;
+    dss[q] = dr_;
+    ds_peel[((size_t)b * H + h) * L + q] = dr_;
+  }
+  __syncthreads();
+  // dV_x[d] = sum_q p[q] dO[q][d] (threads 0..127: 2 interleaved q-parts x 64 dims), dK_x likewise
+  // from Q (threads 128..255)
+  const int d = threadIdx.x & 63, partq = (threadIdx.x >> 6) & 1, which = threadIdx.x >> 7;
+  float acc = 0.f;
+  if (which == 0) {
+    for (int q = partq; q < L; q += 2) acc = fmaf(ps[q], __bfloat162float(do_b[(size_t)q * D + h * HD + d]), acc);
+  } else {
+    for (int q = partq; q < L; q += 2) acc = fmaf(dss[q], __bfloat162float(qkv_b[(size_t)q * D3 + h * HD + d]), acc);
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (partq == 0) {
+    const float tot = part[threadIdx.x] + part[threadIdx.x + 64];
+    __nv_bfloat16* orow = dqkv + ((size_t)b * L + x) * D3 + (which == 0 ? 2 * H + h : H + h) * HD;
+    orow[d] = __float2bfloat16_rn(which == 0 ? tot : tot * scale);
+  }
+}
+
 // dq_accum [B,H,q_tiles,128,64] fp32 (16-byte chunks XOR-swizzled by row) -> dqkv[:, :, h*64 + d] * scale
+// (+ the peeled key's ds_peel[b,h,q] * K_x[d] when ds_peel != null)
 __global__ void __launch_bounds__(256)
 attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, int B, int H,
-                           int L, int q_tiles, float scale) {
+                           int L, int q_tiles, float scale, const float* __restrict__ ds_peel,
+                           const __nv_bfloat16* __restrict__ qkv) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, q, h, 8-column group)
   const long long total = (long long)B * L * H * 8;
   if (idx >= total) return;
@@ -1075,8 +1156,17 @@ attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restr
   const int b = (int)(bq / L);
   const int r = q & 127;
   const float* rowp = acc + (((size_t)(b * H + hh) * q_tiles + (q >> 7)) * 128 + r) * 64;
-  const float4 lo = *reinterpret_cast<const float4*>(rowp + (((2 * g8) ^ (r & 15)) << 2));
-  const float4 hi = *reinterpret_cast<const float4*>(rowp + (((2 * g8 + 1) ^ (r & 15)) << 2));
+  float4 lo = *reinterpret_cast<const float4*>(rowp + (((2 * g8) ^ (r & 15)) << 2));
+  float4 hi = *reinterpret_cast<const float4*>(rowp + (((2 * g8 + 1) ^ (r & 15)) << 2));
+  if (ds_peel) {
+    const float dsq = ds_peel[((size_t)b * H + hh) * L + q];
+    const uint4 kraw = __ldg(reinterpret_cast<const uint4*>(qkv + ((size_t)b * L + (L - 1)) * 3 * H * HD + (H + hh) * HD + g8 * 8));
+    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kraw);
+    const float2 k0 = __bfloat1622float2(k2[0]), k1 = __bfloat1622float2(k2[1]);
+    const float2 k2f = __bfloat1622float2(k2[2]), k3 = __bfloat1622float2(k2[3]);
+    lo.x = fmaf(dsq, k0.x, lo.x); lo.y = fmaf(dsq, k0.y, lo.y); lo.z = fmaf(dsq, k1.x, lo.z); lo.w = fmaf(dsq, k1.y, lo.w);
+    hi.x = fmaf(dsq, k2f.x, hi.x); hi.y = fmaf(dsq, k2f.y, hi.y); hi.z = fmaf(dsq, k3.x, hi.z); hi.w = fmaf(dsq, k3.y, hi.w);
+  }
   uint4 v;
   v.x = pack_bf16(lo.x * scale, lo.y * scale);
   v.y = pack_bf16(lo.z * scale, lo.w * scale);
@@ -1118,7 +1208,7 @@ bool s4_attention_tc_bwd_supported(int B, int H, int L, int hd, int dtype) {
 // workspace of the fused backward: delta [B,H,L] + dq_accum [B,H,q_tiles,128,64], fp32
 size_t s4_attention_tc_bwd_workspace(int B, int H, int L) {
   const size_t qt = (size_t)(L + 127) / 128;
-  return ((size_t)B * H * L * 4 + 255) / 256 * 256 + (size_t)B * H * qt * 128 * 64 * 4;
+  return 2 * (((size_t)B * H * L * 4 + 255) / 256 * 256) + (size_t)B * H * qt * 128 * 64 * 4;
 }
 
 int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, float w, void* out,
@@ -1184,7 +1274,9 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
   const int q_tiles = (L + 127) / 128;
   float* delta = (float*)ws;
   const size_t delta_bytes = ((size_t)B * H * L * 4 + 255) / 256 * 256;
-  float* dq_accum = (float*)((char*)ws + delta_bytes);
+  float* ds_peel = (float*)((char*)ws + delta_bytes);
+  float* dq_accum = (float*)((char*)ws + 2 * delta_bytes);
+  const bool peel = (L % 128 == 1) && L > 128 && L <= 8192;
   const size_t acc_bytes = (size_t)B * H * q_tiles * 128 * 64 * 4;
   CUtensorMap tq, tdo;
   int rc;
@@ -1204,6 +1296,7 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
   p.dqkv = dqkv; p.dq_accum = dq_accum; p.lse = lse; p.delta = delta; p.u0 = u0; p.gate = gate;
   p.w = w; p.scale = 1.0f / sqrtf((float)hd);
   p.B = B; p.H = H; p.L = L; p.q_tiles = q_tiles;
+  p.kv_tiles = peel ? q_tiles - 1 : q_tiles;
   const size_t smem = 1024 + 12 * TILE_BYTES + 128 + (size_t)3 * q_tiles * 128 * 4;
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -1228,14 +1321,27 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
         (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, delta, B, H, L);
     if ((rc = s4_check_launch("attn_bwd_delta"))) return rc;
   }
+  if (peel) {
+    const size_t psmem = ((size_t)2 * L + 128 + 256) * sizeof(float);
+    static size_t psmem_set = 0;
+    if (psmem > 48 * 1024 && psmem > psmem_set) {
+      cudaFuncSetAttribute(attn_bwd_peel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+      psmem_set = psmem;
+    }
+    attn_bwd_peel_kernel<<<B * H, 256, psmem, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, lse,
+                                                    delta, u0, gate, w, p.scale, (__nv_bfloat16*)dqkv, ds_peel,
+                                                    B, H, L);
+    if ((rc = s4_check_launch("attn_bwd_peel"))) return rc;
+  }
   p.trace = g_trace;
-  if (g_trace.buf) attn_bwd_kernel<true><<<B * H * q_tiles, BWD_THREADS, smem, st>>>(tq, tdo, p);
-  else attn_bwd_kernel<false><<<B * H * q_tiles, BWD_THREADS, smem, st>>>(tq, tdo, p);
+  if (g_trace.buf) attn_bwd_kernel<true><<<B * H * p.kv_tiles, BWD_THREADS, smem, st>>>(tq, tdo, p);
+  else attn_bwd_kernel<false><<<B * H * p.kv_tiles, BWD_THREADS, smem, st>>>(tq, tdo, p);
   if ((rc = s4_check_launch("attn_bwd_tc"))) return rc;
   {
     const long long total = (long long)B * L * H * 8;
     attn_bwd_dq_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        dq_accum, (__nv_bfloat16*)dqkv, B, H, L, q_tiles, p.scale);
+        dq_accum, (__nv_bfloat16*)dqkv, B, H, L, q_tiles, p.scale, peel ? ds_peel : nullptr,
+        (const __nv_bfloat16*)qkv);
     rc = s4_check_launch("attn_bwd_dq_convert");
   }
   return rc;

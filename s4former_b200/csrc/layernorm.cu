@@ -106,7 +106,10 @@ ln_fwd_kernel(const T* __restrict__ x, const int* __restrict__ row_map,
 // Variant for many rows (the encoder's [B*L, D] launches): gamma / beta are NOT held in registers
 // (2 x VPL x VN = 48 of the ~100 registers of the kernel above) but re-read through L1 for every
 // row, so 3x more warps are resident and hide the ~1 us row round trip through L2.
-template <typename T, int VPL>
+// EXACT: D == VPL * 32 * VN (e.g. 768 = 3 x 32 x 8 bf16): every `vi < nvec` test is dropped at
+// compile time (they cost ~20 % of the instructions of this issue-bound kernel: predicates and
+// BSSY/BSYNC reconvergence pairs around each guarded group).
+template <typename T, int VPL, bool EXACT>
 __global__ void __launch_bounds__(128, 10)
 ln_fwd_lean_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
@@ -124,12 +127,12 @@ ln_fwd_lean_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int vi = lane + k * 32;
-      if (vi < nvec) v[k].load(xr + vi * VN);
+      if (EXACT || vi < nvec) v[k].load(xr + vi * VN);
     }
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int vi = lane + k * 32;
-      if (vi < nvec) {
+      if (EXACT || vi < nvec) {
 #pragma unroll
         for (int e = 0; e < VN; ++e) sum += v[k].get(e);
       }
@@ -139,7 +142,7 @@ ln_fwd_lean_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int vi = lane + k * 32;
-      if (vi < nvec) {
+      if (EXACT || vi < nvec) {
 #pragma unroll
         for (int e = 0; e < VN; ++e) {
           const float d = v[k].get(e) - mean;
@@ -156,7 +159,7 @@ ln_fwd_lean_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int vi = lane + k * 32;
-      if (vi < nvec) {
+      if (EXACT || vi < nvec) {
         float gm[VN], bt[VN];
         load_cols<VN>(gamma, vi, gm);
         load_cols<VN>(beta, vi, bt);
@@ -172,7 +175,7 @@ ln_fwd_lean_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
 // dx (written at the mapped source row of a pre-zeroed buffer when row_map != null).
 // dgamma/dbeta: every warp keeps register partials over its rows, the block folds them through
 // shared memory (plain stores, one slab per warp) and issues ONE global atomic per column.
-template <typename T, int VPL>
+template <typename T, int VPL, bool EXACT>
 __global__ void __launch_bounds__(128, 4)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __restrict__ row_map,
               const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -188,7 +191,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int vi = lane + k * 32;
-    if (vi < nvec) load_cols<VN>(gamma, vi, gm[k]);
+    if (EXACT || vi < nvec) load_cols<VN>(gamma, vi, gm[k]);
 #pragma unroll
     for (int e = 0; e < VN; ++e) { ag[k][e] = 0.f; ab[k][e] = 0.f; }
   }
@@ -202,7 +205,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int vi = lane + k * 32;
-      if (vi < nvec) {
+      if (EXACT || vi < nvec) {
         xv[k].load(xr + vi * VN);
         gv[k].load(gr + vi * VN);
         if (dres) rv[k].load(dres + (size_t)src * D + vi * VN);
@@ -215,7 +218,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
           const int vi = lane + k * 32;
-          if (vi < nvec) {
+          if (EXACT || vi < nvec) {
             prefetch_l1(x + (size_t)nsrc * D + vi * VN);
             prefetch_l1(dy + (size_t)nrow * D + vi * VN);
             if (dres) prefetch_l1(dres + (size_t)nsrc * D + vi * VN);
@@ -227,7 +230,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int vi = lane + k * 32;
-      if (vi < nvec) {
+      if (EXACT || vi < nvec) {
 #pragma unroll
         for (int e = 0; e < VN; ++e) {
           const float xh = (xv[k].get(e) - mu) * rs;
@@ -246,7 +249,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int vi = lane + k * 32;
-      if (vi < nvec) {
+      if (EXACT || vi < nvec) {
         Vec16<T> o;
 #pragma unroll
         for (int e = 0; e < VN; ++e) {
@@ -264,7 +267,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int vi = lane + k * 32;
-    if (vi < nvec) {
+    if (EXACT || vi < nvec) {
 #pragma unroll
       for (int e = 0; e < VN; ++e) {
         mine[vi * VN + e] = ag[k][e];
@@ -308,8 +311,13 @@ extern "C" int s4_layernorm_fwd(const void* x, const int* row_map, const float* 
     int lb = (rows + 3) / 4;
     const int lcap = s4_num_sms() * 10;
     if (lb > lcap) lb = lcap;
-    LN_DISPATCH_VPL(vpl, (ln_fwd_lean_kernel<__nv_bfloat16, VPL><<<lb, FT, 0, stream>>>(
-        (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, D, eps)));
+    if (D == vpl * 32 * vn) {
+      LN_DISPATCH_VPL(vpl, (ln_fwd_lean_kernel<__nv_bfloat16, VPL, true><<<lb, FT, 0, stream>>>(
+          (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, D, eps)));
+    } else {
+      LN_DISPATCH_VPL(vpl, (ln_fwd_lean_kernel<__nv_bfloat16, VPL, false><<<lb, FT, 0, stream>>>(
+          (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, D, eps)));
+    }
     return s4_check_launch("layernorm_fwd");
   }
   if (dtype == S4_BF16) {
@@ -340,22 +348,28 @@ extern "C" int s4_layernorm_bwd(const void* dy, const void* x, const int* row_ma
   if (smem > 48 * 1024) {
     static bool attr_done = false;
     if (!attr_done) {
-      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(ln_bwd_kernel<float, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(ln_bwd_kernel<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
       attr_done = true;
     }
   }
   const int vpl = (D / vn + 31) / 32;
+  const bool exact = D == vpl * 32 * vn;
+#define S4_LN_BWD(TT, EX)                                                                      \
+  LN_DISPATCH_VPL(vpl, (ln_bwd_kernel<TT, VPL, EX><<<blocks, BT, smem, stream>>>(              \
+      (const TT*)dy, (const TT*)x, row_map, gamma, mean, rstd, (const TT*)dres, (TT*)dx, dgamma, \
+      dbeta, rows, D)))
   if (dtype == S4_BF16) {
-    LN_DISPATCH_VPL(vpl, (ln_bwd_kernel<__nv_bfloat16, VPL><<<blocks, BT, smem, stream>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, row_map, gamma, mean, rstd,
-        (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dgamma, dbeta, rows, D)));
+    if (exact) S4_LN_BWD(__nv_bfloat16, true); else S4_LN_BWD(__nv_bfloat16, false);
   } else {
-    LN_DISPATCH_VPL(vpl, (ln_bwd_kernel<float, VPL><<<blocks, BT, smem, stream>>>(
-        (const float*)dy, (const float*)x, row_map, gamma, mean, rstd, (const float*)dres,
-        (float*)dx, dgamma, dbeta, rows, D)));
+    if (exact) S4_LN_BWD(float, true); else S4_LN_BWD(float, false);
   }
+#undef S4_LN_BWD
   return s4_check_launch("layernorm_bwd");
 }
