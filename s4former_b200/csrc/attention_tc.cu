@@ -1062,81 +1062,139 @@ attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat1
   delta[((size_t)b * H + hh) * L + q] = acc;
 }
 
-// PEELED KEY (L = 128 k + 1: a ViT's cls token + square patch grid).  Key L-1 would be a 128-key
-// tile of its own with ONE valid key: a CTA walking all query tiles with full-size MMAs for 1/128
-// of their rows (1 of 9 CTAs at L = 1025, 11 % of the kernel).  Its contribution is a rank-1 term
-// instead, computed on the CUDA cores by one small block per (batch, head):
+// PEELED KEY (L = 128 k + 1: a ViT's cls token + square patch grid).  Key x = L-1 would be a
+// 128-key tile of its own with ONE valid key: a CTA walking all query tiles with full-size MMAs for
+// 1/128 of their rows (1 of 9 CTAs at L = 1025: 11 % of the kernel).  Its contribution is a rank-1
+// term instead, computed on the CUDA cores in the SAME pass that forms delta = rowsum(dO * O):
 //   p[q]  = 2^(c1 Q_q.K_x + w gate_q u0_x log2e - lse_q log2e)   ds[q] = p[q] (dO_q.V_x - delta_q)
-//   dV_x  = sum_q p[q] dO_q     dK_x = scale sum_q ds[q] Q_q     dQ_q += ds[q] K_x  (added by the
-//   dq convert kernel from ds_peel[b,h,q])
-// p / ds are rounded to bf16 before they are used, as the tensor-core path rounds P^T / dS^T.
-__global__ void __launch_bounds__(256)
-attn_bwd_peel_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
-                     const float* __restrict__ lse, const float* __restrict__ delta,
-                     const float* __restrict__ u0, const float* __restrict__ gate, float w, float scale,
-                     __nv_bfloat16* __restrict__ dqkv, float* __restrict__ ds_peel, int B, int H, int L) {
-  extern __shared__ float psm[];            // [L] p, [L] ds, [64] K_x, [64] V_x, [4][128] partials
-  float* ps = psm;
-  float* dss = psm + L;
-  float* kx = dss + L;
-  float* vx = kx + 64;
-  float* part = vx + 64;
-  const int bh = blockIdx.x, h = bh % H, b = bh / H;
-  const int D3 = 3 * H * HD, D = H * HD;
+//   dV_x  = sum_q p[q] dO_q     dK_x = scale sum_q ds[q] Q_q     dQ_q += ds[q] K_x
+// p / ds are rounded to bf16 before use, as the tensor-core path rounds P^T / dS^T.
+// Block = 32 queries (lanes) x H heads (warps) of one image: the block reads 32 contiguous rows of
+// dO / O / qkv (a per-(b,h) kernel read 128 B out of every 4.6 KB and ran at 25 % of the DRAM rate).
+// The sums over queries are a warp reduce-scatter (lane l ends with dims 2l, 2l+1) and one fp32
+// atomic per (warp, dim) into peel_acc[b,h,{dV,dK},64]; ds goes to ds_peel[b,h,q] for the dQ term,
+// which the dq convert kernel adds (that kernel also writes the dK_x / dV_x rows).
+// A WARP walks QPW consecutive query rows of one image; lane l owns the 16-byte chunks l, l+32, l+64
+// ... of a row (8 head dims of head (l/8) + 4k): every load is a fully coalesced row segment, the
+// per-head dot products are xor-reductions over aligned 8-lane groups, and the sums over queries
+// stay in the lane's registers (its dims never change) until one atomic per (lane, dim) at the end.
+constexpr int DP_QPW = 16;       // queries per warp
+constexpr int DP_WARPS = 4;      // warps per block
+
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(h2[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+
+template <int NCH>     // 16-byte chunks per lane: ceil(H * 8 / 32)
+__global__ void __launch_bounds__(DP_WARPS * 32)
+attn_bwd_delta_peel_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                           const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ lse,
+                           const float* __restrict__ u0, const float* __restrict__ gate, float w, float scale,
+                           float* __restrict__ delta, float* __restrict__ ds_peel, float* __restrict__ peel_acc,
+                           int B, int H, int L, int peel) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int qgroups = (L + DP_QPW * DP_WARPS - 1) / (DP_QPW * DP_WARPS);
+  const int b = blockIdx.x / qgroups;
+  const int q0 = ((blockIdx.x % qgroups) * DP_WARPS + wib) * DP_QPW;
+  const int D = H * HD, D3 = 3 * D;
+  const int nchunks = H * 8;
   const int x = L - 1;
-  const __nv_bfloat16* qkv_b = qkv + (size_t)b * L * D3;
-  const __nv_bfloat16* do_b = dout + (size_t)b * L * D;
-  if (threadIdx.x < 64) kx[threadIdx.x] = __bfloat162float(qkv_b[(size_t)x * D3 + (H + h) * HD + threadIdx.x]);
-  else if (threadIdx.x < 128) vx[threadIdx.x - 64] = __bfloat162float(qkv_b[(size_t)x * D3 + (2 * H + h) * HD + threadIdx.x - 64]);
-  __syncthreads();
+  float kx[NCH][8], vx[NCH][8], accv[NCH][8], acck[NCH][8];
+  if (peel) {
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nchunks) {
+        const __nv_bfloat16* xr = qkv + ((size_t)b * L + x) * D3;
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(xr + D + c * 8)), kx[k]);
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(xr + 2 * D + c * 8)), vx[k]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { accv[k][e] = 0.f; acck[k][e] = 0.f; }
+    }
+  }
   const float c1 = scale * LOG2E;
-  const float u0x = u0 ? u0[(size_t)b * L + x] : 0.f;
-  const float* lse_b = lse + ((size_t)b * H + h) * L;
-  const float* dl_b = delta + ((size_t)b * H + h) * L;
-  for (int q = threadIdx.x; q < L; q += blockDim.x) {
-    const uint4* qr = reinterpret_cast<const uint4*>(qkv_b + (size_t)q * D3 + h * HD);
-    const uint4* dr = reinterpret_cast<const uint4*>(do_b + (size_t)q * D + h * HD);
-    float s = 0.f, dp = 0.f;
+  const float u0x = (peel && u0) ? u0[(size_t)b * L + x] : 0.f;
+  for (int qi = 0; qi < DP_QPW; ++qi) {
+    const int q = q0 + qi;
+    if (q >= L) break;                      // (warp-uniform; the barrier below is reached by every warp)
+    const size_t bq = (size_t)b * L + q;
+    float wg = 0.f;
+    if (peel && u0) wg = w * LOG2E * (gate ? gate[bq] : 1.f);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 qa = __ldg(qr + c), da = __ldg(dr + c);
-      const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qa);
-      const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&da);
+    for (int k = 0; k < NCH; ++k) {
+      const int c = lane + 32 * k;
+      const bool cok = c < nchunks;
+      const int hh = cok ? (c >> 3) : 0;
+      float dof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, of[8] = {0, 0, 0, 0, 0, 0, 0, 0}, qf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (cok) {
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(dout + bq * D + c * 8)), dof);
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(out + bq * D + c * 8)), of);
+        if (peel) bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(qkv + bq * D3 + c * 8)), qf);
+      }
+      float dl = 0.f, sd = 0.f, dp = 0.f;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 qf = __bfloat1622float2(q2[e]), df = __bfloat1622float2(d2[e]);
-        s = fmaf(qf.x, kx[c * 8 + 2 * e], s);
-        s = fmaf(qf.y, kx[c * 8 + 2 * e + 1], s);
-        dp = fmaf(df.x, vx[c * 8 + 2 * e], dp);
-        dp = fmaf(df.y, vx[c * 8 + 2 * e + 1], dp);
+      for (int e = 0; e < 8; ++e) dl = fmaf(dof[e], of[e], dl);
+      dl = group8_sum(dl);
+      if (cok && (lane & 7) == 0) delta[((size_t)b * H + hh) * L + q] = dl;
+      if (peel) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          sd = fmaf(qf[e], kx[k][e], sd);
+          dp = fmaf(dof[e], vx[k][e], dp);
+        }
+        sd = group8_sum(sd);
+        dp = group8_sum(dp);
+        if (cok) {
+          const float pe = tc::ex2(fmaf(sd, c1, fmaf(wg, u0x, -lse[((size_t)b * H + hh) * L + q] * LOG2E)));
+          const float pr = __bfloat162float(__float2bfloat16_rn(pe));
+          const float dsr = __bfloat162float(__float2bfloat16_rn(pe * (dp - dl)));
+          if ((lane & 7) == 0) ds_peel[((size_t)b * H + hh) * L + q] = dsr;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            accv[k][e] = fmaf(pr, dof[e], accv[k][e]);
+            acck[k][e] = fmaf(dsr, qf[e], acck[k][e]);
+          }
+        }
       }
     }
-    float wg = 0.f;
-    if (u0) wg = w * LOG2E * (gate ? gate[(size_t)b * L + q] : 1.f);
-    const float pe = tc::ex2(fmaf(s, c1, fmaf(wg, u0x, -lse_b[q] * LOG2E)));
-    const float dsv = pe * (dp - dl_b[q]);
-    const float pr = __bfloat162float(__float2bfloat16_rn(pe));
-    const float dr_ = __bfloat162float(__float2bfloat16_rn(dsv));
-    ps[q] = pr;
-    dss[q] = dr_;
-    ds_peel[((size_t)b * H + h) * L + q] = dr_;
   }
-  __syncthreads();
-  // dV_x[d] = sum_q p[q] dO[q][d] (threads 0..127: 2 interleaved q-parts x 64 dims), dK_x likewise
-  // from Q (threads 128..255)
-  const int d = threadIdx.x & 63, partq = (threadIdx.x >> 6) & 1, which = threadIdx.x >> 7;
-  float acc = 0.f;
-  if (which == 0) {
-    for (int q = partq; q < L; q += 2) acc = fmaf(ps[q], __bfloat162float(do_b[(size_t)q * D + h * HD + d]), acc);
-  } else {
-    for (int q = partq; q < L; q += 2) acc = fmaf(dss[q], __bfloat162float(qkv_b[(size_t)q * D3 + h * HD + d]), acc);
-  }
-  part[threadIdx.x] = acc;
-  __syncthreads();
-  if (partq == 0) {
-    const float tot = part[threadIdx.x] + part[threadIdx.x + 64];
-    __nv_bfloat16* orow = dqkv + ((size_t)b * L + x) * D3 + (which == 0 ? 2 * H + h : H + h) * HD;
-    orow[d] = __float2bfloat16_rn(which == 0 ? tot : tot * scale);
+  if (peel) {
+    // fold the block's warps through shared memory first: one global atomic per (block, head, dim)
+    // (4.9 M same-address atomics from every lane made this kernel 3x slower than its loads)
+    extern __shared__ float red[];              // [DP_WARPS][H * 128]
+    float* mine = red + (size_t)wib * H * 128;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nchunks) {
+        float* dst = mine + (c >> 3) * 128 + (c & 7) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          dst[e] = accv[k][e];
+          dst[64 + e] = acck[k][e];
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * 128; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < DP_WARPS; ++w2) t += red[(size_t)w2 * H * 128 + i];
+      atomicAdd(peel_acc + (size_t)b * H * 128 + i, t);
+    }
   }
 }
 
@@ -1145,7 +1203,7 @@ attn_bwd_peel_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 __global__ void __launch_bounds__(256)
 attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, int B, int H,
                            int L, int q_tiles, float scale, const float* __restrict__ ds_peel,
-                           const __nv_bfloat16* __restrict__ qkv) {
+                           const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ peel_acc) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, q, h, 8-column group)
   const long long total = (long long)B * L * H * 8;
   if (idx >= total) return;
@@ -1173,6 +1231,17 @@ attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restr
   v.z = pack_bf16(hi.x * scale, hi.y * scale);
   v.w = pack_bf16(hi.z * scale, hi.w * scale);
   *reinterpret_cast<uint4*>(dqkv + (size_t)bq * 3 * H * HD + hh * HD + g8 * 8) = v;
+  if (ds_peel && q == L - 1) {     // the peeled key's own gradient rows: dK_x (scaled) and dV_x
+    const float* pa = peel_acc + ((size_t)b * H + hh) * 128 + g8 * 8;
+    uint4 dv, dk;
+    dv.x = pack_bf16(pa[0], pa[1]); dv.y = pack_bf16(pa[2], pa[3]);
+    dv.z = pack_bf16(pa[4], pa[5]); dv.w = pack_bf16(pa[6], pa[7]);
+    dk.x = pack_bf16(pa[64] * scale, pa[65] * scale); dk.y = pack_bf16(pa[66] * scale, pa[67] * scale);
+    dk.z = pack_bf16(pa[68] * scale, pa[69] * scale); dk.w = pack_bf16(pa[70] * scale, pa[71] * scale);
+    __nv_bfloat16* row = dqkv + (size_t)bq * 3 * H * HD;
+    *reinterpret_cast<uint4*>(row + (H + hh) * HD + g8 * 8) = dk;
+    *reinterpret_cast<uint4*>(row + (2 * H + hh) * HD + g8 * 8) = dv;
+  }
 }
 
 TraceCfg g_trace{nullptr, 0};
@@ -1208,7 +1277,8 @@ bool s4_attention_tc_bwd_supported(int B, int H, int L, int hd, int dtype) {
 // workspace of the fused backward: delta [B,H,L] + dq_accum [B,H,q_tiles,128,64], fp32
 size_t s4_attention_tc_bwd_workspace(int B, int H, int L) {
   const size_t qt = (size_t)(L + 127) / 128;
-  return 2 * (((size_t)B * H * L * 4 + 255) / 256 * 256) + (size_t)B * H * qt * 128 * 64 * 4;
+  return 2 * (((size_t)B * H * L * 4 + 255) / 256 * 256) + (size_t)B * H * qt * 128 * 64 * 4 +
+         (size_t)B * H * 128 * 4;
 }
 
 int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, float w, void* out,
@@ -1276,7 +1346,7 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
   const size_t delta_bytes = ((size_t)B * H * L * 4 + 255) / 256 * 256;
   float* ds_peel = (float*)((char*)ws + delta_bytes);
   float* dq_accum = (float*)((char*)ws + 2 * delta_bytes);
-  const bool peel = (L % 128 == 1) && L > 128 && L <= 8192;
+  const bool peel = (L % 128 == 1) && L > 128 && H <= 16;
   const size_t acc_bytes = (size_t)B * H * q_tiles * 128 * 64 * 4;
   CUtensorMap tq, tdo;
   int rc;
@@ -1310,28 +1380,27 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
     smem_set = smem;
   }
   S4ProfScope prof("attn_bwd_tc", 8.0 * B * H * (double)L * L * HD, 0, st);
-  cudaError_t e = cudaMemsetAsync(dq_accum, 0, acc_bytes, st);
+  float* peel_acc = (float*)((char*)dq_accum + acc_bytes);      // [B,H,2,64], zeroed with dq_accum
+  cudaError_t e = cudaMemsetAsync(dq_accum, 0, acc_bytes + (size_t)B * H * 128 * 4, st);
   if (e != cudaSuccess) {
     s4_set_error("attention_tc_bwd: memset failed: %s", cudaGetErrorString(e));
     return S4_ERR_CUDA;
   }
-  {
+  if (H <= 16) {
+    const int qgroups = (L + DP_QPW * DP_WARPS - 1) / (DP_QPW * DP_WARPS);
+    const int nch = (H * 8 + 31) / 32;
+#define S4_DP(N)                                                                                         \
+  attn_bwd_delta_peel_kernel<N><<<B * qgroups, DP_WARPS * 32, peel ? (size_t)DP_WARPS * H * 128 * 4 : 0, st>>>(                                    \
+      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)qkv, lse, u0, gate, w, \
+      p.scale, delta, ds_peel, peel_acc, B, H, L, peel ? 1 : 0)
+    if (nch <= 1) S4_DP(1); else if (nch == 2) S4_DP(2); else if (nch == 3) S4_DP(3); else S4_DP(4);
+#undef S4_DP
+    if ((rc = s4_check_launch("attn_bwd_delta"))) return rc;
+  } else {
     const long long total = (long long)B * L * H;
     attn_bwd_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, delta, B, H, L);
     if ((rc = s4_check_launch("attn_bwd_delta"))) return rc;
-  }
-  if (peel) {
-    const size_t psmem = ((size_t)2 * L + 128 + 256) * sizeof(float);
-    static size_t psmem_set = 0;
-    if (psmem > 48 * 1024 && psmem > psmem_set) {
-      cudaFuncSetAttribute(attn_bwd_peel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-      psmem_set = psmem;
-    }
-    attn_bwd_peel_kernel<<<B * H, 256, psmem, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, lse,
-                                                    delta, u0, gate, w, p.scale, (__nv_bfloat16*)dqkv, ds_peel,
-                                                    B, H, L);
-    if ((rc = s4_check_launch("attn_bwd_peel"))) return rc;
   }
   p.trace = g_trace;
   if (g_trace.buf) attn_bwd_kernel<true><<<B * H * p.kv_tiles, BWD_THREADS, smem, st>>>(tq, tdo, p);
@@ -1341,7 +1410,7 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
     const long long total = (long long)B * L * H * 8;
     attn_bwd_dq_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         dq_accum, (__nv_bfloat16*)dqkv, B, H, L, q_tiles, p.scale, peel ? ds_peel : nullptr,
-        (const __nv_bfloat16*)qkv);
+        (const __nv_bfloat16*)qkv, peel_acc);
     rc = s4_check_launch("attn_bwd_dq_convert");
   }
   return rc;
