@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument('--no-extra-configs', action='store_true',
                     help='skip the short runs of BASELINE configs 1/2/4 (sup-only, MT, 768x768/19)')
     ap.add_argument('--no-parity', action='store_true', help='skip the in-bench parity block')
+    ap.add_argument('--bucket-mb', type=float, default=25.0, help='gradient all-reduce bucket size (N > 1)')
     ap.add_argument('--no-graph', action='store_true',
                     help='launch every kernel from the host each step instead of replaying the captured CUDA graph')
     return ap.parse_args()
@@ -404,7 +405,7 @@ def main():
     model.backbone_ema.load_state_dict(model.backbone.state_dict())
     model.decode_head_ema.load_state_dict(model.decode_head.state_dict())
     model = model.to(dev).train()
-    step = TrainStep(model, cuda_graph=not a.no_graph, graph_warmup=2)
+    step = TrainStep(model, cuda_graph=not a.no_graph, graph_warmup=2, bucket_mb=a.bucket_mb)
 
     img, gt, metas = make_batch(a.sup, n_unsup, a.size, a.classes, seed=1999 + rank)
     img_h, gt_h = img.pin_memory(), gt.pin_memory()
@@ -483,7 +484,8 @@ def main():
         launches = step.graph_kernel_launches
     else:
         launches = (lib.s4_launch_count() - l0) // a.steps
-    run_e2e(0)
+    for i in range(3):          # both staging slots warm (each has its own captured graph)
+        run_e2e(i, 3)
     drain_e2e()
     ms_e2e = timed(lambda i: run_e2e(i, a.steps), a.steps, after=drain_e2e)
     clk = clocks.stop() if rank == 0 else None
@@ -516,6 +518,7 @@ def main():
         without the collective teardown."""
         if step is not None:
             step._graph = None
+            step._graphs = {}
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -583,6 +586,7 @@ def main():
     if world == 1 and not (a.no_gpu_eager and a.no_extra_configs and a.no_cpu_baseline):
         # the comparison legs need the memory: drop this arm's model, graph and staging buffers
         step._graph = None
+        step._graphs = {}
         step = model = img_d = gt_d = None
         import gc
         gc.collect()
