@@ -45,6 +45,8 @@ def parse_args():
                     help='skip the short runs of BASELINE configs 1/2/4 (sup-only, MT, 768x768/19)')
     ap.add_argument('--no-parity', action='store_true', help='skip the in-bench parity block')
     ap.add_argument('--bucket-mb', type=float, default=25.0, help='gradient all-reduce bucket size (N > 1)')
+    ap.add_argument('--norm', default='SyncBN', choices=['SyncBN', 'BN'],
+                    help='BN = per-rank statistics (diagnostic: isolates the cost of the SyncBN collectives)')
     ap.add_argument('--no-graph', action='store_true',
                     help='launch every kernel from the host each step instead of replaying the captured CUDA graph')
     return ap.parse_args()
@@ -398,7 +400,7 @@ def main():
     ops.set_compute_dtype(torch.bfloat16 if a.dtype == 'bf16' else torch.float32)
 
     n_unsup = a.unsup if a.variant != 'sup' else 0
-    cfg = configs.setr_pup_deit_base(a.variant, a.size, a.classes, norm='SyncBN')
+    cfg = configs.setr_pup_deit_base(a.variant, a.size, a.classes, norm=a.norm)
     torch.manual_seed(1999)
     model = s4.build_segmentor(cfg)
     model.init_weights()

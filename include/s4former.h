@@ -304,6 +304,21 @@ int s4_accumulate_crop(const float* crop, float* preds, float* count, int B, int
 int s4_intersect_union(const long long* pred, const long long* label, long long n, int num_classes,
                        long long ignore_index, long long* hist3, cudaStream_t stream);
 
+/* ---- GPU-side input pipeline -------------------------------------
+ * configs/setr/..._MT_w_ours.py:42-126 strong / weak / sup branch pipelines after RandomCrop / RandomFlip:
+ * PhotoMetricDistortion (transforms.py:1165-1272), Normalize (:572-604), Pad (:484-565),
+ * DefaultFormatBundle (formatting.py:202-225) for every branch in one launch.
+ * crops[i] -> device uint8 [h_i, w_i, 3] BGR, labels[i] -> device uint8 [h_i, w_i] or NULL, crop_hw = {h_0, w_0, ...};
+ * branch j reads crop crop_of[j] with the distortion draws pmd_params[j] (9 x 4 bytes:
+ * do_brightness, beta, mode, do_contrast, alpha_c, do_saturation, alpha_s, do_hue, hue_delta);
+ * out_img [n_branches, 3, pad_h, pad_w] f32, out_label [n_branches, 1, pad_h, pad_w] i64 (may be NULL),
+ * out_u8 (may be NULL): the distorted image before normalisation, [n_branches, pad_h, pad_w, 3]. */
+int s4_branch_pipeline(const void* const* crops, const void* const* labels, const int* crop_hw,
+                       const int* crop_of, const void* pmd_params, const float* mean, const float* stdinv,
+                       int to_rgb, int seg_pad_val, float* out_img, long long* out_label, void* out_u8,
+                       int n_branches, int pad_h, int pad_w, cudaStream_t stream);
+int s4_pmd_params_size(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,8 @@ _SPEC = {
     's4_softmax_argmax_nchw': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     's4_accumulate_crop': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     's4_intersect_union': (_I, [_P, _P, _L, _I, _L, _P, _P]),
+    's4_branch_pipeline': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _P]),
+    's4_pmd_params_size': (_I, []),
     's4_sgd_ema_multi_tensor': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P]),
 }
 

@@ -230,7 +230,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc::fence_before_sync();
   if (PAIR) tc::cluster_sync();     // peer barriers initialised before any remote arrive / TMA signal
-  else __syncthreads();
+  // (CTA barrier in both modes: compute-sanitizer's racecheck does not credit barrier.cluster for the
+  // tcgen05.alloc -> shared-memory slot -> read hand-over below and reported it as a hazard)
+  __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
