@@ -311,10 +311,11 @@ int s4_intersect_union(const long long* pred, const long long* label, long long 
  * crops[i] -> device uint8 [h_i, w_i, 3] BGR, labels[i] -> device uint8 [h_i, w_i] or NULL, crop_hw = {h_0, w_0, ...};
  * branch j reads crop crop_of[j] with the distortion draws pmd_params[j] (9 x 4 bytes:
  * do_brightness, beta, mode, do_contrast, alpha_c, do_saturation, alpha_s, do_hue, hue_delta);
+ * mean: 3 floats, stdinv: 3 DOUBLES (= 1 / double(float(std)), what cv2.multiply is handed);
  * out_img [n_branches, 3, pad_h, pad_w] f32, out_label [n_branches, 1, pad_h, pad_w] i64 (may be NULL),
  * out_u8 (may be NULL): the distorted image before normalisation, [n_branches, pad_h, pad_w, 3]. */
 int s4_branch_pipeline(const void* const* crops, const void* const* labels, const int* crop_hw,
-                       const int* crop_of, const void* pmd_params, const float* mean, const float* stdinv,
+                       const int* crop_of, const void* pmd_params, const float* mean, const double* stdinv,
                        int to_rgb, int seg_pad_val, float* out_img, long long* out_label, void* out_u8,
                        int n_branches, int pad_h, int pad_w, cudaStream_t stream);
 int s4_pmd_params_size(void);

@@ -18,7 +18,8 @@
 //                               truncation, which is what OpenCV's SIMD row path computes -- OpenCV's own
 //                               scalar tail rounds instead, so the reference is position dependent here
 //                               (tests/test_pipeline_gpu.py: <= 1 LSB on < 0.05 % of the pixels).
-//   normalize                 = (float(x) - float(mean)) * float(1 / double(std)), BGR -> RGB first
+//   normalize                 = float(double(float(x) - float(mean)) * (1 / double(std))), BGR -> RGB first
+//                               (cv2.multiply keeps its scalar in double: pinned against OpenCV, bit-exact)
 //   pad                       = 0.0 for the image (after normalisation), seg_pad_val for the labels
 #include <algorithm>
 
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256)
 branch_pipeline_kernel(const unsigned char* const* __restrict__ crops, const unsigned char* const* __restrict__ labels,
                        const int* __restrict__ crop_hw, const int* __restrict__ crop_of,
                        const S4PmdParams* __restrict__ params, const float* __restrict__ mean_rgb,
-                       const float* __restrict__ stdinv_rgb, int to_rgb, int seg_pad, float* __restrict__ out_img,
+                       const double* __restrict__ stdinv_rgb, int to_rgb, int seg_pad, float* __restrict__ out_img,
                        long long* __restrict__ out_lab, unsigned char* __restrict__ out_u8, int PH, int PW) {
   const int br = blockIdx.y;
   const int ci = crop_of[br];
@@ -126,9 +127,9 @@ branch_pipeline_kernel(const unsigned char* const* __restrict__ crops, const uns
         q[0] = (unsigned char)b; q[1] = (unsigned char)g; q[2] = (unsigned char)r;
       }
       const int c0 = to_rgb ? r : b, c2 = to_rgb ? b : r;
-      o0 = __fmul_rn(__fsub_rn((float)c0, mean_rgb[0]), stdinv_rgb[0]);
-      o1 = __fmul_rn(__fsub_rn((float)g, mean_rgb[1]), stdinv_rgb[1]);
-      o2 = __fmul_rn(__fsub_rn((float)c2, mean_rgb[2]), stdinv_rgb[2]);
+      o0 = (float)((double)__fsub_rn((float)c0, mean_rgb[0]) * stdinv_rgb[0]);
+      o1 = (float)((double)__fsub_rn((float)g, mean_rgb[1]) * stdinv_rgb[1]);
+      o2 = (float)((double)__fsub_rn((float)c2, mean_rgb[2]) * stdinv_rgb[2]);
       if (labels && labels[ci]) lab = labels[ci][(size_t)y * w + x];
     } else if (out_u8) {
       unsigned char* q = out_u8 + ((size_t)br * plane + i) * 3;
@@ -141,7 +142,7 @@ branch_pipeline_kernel(const unsigned char* const* __restrict__ crops, const uns
 }
 
 extern "C" int s4_branch_pipeline(const void* const* crops, const void* const* labels, const int* crop_hw,
-                                  const int* crop_of, const void* pmd_params, const float* mean, const float* stdinv,
+                                  const int* crop_of, const void* pmd_params, const float* mean, const double* stdinv,
                                   int to_rgb, int seg_pad_val, float* out_img, long long* out_label, void* out_u8,
                                   int n_branches, int pad_h, int pad_w, cudaStream_t stream) {
   S4ProfScope prof_("branch_pipeline", 0.0, 1, stream);

@@ -65,7 +65,7 @@ class BranchPipeline:
         std32 = np.asarray(std, dtype=np.float32)
         # mmcv.imnormalize_: stdinv = 1 / np.float64(std); cv2 applies it to the float32 image in float32
         self.mean = torch.from_numpy(mean32.copy()).to(self.device)
-        self.stdinv = torch.from_numpy((1.0 / std32.astype(np.float64)).astype(np.float32)).to(self.device)
+        self.stdinv = torch.from_numpy(1.0 / std32.astype(np.float64)).to(self.device)          # float64
         self._stage = None
 
     def draw(self, n_sup, n_unsup):
@@ -128,7 +128,7 @@ class BranchPipeline:
             base = dict(metas[ci]) if metas is not None else dict(filename=f'crop_{ci}.jpg')
             h, w = hw[2 * ci], hw[2 * ci + 1]
             base.update(tag=t, img_shape=(h, w, 3), pad_shape=(PH, PW, 3),
-                        img_norm_cfg=dict(mean=self.mean.cpu().numpy(), std=1.0 / self.stdinv.cpu().numpy(),
+                        img_norm_cfg=dict(mean=self.mean.cpu().numpy(), std=(1.0 / self.stdinv.cpu().numpy()).astype(np.float32),
                                           to_rgb=self.to_rgb))
             base.setdefault('ori_shape', (h, w, 3))
             base.setdefault('scale_factor', 1.0)

@@ -51,15 +51,24 @@ def test_opencv_hsv2bgr_is_position_dependent():
     assert np.abs(alone.astype(int) - in_row.astype(int)).max() == 1
 
 
-def _check(u8_got, u8_want, x_got, x_want, stdinv_max):
+def _check(u8_got, u8_want, x_got, x_want, stdinv_max, max_frac=1e-3, max_lsb=1):
     d = np.abs(u8_got.astype(int) - u8_want.astype(int))
-    assert d.max() <= 1, d.max()
+    assert d.max() <= max_lsb, d.max()
     frac = float((d > 0).mean())
-    assert frac < 1e-3, frac
+    assert frac <= max_frac, frac
+    assert float(d.mean()) <= 0.25
     dx = np.abs(x_got - x_want)
-    assert dx.max() <= stdinv_max * 1.0001 + 1e-6            # one LSB of the uint8 image, normalised
-    assert float((dx > 1e-6).mean()) < 1e-3
+    assert dx.max() <= max_lsb * stdinv_max * 1.0001 + 1e-6  # LSBs of the uint8 image, normalised
+    assert float((dx > 0).mean()) <= max_frac                # (exactly equal wherever the uint8 image is)
     return frac
+
+
+def _u8_from_normalised(x, h, w):
+    """The distorted uint8 image behind a reference output [3, H, W] (RGB, normalised): exact inverse."""
+    mean = np.asarray(NORM['mean'], dtype=np.float32).reshape(3, 1, 1)
+    std = np.asarray(NORM['std'], dtype=np.float32).reshape(3, 1, 1)
+    rgb = np.rint(x[:, :h, :w].astype(np.float64) * std + mean).astype(np.uint8)
+    return np.ascontiguousarray(rgb[::-1].transpose(1, 2, 0))       # -> HWC, BGR
 
 
 @pytest.mark.gpu
@@ -75,12 +84,11 @@ def test_branch_pipeline_vs_reference_golden(G):
         assert torch.equal(gt[0, 0].cpu(), c['gt'][0].long()) and torch.equal(gt[1], gt[0])
         for j, key in enumerate(('student', 'teacher')):
             want = c[key].numpy()
-            # the golden's distorted uint8 image, recovered through the oracle with the same draws
-            np.random.seed(c['seed'])
-            ps = [draw_pmd_params(), draw_pmd_params()][j]
-            d_want = PO.photometric_distortion(img.copy(), ps)
+            # the reference's distorted uint8 image, recovered from ITS normalised output (the fixture was
+            # produced where OpenCV's HSV->BGR takes the truncating SIMD path the kernel restates)
+            d_want = _u8_from_normalised(want, h, w)
             _check(u8[j, :h, :w].cpu().numpy(), d_want, x[j].cpu().numpy(), want, 1 / 57.12)
-            assert float(x[j, :, h:].abs().max()) == 0 and float(x[j, :, :, w:].abs().max()) == 0
+            assert float(x[j, :, h:].abs().sum()) == 0 and float(x[j, :, :, w:].abs().sum()) == 0     # Pad: zeros
         assert metas[0]['img_shape'] == (h, w, 3) and metas[0]['pad_shape'] == (*G['pad'], 3)
 
 
@@ -100,11 +108,21 @@ def test_branch_pipeline_train_shape_vs_oracle():
     assert x.shape == (24, 3, 512, 512) and gt.shape == (24, 1, 512, 512) and gt.dtype == torch.int64
     assert [m['tag'] for m in metas] == ['sup'] * 8 + ['unsup_student', 'unsup_teacher'] * 8
     crop_of = list(range(8)) + [8 + i // 2 for i in range(16)]
-    worst = 0.0
     for j in range(24):
         c, lb = crops[crop_of[j]], labs[crop_of[j]]
         xw, gw, dw = PO.branch(c, lb, params[j], (512, 512), **NORM)
         h, w = c.shape[:2]
-        worst = max(worst, _check(u8[j, :h, :w].cpu().numpy(), dw, x[j].cpu().numpy(), xw, 1 / 57.12))
+        # against THIS host's OpenCV, whose HSV->BGR rounding depends on the CPU's SIMD dispatch and on the
+        # pixel's position in its row (vector body truncates, scalar tail rounds): one LSB per HSV round trip,
+        # two round trips (saturation, hue), and a flipped LSB can move the second trip's H / S by one more
+        _check(u8[j, :h, :w].cpu().numpy(), dw, x[j].cpu().numpy(), xw, 1 / 57.12, max_frac=1.0, max_lsb=4)
         assert np.array_equal(gt[j].cpu().numpy(), gw)
-    assert worst < 1e-3
+    # without the two HSV steps every remaining operation is exactly defined: bit-exact
+    p2 = [(p[0], p[1], p[2], p[3], p[4], 0, 1.0, 0, 0) for p in params]
+    x2, gt2, _, u82 = pipe(crops[:8], labs[:8], crops[8:], labs[8:], params=p2, want_u8=True)
+    for j in range(24):
+        c, lb = crops[crop_of[j]], labs[crop_of[j]]
+        xw, gw, dw = PO.branch(c, lb, p2[j], (512, 512), **NORM)
+        h, w = c.shape[:2]
+        assert np.array_equal(u82[j, :h, :w].cpu().numpy(), dw), j
+        assert np.array_equal(x2[j].cpu().numpy(), xw), j
