@@ -106,10 +106,12 @@ int s4_layernorm_fwd(const void* x, const int* row_map, const float* gamma, cons
                      cudaStream_t stream);
 /* dx is written at the mapped source rows (pre-zero it when row_map skips rows); dres (optional,
  * indexed like dx) is added to it: the gradient arriving over the residual connection;
- * dgamma/dbeta are accumulated (+=). */
+ * dgamma/dbeta are accumulated (+=).  dres_sum (optional fp32 [D], needs dres and no row_map) is
+ * accumulated with the column sums of dres: the bias gradient of the linear layer whose output
+ * joined the residual stream there (fc2 / out_proj bias of vit.py:113-127), for free. */
 int s4_layernorm_bwd(const void* dy, const void* x, const int* row_map, const float* gamma,
                      const float* mean, const float* rstd, const void* dres, void* dx,
-                     float* dgamma, float* dbeta, int rows, int D, int dtype,
+                     float* dgamma, float* dbeta, float* dres_sum, int rows, int D, int dtype,
                      cudaStream_t stream);
 
 /* ---- attention with the patch-adaptive (PASA) bias ---------------------------------------------

@@ -21,8 +21,10 @@
 // one), so no per-pixel weight evaluation is needed in the forward; the transpose (backward)
 // folds the clamped taps' weights into the edge pixel explicitly.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -307,6 +309,176 @@ bn_relu_upsample_bwd_walk(const __nv_bfloat16* __restrict__ dout, const __nv_bfl
 }
 
 // ---------------------------------------------------------------------------------------------
+// backward STRIP kernel: the same arithmetic as the walker, but the dout rows are staged in shared
+// memory by bulk async copies (cp.async.bulk + mbarrier) instead of per-thread loads.  The walker
+// is latency-bound: a thread's 2S*S loads of a step must land before the next step's are issued,
+// its registers are exhausted (128), and every dout row is fetched by the two input rows that
+// share it (ncu: 25 % occupancy, 31 % issue slots, 2.6 TB/s).  Here a block owns a column strip of
+// SEGW input pixels of one image and walks DOWN a chunk of input rows; the contiguous
+// (S*SEGW + S)-pixel pieces of the dout rows stream through a ring of R = 3S slots (2S live rows +
+// S rows in flight), so every dout row is read once per strip, S*piece bytes per block are always
+// in flight without costing a register, and the compute reads conflict-free 16-byte vectors.
+// Thread = (16-byte channel vector, pixel lane); a lane owns RL adjacent input pixels of the strip
+// and applies the separable filter transpose as the walker does (vertical reduce per dout column,
+// then two horizontal taps).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+
+template <int S, int RL>
+__global__ void __launch_bounds__(256)
+bn_relu_upsample_bwd_strip(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+                           const float* __restrict__ scale, const float* __restrict__ shift,
+                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                           __nv_bfloat16* __restrict__ dact, float* __restrict__ dsum,
+                           float* __restrict__ ddot, int B, int H, int W, int C, int strips, int rchunks,
+                           int rows_per, uint32_t slot_bytes) {
+  constexpr int R = 3 * S, NT = 2 * S;
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t raw = tc::smem_u32(smem_dyn);
+  const uint32_t ring = (raw + 127u) & ~127u;
+  const uint32_t bars = ring + R * slot_bytes;
+  float* sh = reinterpret_cast<float*>(smem_dyn + (bars + 128u - raw));      // [2][C]
+  const int cv = C >> 3, npl = 256 / cv, segw = RL * npl;
+  const int v = threadIdx.x % cv, pl = threadIdx.x / cv;
+  const int item = blockIdx.x;
+  const int rc = item % rchunks, st = (item / rchunks) % strips, b = item / (rchunks * strips);
+  const int ya = rc * rows_per, yb = min(ya + rows_per, H);
+  const int n_rows = yb - ya;
+  const int OH = H * S, OW = W * S;
+  const int x0 = st * segw, x1 = min(x0 + segw, W);
+  const int oxa_u = S * x0 - S / 2;                   // first dout column of the strip (may be -S/2)
+  const int oxa = max(oxa_u, 0), oxb = min(S * x1 + S / 2, OW);
+  const uint32_t piece_bytes = (uint32_t)(oxb - oxa) * (uint32_t)C * 2u;
+  const uint32_t dst_off = (uint32_t)(oxa - oxa_u) * (uint32_t)C * 2u;
+  const int oy_first = S * ya - S / 2;                // dout row of ring index q = 0
+  const int total_q = S * n_rows + S;
+  const __nv_bfloat16* dimg = dout + (size_t)b * OH * OW * C;
+  auto issue = [&](int q) {
+    const int oy = min(max(oy_first + q, 0), OH - 1);   // rows outside the image carry weight 0
+    const int slot = q % R;
+    tc::mbar_expect_tx(bars + 8u * slot, piece_bytes);
+    bulk_load_1d(ring + slot * slot_bytes + dst_off, dimg + ((size_t)oy * OW + oxa) * C, piece_bytes,
+                 bars + 8u * slot);
+  };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < R; ++i) tc::mbar_init(bars + 8u * i, 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  int next_q = 0;
+  if (threadIdx.x == 0 && n_rows > 0)
+    for (; next_q < min(total_q, R); ++next_q) issue(next_q);
+
+  float sc[8], sf[8], mu[8], as[8], ad[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = __ldg(scale + v * 8 + e); sf[e] = __ldg(shift + v * 8 + e); mu[e] = __ldg(mean + v * 8 + e);
+    as[e] = 0.f; ad[e] = 0.f;
+  }
+  const int c0 = x0 + RL * pl;                         // this lane's first input pixel
+  const bool lane_on = c0 < x1;
+  const uint32_t vec_off = (uint32_t)v * 16u;
+  for (int i = 0; i < n_rows; ++i) {
+    const int iy = ya + i;
+    const size_t rowbase = (((size_t)b * H + iy) * W) * C + (size_t)v * 8;
+    uint4 xr[RL];
+#pragma unroll
+    for (int r = 0; r < RL; ++r)
+      if (c0 + r < x1) xr[r] = ldg16(x + rowbase + (size_t)(c0 + r) * C);
+    float wy[NT];
+    uint32_t rowaddr[NT];
+    const bool yin = iy > 0 && iy < H - 1;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      wy[t] = yin ? 1.f - fabsf((float)t + 0.5f - (float)S) / (float)S : axis_w<S>(S * iy - S / 2 + t, iy, H);
+      const int q = S * i + t;
+      const int slot = q % R;
+      rowaddr[t] = ring + slot * slot_bytes + vec_off;
+      tc::mbar_wait(bars + 8u * slot, (uint32_t)(q / R) & 1u);
+    }
+    if (lane_on) {
+      float g[RL][8];
+#pragma unroll
+      for (int r = 0; r < RL; ++r)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[r][e] = 0.f;
+#pragma unroll
+      for (int pr = 0; pr <= RL; ++pr) {
+        const int c = c0 - 1 + pr;                     // pair (c, c + 1)
+        const bool inner = c >= 0 && c + 1 < W;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          const int ox = S * c + S / 2 + j;
+          if (ox < 0 || ox >= OW) continue;
+          const uint32_t coff = (uint32_t)(ox - oxa_u) * (uint32_t)C * 2u;
+          uint4 rawv[NT];
+#pragma unroll
+          for (int t = 0; t < NT; ++t) rawv[t] = lds16(rowaddr[t] + coff);
+          float T[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) T[e] = 0.f;
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            float d[8];
+            unpack8(rawv[t], d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) T[e] = fmaf(wy[t], d[e], T[e]);
+          }
+          const float wl = inner ? (j + 0.5f) / S : axis_w<S>(ox, c + 1, W);
+          const float wr = inner ? 1.f - (j + 0.5f) / S : axis_w<S>(ox, c, W);
+          if (pr > 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[pr > 0 ? pr - 1 : 0][e] = fmaf(wr, T[e], g[pr > 0 ? pr - 1 : 0][e]);
+          }
+          if (pr < RL) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[pr < RL ? pr : 0][e] = fmaf(wl, T[e], g[pr < RL ? pr : 0][e]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RL; ++r) {
+        if (c0 + r < x1) {
+          float xe[8], o[8];
+          unpack8(xr[r], xe);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float da = fmaf(xe[e], sc[e], sf[e]) > 0.f ? g[r][e] : 0.f;
+            o[e] = da;
+            as[e] += da;
+            ad[e] = fmaf(da, xe[e] - mu[e], ad[e]);
+          }
+          *reinterpret_cast<uint4*>(dact + rowbase + (size_t)(c0 + r) * C) = pack8(o);
+        }
+      }
+    }
+    __syncthreads();          // rows q < S (i + 1) are dead: their slots may be refilled
+    if (threadIdx.x == 0)
+      for (; next_q < total_q && next_q - R < S * (i + 1); ++next_q) issue(next_q);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = v * 8 + e;
+    atomicAdd(&sh[c], as[e]);
+    atomicAdd(&sh[C + c], ad[e] * __ldg(invstd + c));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dsum + i, sh[i]);
+    atomicAdd(ddot + i, sh[C + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dy = gamma*invstd*(dact - dsum/n - xhat*ddot/n) = A*dact + Bc*y + Cc; four 16-byte vectors of
 // each operand in flight per thread (the first-generation kernel had one: latency-bound).
 // ---------------------------------------------------------------------------------------------
@@ -434,6 +606,42 @@ static void launch_bwd_walk(const void* dout, const void* x, const float* scale,
       dsum, ddot, B, H, W, C, (int)units);
 }
 
+// strip kernel launch: returns false when the shape does not fit (the walker takes over)
+template <int S, int RL>
+static bool launch_bwd_strip(const void* dout, const void* x, const float* scale, const float* shift,
+                             const float* mean, const float* invstd, void* dact, float* dsum, float* ddot,
+                             int B, int H, int W, int C, cudaStream_t st) {
+  const int cv = C / 8, npl = 256 / cv, segw = RL * npl;
+  const size_t slot = (size_t)(S * segw + S) * C * 2;
+  const size_t smem = 3 * S * slot + 128 + 128 + 2 * (size_t)C * sizeof(float);
+  if (smem > 227 * 1024) return false;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(bn_relu_upsample_bwd_strip<S, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_done = true;
+  }
+  const int strips = (W + segw - 1) / segw;
+  int bps = (int)((227 * 1024) / (smem + 1024));
+  if (bps > 3) bps = 3;
+  if (bps < 1) bps = 1;
+  const long long slots = (long long)s4_num_sms() * bps;
+  int rchunks = (int)std::max<long long>(1, slots / ((long long)B * strips));
+  if (rchunks > H) rchunks = H;
+  int rows_per = (H + rchunks - 1) / rchunks;
+  if (rows_per < 4) rows_per = std::min(4, H);       // halo rows: S per chunk
+  rchunks = (H + rows_per - 1) / rows_per;
+  const long long grid = (long long)B * strips * rchunks;
+  if (grid >= (1ll << 31)) return false;
+  bn_relu_upsample_bwd_strip<S, RL><<<(unsigned)grid, 256, smem, st>>>(
+      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)x, scale, shift, mean, invstd, (__nv_bfloat16*)dact,
+      dsum, ddot, B, H, W, C, strips, rchunks, rows_per, (uint32_t)slot);
+  return true;
+}
+
 bool s4_stream_upsample_bwd(const void* dout, const void* x, const float* scale, const float* shift,
                             const float* mean, const float* invstd, void* dact, float* dsum, float* ddot,
                             int B, int H, int W, int C, int s, cudaStream_t st) {
@@ -442,6 +650,16 @@ bool s4_stream_upsample_bwd(const void* dout, const void* x, const float* scale,
   if ((s != 2 && s != 4) || !vn) return false;
   if ((long long)B * H * W * s * s * (C / vn) >= (1ll << 31)) return false;
   if ((long long)B * H * ((W + 7) / 8) >= (1ll << 30)) return false;
+  // bulk-copy strip kernel (C a multiple of 8 with C/8 dividing 256, 16-byte aligned rows)
+  static const bool no_strip = getenv("S4_NO_BWD_STRIP") != nullptr;
+  if (!no_strip && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && H >= 2 && W >= 2) {
+    const int npl = 256 / (C / 8);
+    bool ok = false;
+    if (s == 2 && W >= 4 * npl) ok = launch_bwd_strip<2, 2>(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, st);
+    else if (s == 2) ok = launch_bwd_strip<2, 1>(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, st);
+    else ok = launch_bwd_strip<4, 1>(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, st);
+    if (ok) return true;
+  }
   if (s == 2 && vn == 4) launch_bwd_walk<2, 4>(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, st);
   else if (s == 2) launch_bwd_walk<2, 8>(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, st);
   else if (vn == 4) launch_bwd_walk<4, 4>(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, st);

@@ -175,17 +175,34 @@ ln_fwd_lean_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
 // dx (written at the mapped source row of a pre-zeroed buffer when row_map != null).
 // dgamma/dbeta: every warp keeps register partials over its rows, the block folds them through
 // shared memory (plain stores, one slab per warp) and issues ONE global atomic per column.
-template <typename T, int VPL, bool EXACT>
+// RSUM: the column sums of `dres` (the residual-stream gradient the kernel reads anyway) are
+// accumulated too - it is the bias gradient of the linear layer that produced the residual branch
+// (fc2.bias / out_proj.bias in an encoder layer), which otherwise costs a pass of its own over dres.
+// Those partials live in the warp's shared-memory slab (the register file is full: 128 per thread).
+template <typename T, int VPL, bool EXACT, bool RSUM>
 __global__ void __launch_bounds__(128, 4)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __restrict__ row_map,
               const float* __restrict__ gamma, const float* __restrict__ mean,
               const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dres_sum,
+              int rows, int D) {
   constexpr int VN = Vec16<T>::N;
-  extern __shared__ float sh[];  // [warps][2][D]
+  constexpr int NS = RSUM ? 3 : 2;
+  extern __shared__ float sh[];  // [warps][NS][D]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const int nvec = D / VN;
+  float* mine = sh + (size_t)wib * NS * D;
+  if (RSUM) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      if (EXACT || vi < nvec) {
+#pragma unroll
+        for (int e = 0; e < VN; ++e) mine[2 * D + vi * VN + e] = 0.f;
+      }
+    }
+  }
   float gm[VPL][VN];
   float ag[VPL][VN], ab[VPL][VN];
 #pragma unroll
@@ -260,10 +277,22 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
           o.set(e, val);
         }
         o.store(dr + vi * VN);
+        if (RSUM) {
+          // lane-private columns of the warp-private slab: no synchronisation needed
+          float4* acc4 = reinterpret_cast<float4*>(mine + 2 * D + vi * VN);
+#pragma unroll
+          for (int q = 0; q < VN / 4; ++q) {
+            float4 a = acc4[q];
+            a.x += rv[k].get(4 * q);
+            a.y += rv[k].get(4 * q + 1);
+            a.z += rv[k].get(4 * q + 2);
+            a.w += rv[k].get(4 * q + 3);
+            acc4[q] = a;
+          }
+        }
       }
     }
   }
-  float* mine = sh + (size_t)wib * 2 * D;
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int vi = lane + k * 32;
@@ -276,10 +305,11 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const int* __re
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NS * D; i += blockDim.x) {
     float acc = 0.f;
-    for (int w2 = 0; w2 < wpb; ++w2) acc += sh[(size_t)w2 * 2 * D + i];
-    atomicAdd((i < D ? dgamma : dbeta - D) + i, acc);
+    for (int w2 = 0; w2 < wpb; ++w2) acc += sh[(size_t)w2 * NS * D + i];
+    float* dst = i < D ? dgamma + i : (i < 2 * D ? dbeta + (i - D) : dres_sum + (i - 2 * D));
+    atomicAdd(dst, acc);
   }
 }
 
@@ -332,9 +362,11 @@ extern "C" int s4_layernorm_fwd(const void* x, const int* row_map, const float* 
 
 extern "C" int s4_layernorm_bwd(const void* dy, const void* x, const int* row_map,
                                 const float* gamma, const float* mean, const float* rstd,
-                                const void* dres, void* dx, float* dgamma, float* dbeta, int rows,
-                                int D, int dtype, cudaStream_t stream) {
+                                const void* dres, void* dx, float* dgamma, float* dbeta,
+                                float* dres_sum, int rows, int D, int dtype, cudaStream_t stream) {
   S4ProfScope prof_("layernorm_bwd", 0.0, 1, stream);
+  S4_REQUIRE(dres_sum == nullptr || (dres != nullptr && row_map == nullptr),
+             "layernorm_bwd: dres_sum needs dres and no row_map");
   const int vn = dtype == S4_BF16 ? 8 : 4;
   S4_REQUIRE(D % vn == 0 && D / vn <= 32 * LN_MAX_VPL, "layernorm: unsupported D=%d", D);
   if (rows == 0) return S4_OK;
@@ -344,32 +376,42 @@ extern "C" int s4_layernorm_bwd(const void* dy, const void* x, const int* row_ma
   int blocks = (rows + 3) / 4;
   const int cap = s4_num_sms() * 4;
   if (blocks > cap) blocks = cap;
-  const size_t smem = (BT / 32) * 2 * (size_t)D * sizeof(float);
+  const size_t smem = (BT / 32) * (dres_sum ? 3 : 2) * (size_t)D * sizeof(float);
   if (smem > 48 * 1024) {
     static bool attr_done = false;
     if (!attr_done) {
-      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(ln_bwd_kernel<float, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(ln_bwd_kernel<float, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(ln_bwd_kernel<float, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(ln_bwd_kernel<float, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<__nv_bfloat16, 4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 6, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 6, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 6, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 6, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(ln_bwd_kernel<float, 8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
       attr_done = true;
     }
   }
   const int vpl = (D / vn + 31) / 32;
   const bool exact = D == vpl * 32 * vn;
-#define S4_LN_BWD(TT, EX)                                                                      \
-  LN_DISPATCH_VPL(vpl, (ln_bwd_kernel<TT, VPL, EX><<<blocks, BT, smem, stream>>>(              \
+#define S4_LN_BWD(TT, EX, RS)                                                                  \
+  LN_DISPATCH_VPL(vpl, (ln_bwd_kernel<TT, VPL, EX, RS><<<blocks, BT, smem, stream>>>(          \
       (const TT*)dy, (const TT*)x, row_map, gamma, mean, rstd, (const TT*)dres, (TT*)dx, dgamma, \
-      dbeta, rows, D)))
+      dbeta, dres_sum, rows, D)))
+#define S4_LN_BWD2(TT, EX) do { if (dres_sum) S4_LN_BWD(TT, EX, true); else S4_LN_BWD(TT, EX, false); } while (0)
   if (dtype == S4_BF16) {
-    if (exact) S4_LN_BWD(__nv_bfloat16, true); else S4_LN_BWD(__nv_bfloat16, false);
+    if (exact) S4_LN_BWD2(__nv_bfloat16, true); else S4_LN_BWD2(__nv_bfloat16, false);
   } else {
-    if (exact) S4_LN_BWD(float, true); else S4_LN_BWD(float, false);
+    if (exact) S4_LN_BWD2(float, true); else S4_LN_BWD2(float, false);
   }
+#undef S4_LN_BWD2
 #undef S4_LN_BWD
   return s4_check_launch("layernorm_bwd");
 }

@@ -407,12 +407,16 @@ def layernorm_fwd(x2d, gamma, beta, eps, row_map=None, out_rows=None):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x2d, gamma_p, beta_p, mean, rstd, row_map=None, dres=None, dx=None):
+def layernorm_bwd(dy, x2d, gamma_p, beta_p, mean, rstd, row_map=None, dres=None, dx=None,
+                  dres_bias=None):
+    """``dres_bias``: a bias parameter whose gradient is colsum(dres) (the linear layer whose output
+    joined the residual stream here); accumulated by the same pass."""
     rows, D = dy.shape
     if dx is None:
         dx = torch.zeros_like(x2d) if row_map is not None else torch.empty_like(x2d)
     L.call('s4_layernorm_bwd', _p(dy), _p(x2d), _p(row_map), _p(gamma_p.detach()), _p(mean), _p(rstd),
-           _p(dres), _p(dx), _p(grad_buffer(gamma_p)), _p(grad_buffer(beta_p)), rows, D,
+           _p(dres), _p(dx), _p(grad_buffer(gamma_p)), _p(grad_buffer(beta_p)),
+           _p(grad_buffer(dres_bias)) if dres_bias is not None else None, rows, D,
            _code(dy.dtype), _st())
     return dx
 
@@ -499,17 +503,21 @@ class EncoderLayerFn(torch.autograd.Function):
         # FFN
         # (dy W2) * gelu'(pre); the same epilogue accumulates fc1.bias.grad = colsum(dpre)
         dpre = linear_dgrad(dy, lowp(fc2.weight), aux=pre, colsum_param=fc1.bias)
-        linear_wgrad(dy, h, fc2.weight, fc2.bias)
+        linear_wgrad(dy, h, fc2.weight, None)
         dxl2 = linear_dgrad(dpre, lowp(fc1.weight))
         linear_wgrad(dpre, xl2, fc1.weight, None)
-        dxm = layernorm_bwd(dxl2, xm, layer.ln2.weight, layer.ln2.bias, mean2, rstd2, dres=dy)
+        # fc2.bias.grad = colsum(dy) and out_proj.bias.grad = colsum(dxm) come out of the
+        # LayerNorm-backward passes that read dy / dxm as their residual gradient
+        dxm = layernorm_bwd(dxl2, xm, layer.ln2.weight, layer.ln2.bias, mean2, rstd2, dres=dy,
+                            dres_bias=fc2.bias)
         # attention block
         datt = linear_dgrad(dxm, lowp(mha.out_proj.weight))
-        linear_wgrad(dxm, att, mha.out_proj.weight, mha.out_proj.bias)
+        linear_wgrad(dxm, att, mha.out_proj.weight, None)
         dqkv = attention_bwd(datt, qkv, att, lse, B, Ltok, H, hd, u0, gate, ctx.w)
         dxl1 = linear_dgrad(dqkv, lowp(mha.in_proj_weight))
         linear_wgrad(dqkv, xl1, mha.in_proj_weight, mha.in_proj_bias)
-        dx = layernorm_bwd(dxl1, x, layer.ln1.weight, layer.ln1.bias, mean1, rstd1, dres=dxm)
+        dx = layernorm_bwd(dxl1, x, layer.ln1.weight, layer.ln1.bias, mean1, rstd1, dres=dxm,
+                           dres_bias=mha.out_proj.bias)
         _pending_dec(layer)
         return dx, None, None, None, None, None, None, None
 

@@ -83,6 +83,27 @@ def test_layernorm_fwd_bwd(dtype, tol, D):
     assert rel(dx.float(), xr.grad + dresd.float().cpu()) < max(tol, 1e-4)
     assert rel(gp.grad, gr.grad) < max(tol, 1e-4)
     assert rel(bp.grad, br.grad) < max(tol, 1e-4)
+    # the same pass can emit colsum(dres) (+=) : the bias gradient of the layer feeding the residual
+    rb = torch.nn.Parameter(torch.zeros(D, device=DEV))
+    rb.grad = torch.ones(D, device=DEV)
+    dx2 = ops.layernorm_bwd(dyd, xd, gp, bp, mean, rstd, dres=dresd, dres_bias=rb)
+    assert torch.equal(dx2, dx)
+    assert rel(rb.grad.cpu(), 1.0 + dresd.float().cpu().sum(0)) < 1e-5
+
+
+def test_layernorm_bwd_many_rows_residual_sum():
+    rows, D = 24600, 768
+    g = gen(5)
+    xd = torch.randn(rows, D, generator=g).to(DEV, torch.bfloat16)
+    dyd = torch.randn(rows, D, generator=g).to(DEV, torch.bfloat16)
+    dresd = (torch.randn(rows, D, generator=g) + 0.25).to(DEV, torch.bfloat16)
+    gp = torch.nn.Parameter(torch.ones(D, device=DEV))
+    bp = torch.nn.Parameter(torch.zeros(D, device=DEV))
+    rb = torch.nn.Parameter(torch.zeros(D, device=DEV))
+    _, mean, rstd = ops.layernorm_fwd(xd, gp, bp, 1e-6)
+    ops.layernorm_bwd(dyd, xd, gp, bp, mean, rstd, dres=dresd, dres_bias=rb)
+    assert rel(rb.grad, dresd.double().sum(0).float()) < 1e-5
+    assert rel(bp.grad, dyd.double().sum(0).float()) < 1e-5
 
 
 def test_layernorm_fwd_many_rows_lean_kernel():
@@ -282,7 +303,9 @@ def test_conv_bn_relu_upsample_stage_fp32(s):
 
 
 @pytest.mark.parametrize('dtype,tol', [(torch.bfloat16, 1e-2), (torch.float32, 1e-5)])
-@pytest.mark.parametrize('B,H,W,C,s', [(2, 16, 16, 256, 2), (1, 8, 24, 256, 4), (2, 5, 7, 64, 2), (1, 32, 32, 128, 2)])
+@pytest.mark.parametrize('B,H,W,C,s', [(2, 16, 16, 256, 2), (1, 8, 24, 256, 4), (2, 5, 7, 64, 2), (1, 32, 32, 128, 2),
+                                       (2, 64, 64, 256, 2), (1, 40, 36, 256, 2), (2, 32, 32, 256, 4),
+                                       (12, 32, 32, 256, 2), (1, 2, 2, 256, 2), (1, 3, 5, 256, 4)])
 def test_bn_relu_upsample_kernels(dtype, tol, B, H, W, C, s):
     """fused BN + ReLU + bilinear (and its transpose with the BatchNorm-backward sums) against
     F.interpolate on the same inputs, incl. non-square maps and every border case."""

@@ -61,6 +61,9 @@ for rows in (24600, 8200):
     dy, dres, dx = rnd(rows, D), rnd(rows, D), torch.empty_like(x)
     timeit(f'ln_bwd rows={rows} (+dres)', lambda: ops.layernorm_bwd(dy, x, gamma, beta, mean, rstd, dres=dres, dx=dx),
            rows * D * 8)
+    rb = torch.nn.Parameter(torch.zeros(D, device=dev))
+    timeit(f'ln_bwd rows={rows} (+dres, +colsum(dres))',
+           lambda: ops.layernorm_bwd(dy, x, gamma, beta, mean, rstd, dres=dres, dx=dx, dres_bias=rb), rows * D * 8)
 x = rnd(8 * 1025, D)
 rm = (torch.arange(8 * 1024, device=dev, dtype=torch.int32) + torch.arange(8, device=dev, dtype=torch.int32).repeat_interleave(1024) + 1)
 timeit('ln_fwd head row_map rows=8192', lambda: ops.layernorm_fwd(x, gamma, beta, 1e-6, row_map=rm, out_rows=8192), 8192 * D * 4)
