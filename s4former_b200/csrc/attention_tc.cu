@@ -1069,17 +1069,18 @@ attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat1
 //   p[q]  = 2^(c1 Q_q.K_x + w gate_q u0_x log2e - lse_q log2e)   ds[q] = p[q] (dO_q.V_x - delta_q)
 //   dV_x  = sum_q p[q] dO_q     dK_x = scale sum_q ds[q] Q_q     dQ_q += ds[q] K_x
 // p / ds are rounded to bf16 before use, as the tensor-core path rounds P^T / dS^T.
-// Block = 32 queries (lanes) x H heads (warps) of one image: the block reads 32 contiguous rows of
-// dO / O / qkv (a per-(b,h) kernel read 128 B out of every 4.6 KB and ran at 25 % of the DRAM rate).
-// The sums over queries are a warp reduce-scatter (lane l ends with dims 2l, 2l+1) and one fp32
-// atomic per (warp, dim) into peel_acc[b,h,{dV,dK},64]; ds goes to ds_peel[b,h,q] for the dQ term,
-// which the dq convert kernel adds (that kernel also writes the dK_x / dV_x rows).
-// A WARP walks QPW consecutive query rows of one image; lane l owns the 16-byte chunks l, l+32, l+64
-// ... of a row (8 head dims of head (l/8) + 4k): every load is a fully coalesced row segment, the
-// per-head dot products are xor-reductions over aligned 8-lane groups, and the sums over queries
-// stay in the lane's registers (its dims never change) until one atomic per (lane, dim) at the end.
-constexpr int DP_QPW = 16;       // queries per warp
-constexpr int DP_WARPS = 4;      // warps per block
+// A WARP owns one 512-byte column group of the rows (lane l = the 16-byte chunk 32 k + l: 8 head dims
+// of head (32 k + l) / 8) and walks DP_ROWS consecutive query rows of one image four at a time, all
+// twelve loads of the four rows in flight before the first is consumed (the first version walked
+// row by row with 7 warps per SM resident: latency-bound at 19 % of the DRAM rate).  Every load is
+// a fully coalesced row segment, the per-head dot products are xor-reductions over aligned 8-lane
+// groups, and the sums over queries stay in the lane's registers (its dims never change).  The
+// block's row groups are folded through shared memory into the block's slice of
+// peel_part[b, qgroup, h, {dV, dK}, 64] (plain stores: deterministic, nothing to zero); ds goes to
+// ds_peel[b,h,q] for the dQ term.  The dq convert kernel adds ds_peel * K_x to dQ, sums the slices
+// and writes the dK_x / dV_x rows.
+constexpr int DP_ROWS_MIN = 8;   // query rows per warp (8 or 16), four at a time (their loads all in flight)
+constexpr int DP_RW = 2;         // row groups per block: a block = (chunk groups) x DP_RW warps
 
 __device__ __forceinline__ float group8_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -1097,103 +1098,111 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
   }
 }
 
-template <int NCH>     // 16-byte chunks per lane: ceil(H * 8 / 32)
-__global__ void __launch_bounds__(DP_WARPS * 32)
+template <int NCH, int MINB>     // chunk groups (warps across a row): ceil(H * 8 / 32)
+__global__ void __launch_bounds__(NCH * DP_RW * 32, MINB)
 attn_bwd_delta_peel_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                            const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ lse,
                            const float* __restrict__ u0, const float* __restrict__ gate, float w, float scale,
-                           float* __restrict__ delta, float* __restrict__ ds_peel, float* __restrict__ peel_acc,
-                           int B, int H, int L, int peel) {
+                           float* __restrict__ delta, float* __restrict__ ds_peel, float* __restrict__ peel_part,
+                           int B, int H, int L, int peel, int DP_ROWS) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int qgroups = (L + DP_QPW * DP_WARPS - 1) / (DP_QPW * DP_WARPS);
+  const int k = wib % NCH, rg = wib / NCH;
+  const int qgroups = (L + DP_ROWS * DP_RW - 1) / (DP_ROWS * DP_RW);
   const int b = blockIdx.x / qgroups;
-  const int q0 = ((blockIdx.x % qgroups) * DP_WARPS + wib) * DP_QPW;
+  const int q0 = ((blockIdx.x % qgroups) * DP_RW + rg) * DP_ROWS;
   const int D = H * HD, D3 = 3 * D;
   const int nchunks = H * 8;
   const int x = L - 1;
-  float kx[NCH][8], vx[NCH][8], accv[NCH][8], acck[NCH][8];
-  if (peel) {
+  const int c = lane + 32 * k;
+  const bool cok = c < nchunks;
+  const int hh = cok ? (c >> 3) : 0;
+  float kx[8], vx[8], accv[8], acck[8];
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c = lane + 32 * k;
-      if (c < nchunks) {
-        const __nv_bfloat16* xr = qkv + ((size_t)b * L + x) * D3;
-        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(xr + D + c * 8)), kx[k]);
-        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(xr + 2 * D + c * 8)), vx[k]);
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { accv[k][e] = 0.f; acck[k][e] = 0.f; }
-    }
+  for (int e = 0; e < 8; ++e) { kx[e] = 0.f; vx[e] = 0.f; accv[e] = 0.f; acck[e] = 0.f; }
+  if (peel && cok) {
+    const __nv_bfloat16* xr = qkv + ((size_t)b * L + x) * D3;
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(xr + D + c * 8)), kx);
+    bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(xr + 2 * D + c * 8)), vx);
   }
   const float c1 = scale * LOG2E;
   const float u0x = (peel && u0) ? u0[(size_t)b * L + x] : 0.f;
-  for (int qi = 0; qi < DP_QPW; ++qi) {
-    const int q = q0 + qi;
-    if (q >= L) break;                      // (warp-uniform; the barrier below is reached by every warp)
-    const size_t bq = (size_t)b * L + q;
-    float wg = 0.f;
-    if (peel && u0) wg = w * LOG2E * (gate ? gate[bq] : 1.f);
+  const size_t bh = (size_t)b * H + hh;
+  for (int qi = 0; qi < DP_ROWS; qi += 4) {
+    if (q0 + qi >= L) break;                          // warp-uniform
+    // every load of four rows is issued before the first is consumed
+    uint4 rd[4], ro[4], rq[4];
+    float ls[4], wg[4];
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c = lane + 32 * k;
-      const bool cok = c < nchunks;
-      const int hh = cok ? (c >> 3) : 0;
-      float dof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, of[8] = {0, 0, 0, 0, 0, 0, 0, 0}, qf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (cok) {
-        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(dout + bq * D + c * 8)), dof);
-        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(out + bq * D + c * 8)), of);
-        if (peel) bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(qkv + bq * D3 + c * 8)), qf);
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + qi + u;
+      const bool ok = cok && q < L;
+      const size_t bq = (size_t)b * L + (ok ? q : 0);
+      rd[u] = make_uint4(0, 0, 0, 0); ro[u] = rd[u]; rq[u] = rd[u];
+      ls[u] = 0.f; wg[u] = 0.f;
+      if (ok) {
+        rd[u] = __ldg(reinterpret_cast<const uint4*>(dout + bq * D + c * 8));
+        ro[u] = __ldg(reinterpret_cast<const uint4*>(out + bq * D + c * 8));
+        if (peel) {
+          rq[u] = __ldg(reinterpret_cast<const uint4*>(qkv + bq * D3 + c * 8));
+          ls[u] = __ldg(lse + bh * L + q) * LOG2E;
+          if (u0) wg[u] = w * LOG2E * (gate ? __ldg(gate + bq) : 1.f);
+        }
       }
-      float dl = 0.f, sd = 0.f, dp = 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + qi + u;
+      if (q >= L) break;                              // warp-uniform
+      float dof[8], of[8], qf[8];
+      bf16x8_to_f32(rd[u], dof);
+      bf16x8_to_f32(ro[u], of);
+      float dl = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) dl = fmaf(dof[e], of[e], dl);
       dl = group8_sum(dl);
-      if (cok && (lane & 7) == 0) delta[((size_t)b * H + hh) * L + q] = dl;
+      if (cok && (lane & 7) == 0) delta[bh * L + q] = dl;
       if (peel) {
+        bf16x8_to_f32(rq[u], qf);
+        float sd = 0.f, dp = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          sd = fmaf(qf[e], kx[k][e], sd);
-          dp = fmaf(dof[e], vx[k][e], dp);
+          sd = fmaf(qf[e], kx[e], sd);
+          dp = fmaf(dof[e], vx[e], dp);
         }
         sd = group8_sum(sd);
         dp = group8_sum(dp);
         if (cok) {
-          const float pe = tc::ex2(fmaf(sd, c1, fmaf(wg, u0x, -lse[((size_t)b * H + hh) * L + q] * LOG2E)));
+          const float pe = tc::ex2(fmaf(sd, c1, fmaf(wg[u], u0x, -ls[u])));
           const float pr = __bfloat162float(__float2bfloat16_rn(pe));
           const float dsr = __bfloat162float(__float2bfloat16_rn(pe * (dp - dl)));
-          if ((lane & 7) == 0) ds_peel[((size_t)b * H + hh) * L + q] = dsr;
+          if ((lane & 7) == 0) ds_peel[bh * L + q] = dsr;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            accv[k][e] = fmaf(pr, dof[e], accv[k][e]);
-            acck[k][e] = fmaf(dsr, qf[e], acck[k][e]);
+            accv[e] = fmaf(pr, dof[e], accv[e]);
+            acck[e] = fmaf(dsr, qf[e], acck[e]);
           }
         }
       }
     }
   }
   if (peel) {
-    // fold the block's warps through shared memory first: one global atomic per (block, head, dim)
-    // (4.9 M same-address atomics from every lane made this kernel 3x slower than its loads)
-    extern __shared__ float red[];              // [DP_WARPS][H * 128]
-    float* mine = red + (size_t)wib * H * 128;
+    // the block's row groups are folded through shared memory and the block's partial sums go to
+    // its own slice of peel_part (no atomics: the dq convert kernel adds the slices of an image)
+    extern __shared__ float red[];              // [DP_RW][H * 128]
+    if (cok) {
+      float* dst = red + (size_t)rg * H * 128 + (c >> 3) * 128 + (c & 7) * 8;
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c = lane + 32 * k;
-      if (c < nchunks) {
-        float* dst = mine + (c >> 3) * 128 + (c & 7) * 8;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          dst[e] = accv[k][e];
-          dst[64 + e] = acck[k][e];
-        }
+      for (int e = 0; e < 8; ++e) {
+        dst[e] = accv[e];
+        dst[64 + e] = acck[e];
       }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < H * 128; i += blockDim.x) {
       float t = 0.f;
 #pragma unroll
-      for (int w2 = 0; w2 < DP_WARPS; ++w2) t += red[(size_t)w2 * H * 128 + i];
-      atomicAdd(peel_acc + (size_t)b * H * 128 + i, t);
+      for (int w2 = 0; w2 < DP_RW; ++w2) t += red[(size_t)w2 * H * 128 + i];
+      peel_part[(size_t)blockIdx.x * H * 128 + i] = t;
     }
   }
 }
@@ -1203,8 +1212,32 @@ attn_bwd_delta_peel_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bf
 __global__ void __launch_bounds__(256)
 attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, int B, int H,
                            int L, int q_tiles, float scale, const float* __restrict__ ds_peel,
-                           const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ peel_acc) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, q, h, 8-column group)
+                           const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ peel_part,
+                           int qgroups, int fold_blocks) {
+  if ((int)blockIdx.x < fold_blocks) {
+    // the peeled key's own gradient rows dV_x / dK_x (scaled): sum the delta/peel kernel's per-block
+    // partials [qgroups][H][{dV, dK}][64] of the image.  These blocks come FIRST in the grid so the
+    // short serial sums run under the rest of the kernel.
+    const int i = blockIdx.x * 256 + threadIdx.x;           // (b, h, {dV, dK}, d)
+    if (i >= B * H * 128) return;
+    const int j = i & 127, hh = (i >> 7) % H, b = (i >> 7) / H;
+    const float* pp = peel_part + ((size_t)b * qgroups * H + hh) * 128 + j;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    int g = 0;
+    for (; g + 4 <= qgroups; g += 4) {
+      t0 += pp[(size_t)(g + 0) * H * 128];
+      t1 += pp[(size_t)(g + 1) * H * 128];
+      t2 += pp[(size_t)(g + 2) * H * 128];
+      t3 += pp[(size_t)(g + 3) * H * 128];
+    }
+    for (; g < qgroups; ++g) t0 += pp[(size_t)g * H * 128];
+    const float t = (t0 + t1) + (t2 + t3);
+    __nv_bfloat16* row = dqkv + ((size_t)b * L + (L - 1)) * 3 * H * HD;
+    if (j < 64) row[(2 * H + hh) * HD + j] = __float2bfloat16_rn(t);
+    else row[(H + hh) * HD + (j - 64)] = __float2bfloat16_rn(t * scale);
+    return;
+  }
+  const long long idx = (long long)(blockIdx.x - fold_blocks) * blockDim.x + threadIdx.x;   // (b, q, h, 8-column group)
   const long long total = (long long)B * L * H * 8;
   if (idx >= total) return;
   const int g8 = (int)(idx & 7);
@@ -1231,17 +1264,6 @@ attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restr
   v.z = pack_bf16(hi.x * scale, hi.y * scale);
   v.w = pack_bf16(hi.z * scale, hi.w * scale);
   *reinterpret_cast<uint4*>(dqkv + (size_t)bq * 3 * H * HD + hh * HD + g8 * 8) = v;
-  if (ds_peel && q == L - 1) {     // the peeled key's own gradient rows: dK_x (scaled) and dV_x
-    const float* pa = peel_acc + ((size_t)b * H + hh) * 128 + g8 * 8;
-    uint4 dv, dk;
-    dv.x = pack_bf16(pa[0], pa[1]); dv.y = pack_bf16(pa[2], pa[3]);
-    dv.z = pack_bf16(pa[4], pa[5]); dv.w = pack_bf16(pa[6], pa[7]);
-    dk.x = pack_bf16(pa[64] * scale, pa[65] * scale); dk.y = pack_bf16(pa[66] * scale, pa[67] * scale);
-    dk.z = pack_bf16(pa[68] * scale, pa[69] * scale); dk.w = pack_bf16(pa[70] * scale, pa[71] * scale);
-    __nv_bfloat16* row = dqkv + (size_t)bq * 3 * H * HD;
-    *reinterpret_cast<uint4*>(row + (H + hh) * HD + g8 * 8) = dk;
-    *reinterpret_cast<uint4*>(row + (2 * H + hh) * HD + g8 * 8) = dv;
-  }
 }
 
 TraceCfg g_trace{nullptr, 0};
@@ -1277,8 +1299,9 @@ bool s4_attention_tc_bwd_supported(int B, int H, int L, int hd, int dtype) {
 // workspace of the fused backward: delta [B,H,L] + dq_accum [B,H,q_tiles,128,64], fp32
 size_t s4_attention_tc_bwd_workspace(int B, int H, int L) {
   const size_t qt = (size_t)(L + 127) / 128;
+  const size_t qgroups = ((size_t)L + DP_ROWS_MIN * DP_RW - 1) / (DP_ROWS_MIN * DP_RW);
   return 2 * (((size_t)B * H * L * 4 + 255) / 256 * 256) + (size_t)B * H * qt * 128 * 64 * 4 +
-         (size_t)B * H * 128 * 4;
+         (size_t)B * qgroups * H * 128 * 4;
 }
 
 int s4_attention_tc_fwd(const void* qkv, const float* u0, const float* gate, float w, void* out,
@@ -1380,20 +1403,24 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
     smem_set = smem;
   }
   S4ProfScope prof("attn_bwd_tc", 8.0 * B * H * (double)L * L * HD, 0, st);
-  float* peel_acc = (float*)((char*)dq_accum + acc_bytes);      // [B,H,2,64], zeroed with dq_accum
-  cudaError_t e = cudaMemsetAsync(dq_accum, 0, acc_bytes + (size_t)B * H * 128 * 4, st);
+  float* peel_part = (float*)((char*)dq_accum + acc_bytes);     // [B,qgroups,H,2,64], fully written
+  static const int dp_rows = (getenv("S4_DP_ROWS") && atoi(getenv("S4_DP_ROWS")) == 8) ? 8 : 16;
+  static const int dp_minb = (getenv("S4_DP_MINB") && atoi(getenv("S4_DP_MINB")) == 3) ? 3 : 2;
+  const int qgroups = (L + dp_rows * DP_RW - 1) / (dp_rows * DP_RW);
+  cudaError_t e = cudaMemsetAsync(dq_accum, 0, acc_bytes, st);
   if (e != cudaSuccess) {
     s4_set_error("attention_tc_bwd: memset failed: %s", cudaGetErrorString(e));
     return S4_ERR_CUDA;
   }
   if (H <= 16) {
-    const int qgroups = (L + DP_QPW * DP_WARPS - 1) / (DP_QPW * DP_WARPS);
     const int nch = (H * 8 + 31) / 32;
-#define S4_DP(N)                                                                                         \
-  attn_bwd_delta_peel_kernel<N><<<B * qgroups, DP_WARPS * 32, peel ? (size_t)DP_WARPS * H * 128 * 4 : 0, st>>>(                                    \
+#define S4_DP(N, MB)                                                                                     \
+  attn_bwd_delta_peel_kernel<N, MB><<<B * qgroups, N * DP_RW * 32, peel ? (size_t)DP_RW * H * 128 * 4 : 0, st>>>( \
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)qkv, lse, u0, gate, w, \
-      p.scale, delta, ds_peel, peel_acc, B, H, L, peel ? 1 : 0)
-    if (nch <= 1) S4_DP(1); else if (nch == 2) S4_DP(2); else if (nch == 3) S4_DP(3); else S4_DP(4);
+      p.scale, delta, ds_peel, peel_part, B, H, L, peel ? 1 : 0, dp_rows)
+    if (nch <= 1) S4_DP(1, 2); else if (nch == 2) S4_DP(2, 2);
+    else if (nch == 3) { if (dp_minb == 3) S4_DP(3, 3); else S4_DP(3, 2); }
+    else S4_DP(4, 2);
 #undef S4_DP
     if ((rc = s4_check_launch("attn_bwd_delta"))) return rc;
   } else {
@@ -1408,9 +1435,10 @@ int s4_attention_tc_bwd(const void* dout, const void* qkv, const void* out, cons
   if ((rc = s4_check_launch("attn_bwd_tc"))) return rc;
   {
     const long long total = (long long)B * L * H * 8;
-    attn_bwd_dq_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+    const int fold_blocks = peel ? (B * H * 128 + 255) / 256 : 0;
+    attn_bwd_dq_convert_kernel<<<(unsigned)((total + 255) / 256) + fold_blocks, 256, 0, st>>>(
         dq_accum, (__nv_bfloat16*)dqkv, B, H, L, q_tiles, p.scale, peel ? ds_peel : nullptr,
-        (const __nv_bfloat16*)qkv, peel_acc);
+        (const __nv_bfloat16*)qkv, peel_part, qgroups, fold_blocks);
     rc = s4_check_launch("attn_bwd_dq_convert");
   }
   return rc;
