@@ -96,6 +96,13 @@ int s4_gemm_uses_tc(const S4GemmParams* p);
  * problem allows them.  Returns the previous mode.  A tuning / test knob: results are the same
  * GEMM in every mode. */
 int s4_set_tc_pair_mode(int mode);
+/* Tile scheduling of the persistent tcgen05 GEMM / conv grid: 0 = static round-robin (default; also
+ * S4_TC_SCHED), 1 = dynamic (CTA groups take tiles from a global counter).  Dynamic costs 1-2 us per
+ * launch on an otherwise idle GPU and saves up to half of a launch's time when another kernel (NCCL's
+ * all-reduce during the data-parallel backward) holds SMs: CTAs that become resident late find no
+ * work left instead of starting a full static share late.  Returns the previous mode.  Same results
+ * in both modes (split-K weight-gradient tiles are reduce-added in a different order). */
+int s4_set_tc_sched(int mode);
 
 /* ---- LayerNorm (+ row gather) ----------------------------------------------------------------
  * Replaces: ln1/ln2 (vit.py:119-120, eps 1e-6); head LayerNorm with the feature tap

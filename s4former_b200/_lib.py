@@ -47,6 +47,7 @@ _SPEC = {
     's4_gemm': (_I, [C.POINTER(GemmParams), _P]),
     's4_gemm_uses_tc': (_I, [C.POINTER(GemmParams)]),
     's4_set_tc_pair_mode': (_I, [_I]),
+    's4_set_tc_sched': (_I, [_I]),
     's4_layernorm_fwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P]),
     's4_layernorm_bwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     's4_attention_workspace': (_Z, [_I, _I, _I, _I, _I, _I]),

@@ -25,6 +25,8 @@
 // Replaces the cuBLAS / cuDNN calls PyTorch makes for the reference's nn.Linear /
 // nn.MultiheadAttention / Conv2d layers (vit.py:113-127, embed.py:145-153,
 // setr_up_head.py:57-64).
+#include <mutex>
+
 #include "common.cuh"
 #include "gemm_params.h"
 #include "tc_common.cuh"
@@ -70,6 +72,9 @@ struct TcParams {
   // produces dY also emits colsum(dY)) and BatchNorm batch statistics (conv forward).
   float* colsum;
   float* colsq;
+  // dynamic tile scheduler: sched[0] = next tile index, sched[1] = CTA groups that have finished
+  // (both self-resetting: the last group to leave zeroes them); null = static round-robin
+  int* sched;
 };
 
 constexpr int EPI_WARP_BYTES = 8192;     // per epilogue warp: OUT[2] + X[2] boxes of 2 KB
@@ -164,6 +169,77 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
   return t;
 }
 
+
+// ---- dynamic tile queue -----------------------------------------------------------------------
+// Static round-robin tile assignment makes a persistent grid as slow as its slowest CTA: when
+// another kernel holds some SMs (NCCL's all-reduce CTAs during the data-parallel backward), the
+// CTAs that are not yet resident start a full tile-share late and the launch takes ~2x.  With
+// p.sched the LEADER producer takes tiles from a global counter (the atomic for the next tile is
+// issued when a tile's loads start, so its latency hides under them) and publishes them through a
+// 4-slot shared-memory queue that the other roles (and, for a CTA pair, the peer CTA: the index
+// travels by st.async with complete_tx on the peer's queue barrier) consume in order.  CTAs that
+// become resident late find the counter exhausted and leave.
+constexpr int TQ = 4;
+__device__ __forceinline__ uint32_t peer_addr(uint32_t a) {      // same offset in CTA rank 1 of the pair
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 1;" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ void st_async_u32(uint32_t raddr, uint32_t v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
+               ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// A role's view of the tile sequence (whole warp, uniform control flow).
+struct TileSeq {
+  uint32_t q_base;      // bar_base + 640: full[TQ] (8 B each), empty[TQ], values[TQ] (4 B each)
+  int n;                // tiles taken so far
+  int step, total;
+  bool dyn, pair, peer, rearm;
+  __device__ __forceinline__ uint32_t full(int s) const { return q_base + 8u * s; }
+  __device__ __forceinline__ uint32_t empty(int s) const { return q_base + 32u + 8u * s; }
+  __device__ __forceinline__ uint32_t val(int s) const { return q_base + 64u + 4u * s; }
+  // consumer: the n-th tile of this CTA group (static: first + n * step)
+  __device__ __forceinline__ int take(int first) {
+    if (!dyn) return first + (n++) * step;
+    const int s = n & (TQ - 1);
+    tc::mbar_wait(full(s), (uint32_t)(n / TQ) & 1u);
+    // (broadcast from lane 0: tells the compiler the value is warp-uniform, so the coordinates
+    // derived from it stay in uniform registers)
+    const int tile = __shfl_sync(0xffffffffu, (int)lds_u32(val(s)), 0);
+    if ((threadIdx.x & 31) == 0) {
+      if (peer) {
+        tc::mbar_arrive_leader(empty(s));
+        if (rearm) tc::mbar_expect_tx(full(s), 4);     // the peer producer arms the slot's next use
+      } else {
+        tc::mbar_arrive(empty(s));
+      }
+    }
+    ++n;
+    return tile;
+  }
+  // leader producer: hand tile number `tile` (index n of the sequence) to everybody else
+  __device__ __forceinline__ void publish(int tile) {
+    const int s = n & (TQ - 1);
+    tc::mbar_wait(empty(s), ((uint32_t)(n / TQ) & 1u) ^ 1u);
+    if ((threadIdx.x & 31) == 0) {
+      sts_u32(val(s), (uint32_t)tile);
+      tc::mbar_arrive(full(s));
+      if (pair) st_async_u32(peer_addr(val(s)), (uint32_t)tile, peer_addr(full(s)));
+    }
+    __syncwarp();
+    ++n;
+  }
+};
+
 // STATS: the epilogue also emits column sums (/ sums of squares) of the output.  A separate
 // instantiation: the two reduce-scatter butterflies add ~250 instructions per 32-column chunk,
 // and compiled into every GEMM they slowed the plain epilogues down (register count 118 -> 151,
@@ -194,6 +270,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n * p.nb * p.splits;
+  const bool dyn = p.sched != nullptr;
+  // the first tile of the group is requested before anything else so that the round trip runs under
+  // the barrier / TMEM set-up
+  int first_dyn = 0;
+  if (dyn && warp == 0 && lane == 0 && rank == 0) first_dyn = atomicAdd(p.sched, 1);
+  TileSeq seq;
+  seq.q_base = bar_base + 640u;
+  seq.n = 0;
+  seq.step = tile_step;
+  seq.total = total_tiles;
+  seq.dyn = dyn;
+  seq.pair = PAIR;
+  seq.peer = PAIR && rank == 1;
+  seq.rearm = false;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
@@ -216,7 +306,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::mbar_init(xbar(w, 0), 1);
       tc::mbar_init(xbar(w, 1), 1);
     }
+    for (int s = 0; s < TQ; ++s) {
+      tc::mbar_init(seq.full(s), 1);
+      // consumers of a published tile: MMA warp + epilogue warps of the leader, producer + epilogue
+      // warps of the peer
+      tc::mbar_init(seq.empty(s), (1 + NUM_EPI_WARPS) * CT);
+    }
     tc::fence_barrier_init();
+    if (dyn && PAIR && rank == 1)
+      for (int s = 0; s < TQ; ++s) tc::mbar_expect_tx(seq.full(s), 4);    // armed for the first use
   }
   if (warp == 2) {
     if (PAIR) tc::tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
@@ -258,7 +356,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       const int nb_off = rank * C::BN_CTA;          // this CTA's slice of the B tile
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const bool publisher = dyn && rank == 0;
+      seq.rearm = true;
+      int tile;
+      if (publisher) {
+        tile = __shfl_sync(0xffffffffu, first_dyn, 0);
+        seq.publish(tile);
+      } else {
+        tile = seq.take(tile_first);
+      }
+      for (; tile < total_tiles;) {
+        // the request for the next tile is in flight while this one is loaded
+        int next_req = 0;
+        if (publisher && lane == 0) next_req = atomicAdd(p.sched, 1);
+        auto advance = [&]() {
+          if (publisher) {
+            tile = __shfl_sync(0xffffffffu, next_req, 0);
+            seq.publish(tile);
+          } else {
+            tile = seq.take(tile_first);
+          }
+        };
         const TileCoord t = decode_tile(p, tile, BN, CT, rank);
         if (p.a_mode == OP_KMAJOR && p.b_mode == OP_KMAJOR) {
           // ---- plain GEMM, both operands K-major (forward / dgrad linear layers) ----
@@ -271,6 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             load(sa + A_STAGE_BYTES, &tmB, full_bar(stage), k0, t.n0 + nb_off, t.z2, t.z1);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
           }
+          advance();
           continue;
         }
         // conv forward: the m-tile is a cTH x cTW pixel window of image cb
@@ -341,6 +460,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
+        advance();
+      }
+      if (publisher && lane == 0) {
+        // this group has taken its terminating index: the last group to get here re-arms the counters
+        const int groups = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+        __threadfence();
+        if (atomicAdd(p.sched + 1, 1) == groups - 1) {
+          p.sched[0] = 0;
+          p.sched[1] = 0;
+          __threadfence();
+        }
       }
     }
   } else if (warp == 1) {
@@ -369,7 +499,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      for (int tile = seq.take(tile_first); tile < total_tiles; tile = seq.take(tile_first)) {
         const TileCoord t = decode_tile(p, tile, BN, CT, rank);
         tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc::fence_after_sync();
@@ -424,7 +554,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int xi = 0, si = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+    for (int tile = seq.take(tile_first); tile < total_tiles; tile = seq.take(tile_first)) {
       const TileCoord t = decode_tile(p, tile, BN, CT, rank);
       const int c_begin = half * CH_PER_WARP;
       const int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
@@ -584,7 +714,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+    for (int tile = seq.take(tile_first); tile < total_tiles; tile = seq.take(tile_first)) {
       const TileCoord t = decode_tile(p, tile, BN, CT, rank);
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::fence_after_sync();
@@ -724,11 +854,59 @@ EncodeFn get_encode_fn() {
   return fn;
 }
 
+// Counters of the dynamic tile scheduler: one pair per (device, stream slot), zeroed once (the kernel
+// leaves them zeroed).  Kernels of one stream run one after the other, so they can share a pair;
+// Static round-robin is the default (it is 1-2 us per launch faster when the GPU is not shared);
+// s4_set_tc_sched(1) / S4_TC_SCHED=1 selects the dynamic scheduler - the data-parallel wrapper does
+// when NCCL kernels overlap the backward.  Never allocated during a stream capture.
+int g_sched_mode = -1;     // 0 static round-robin, 1 dynamic (global tile counter)
+int env_sched_mode() {
+  if (g_sched_mode < 0) {
+    const char* e = getenv("S4_TC_SCHED");
+    g_sched_mode = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_sched_mode;
+}
+
+int* sched_counters(cudaStream_t stream) {
+  if (!env_sched_mode()) return nullptr;
+  constexpr int SLOTS = 32, MAXDEV = 16;
+  static int* pool[MAXDEV] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;
+  if (!pool[dev]) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    int* ptr = nullptr;
+    if (cudaMalloc(&ptr, SLOTS * 2 * sizeof(int) * 16) != cudaSuccess ||
+        cudaMemset(ptr, 0, SLOTS * 2 * sizeof(int) * 16) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    pool[dev] = ptr;
+  }
+  // one pair per stream (exact table, 128 bytes apart); more than SLOTS streams: static scheduling
+  static std::mutex mu;
+  static cudaStream_t owner[MAXDEV][SLOTS];
+  static int used[MAXDEV] = {0};
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < used[dev]; ++i)
+    if (owner[dev][i] == stream) return pool[dev] + (size_t)i * 32;
+  if (used[dev] >= SLOTS) return nullptr;
+  owner[dev][used[dev]] = stream;
+  return pool[dev] + (size_t)(used[dev]++) * 32;
+}
+
 // p.tiles_m already counts CTA-group tiles (pairs for CT = 2)
 template <int BN, int CT, bool STATS>
 int launch_bn_s(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const CUtensorMap& txm,
-                const TcParams& p, cudaStream_t stream) {
+                const TcParams& p_in, cudaStream_t stream) {
   using C = Cfg<BN, CT>;
+  TcParams p = p_in;
+  p.sched = sched_counters(stream);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -863,6 +1041,12 @@ TileCfg pick_cfg(long long m_tiles, int N, int kblocks, int nb, int splits, bool
 bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 }  // namespace
+
+extern "C" int s4_set_tc_sched(int mode) {
+  const int prev = env_sched_mode();
+  if (mode == 0 || mode == 1) g_sched_mode = mode;
+  return prev;
+}
 
 extern "C" int s4_set_tc_pair_mode(int mode) {
   const int prev = env_pair_mode();

@@ -18,6 +18,14 @@ class GradReducer:
         self.model, self.fg, self.group = model, flat_grads, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.backend = dist.get_backend(group) if self.world > 1 else None
+        if self.world > 1 and self.backend == 'nccl':
+            # NCCL's all-reduce CTAs hold SMs while backward runs: a persistent GEMM grid with a static
+            # tile share per CTA then takes ~2x (the CTAs that are not resident start a whole share
+            # late).  The dynamic tile scheduler lets the resident CTAs take those tiles instead.
+            import os
+            if os.environ.get('S4_TC_SCHED') is None:
+                from . import _lib
+                _lib.load().s4_set_tc_sched(1)
         # buckets over the flat buffer, walking parameters in reverse registration order
         order = list(reversed(self.fg.params))
         self.buckets = []          # [lo, hi) element ranges of the flat buffer

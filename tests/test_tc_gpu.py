@@ -130,6 +130,69 @@ def test_tc_gemm_ab_mnmajor_splitk():
     _gemm_case(136, 200, 1000, BF, L.BACKEND_TC, a_mn=True, b_mn=True, c32=True, accumulate=True, split_k=4)
 
 
+@pytest.fixture
+def dyn_sched():
+    """The persistent grid takes its tiles from a global counter instead of a static round-robin."""
+    prev = L.load().s4_set_tc_sched(1)
+    yield
+    L.load().s4_set_tc_sched(prev)
+
+
+def test_tc_dynamic_tile_scheduler(dyn_sched, pair_mode):
+    """Every operand form / epilogue under the dynamic scheduler, single-CTA tiles and CTA pairs."""
+    _gemm_case(1025, 768, 768, BF, L.BACKEND_TC, bias=True, res=True)
+    _gemm_case(2050, 2304, 768, BF, L.BACKEND_TC, bias=True)
+    _gemm_case(8200, 768, 3072, BF, L.BACKEND_TC, bias=True, res=True)
+    _gemm_case(300, 256, 128, BF, L.BACKEND_TC, bias=True, act=True)
+    _gemm_case(300, 256, 128, BF, L.BACKEND_TC, aux=True)
+    _gemm_case(200, 136, 136, BF, L.BACKEND_TC, batch=(2, 3))
+    _gemm_case(300, 256, 200, BF, L.BACKEND_TC, b_mn=True)
+    _gemm_case(200, 192, 264, BF, L.BACKEND_TC, a_mn=True)
+    _gemm_case(3072, 768, 8200, BF, L.BACKEND_TC, a_mn=True, b_mn=True, c32=True, accumulate=True, split_k=6)
+    _gemm_case(768, 2304, 1000, BF, L.BACKEND_TC, a_mn=True, b_mn=True, c32=True, accumulate=True, split_k=0)
+    _gemm_case(64, 64, 64, BF, L.BACKEND_TC)              # one tile: 1 CTA group, the others never start
+    x, dy, wf, wd, xr, wr, yr, st = _conv_case(2, 64, 64, 128, 256)
+    y = torch.empty(2, 64, 64, 256, device=DEV, dtype=BF)
+    L.call('s4_conv3x3_fwd', x.data_ptr(), wf.data_ptr(), y.data_ptr(), 2, 64, 64, 128, 256, L.BF16, L.BACKEND_TC, st)
+    assert rel(y.float().permute(0, 3, 1, 2), yr) < 2e-2
+    dx = torch.empty_like(x)
+    L.call('s4_conv3x3_dgrad', dy.data_ptr(), wd.data_ptr(), dx.data_ptr(), 2, 64, 64, 128, 256, L.BF16, L.BACKEND_TC, st)
+    assert rel(dx.float().permute(0, 3, 1, 2), xr.grad) < 2e-2
+    dw = torch.zeros(256, 128, 3, 3, device=DEV)
+    L.call('s4_conv3x3_wgrad', x.data_ptr(), dy.data_ptr(), dw.data_ptr(), 2, 64, 64, 128, 256, L.BF16, L.BACKEND_TC, st)
+    assert rel(dw, wr.grad) < 2e-2
+
+
+def test_tc_dynamic_scheduler_same_bits_repeated_and_two_streams(dyn_sched):
+    """Same tile arithmetic as the static schedule (bit-identical outputs), the self-resetting
+    counters survive back-to-back launches, and two streams use separate counters."""
+    g = gen(31)
+    M, N, K = 16400, 768, 768
+    a = torch.randn(M, K, generator=g).to(DEV, BF)
+    w = torch.randn(N, K, generator=g).to(DEV, BF) * 0.05
+    bias = torch.randn(N, generator=g).to(DEV)
+    w2 = torch.randn(3 * N, K, generator=g).to(DEV, BF) * 0.05
+    L.load().s4_set_tc_sched(0)
+    want = ops.linear_fwd(a, w, bias)
+    want2 = ops.linear_fwd(a, w2, None)
+    L.load().s4_set_tc_sched(1)
+    for _ in range(50):
+        got = ops.linear_fwd(a, w, bias)
+    assert torch.equal(got, want)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(10):
+        with torch.cuda.stream(s1):
+            o1 = ops.linear_fwd(a, w, bias)
+        with torch.cuda.stream(s2):
+            o2 = ops.linear_fwd(a, w2, None)
+        outs.append((o1, o2))
+    torch.cuda.synchronize()
+    for o1, o2 in outs:
+        assert torch.equal(o1, want) and torch.equal(o2, want2)
+
+
 def _conv_case(B, H, W, Cin, Cout, seed=20):
     g = gen(seed)
     x = torch.randn(B, H, W, Cin, generator=g).to(DEV, BF)
