@@ -313,6 +313,21 @@ int s4_accumulate_crop(const float* crop, float* preds, float* count, int B, int
 int s4_intersect_union(const long long* pred, const long long* label, long long n, int num_classes,
                        long long ignore_index, long long* hist3, cudaStream_t stream);
 
+/* ---- SyncBatchNorm statistics over NVLink peer memory -------------------
+ * Replaces the cross-rank reduction inside torch.nn.SyncBatchNorm (norm_cfg type='SyncBN' of
+ * configs/_base_/models/setr_pup.py; mmcv ConvModule at setr_up_head.py:57-64) for the [2, C] fp32
+ * statistics of one layer: a one-shot all-reduce (sum) over symmetric buffers, one small kernel per
+ * call, replayable inside a CUDA graph.  Every rank allocates s4_peer_allreduce_buffer_bytes() of
+ * peer-mapped memory (zeroed once, before the first call on any rank); peer_bufs_dev is a DEVICE array
+ * of `world` pointers to those buffers in rank order; seq_state is one zero-initialised uint32 of local
+ * device memory per buffer set.  data [n] (n <= s4_peer_allreduce_max_elems()) is reduced in place;
+ * all ranks add in rank order, so the sums are bit-identical everywhere.  All ranks must make the
+ * same sequence of calls. */
+long long s4_peer_allreduce_buffer_bytes(void);
+int s4_peer_allreduce_max_elems(void);
+int s4_peer_allreduce_f32(float* data, int n, const void* peer_bufs_dev, int rank, int world,
+                          unsigned* seq_state, cudaStream_t stream);
+
 /* ---- GPU-side input pipeline -------------------------------------
  * configs/setr/..._MT_w_ours.py:42-126 strong / weak / sup branch pipelines after RandomCrop / RandomFlip:
  * PhotoMetricDistortion (transforms.py:1165-1272), Normalize (:572-604), Pad (:484-565),

@@ -94,6 +94,9 @@ _SPEC = {
     's4_intersect_union': (_I, [_P, _P, _L, _I, _L, _P, _P]),
     's4_branch_pipeline': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _P]),
     's4_pmd_params_size': (_I, []),
+    's4_peer_allreduce_buffer_bytes': (_L, []),
+    's4_peer_allreduce_max_elems': (_I, []),
+    's4_peer_allreduce_f32': (_I, [_P, _I, _P, _I, _I, _P, _P]),
     's4_sgd_ema_multi_tensor': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P]),
 }
 

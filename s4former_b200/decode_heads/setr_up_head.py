@@ -125,7 +125,11 @@ class SETRUPHead(BaseDecodeHead):
         if self.up_convs[0][0].sync and self.training:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                return dict(world=dist.get_world_size(), group=None)
+                peer = None
+                if dist.get_backend() == 'nccl':
+                    from ..parallel import PeerAllReduce
+                    peer = PeerAllReduce.get(None)
+                return dict(world=dist.get_world_size(), group=None, peer=peer)
         return None
 
     def forward(self, x, PatchMix_N=0, PatchMixIndex=None, return_last_feat=False):

@@ -575,6 +575,9 @@ def _all_reduce_stats(t, group_info):
     """SyncBN: sum the per-rank statistics over the data-parallel group (reference N2)."""
     if group_info is not None and group_info.get('world', 1) > 1:
         import torch.distributed as dist
+        peer = group_info.get('peer')
+        if peer is not None and peer.usable(t):
+            return peer.all_reduce(t)        # one-shot sum over NVLink peer memory (csrc/peer.cu)
         dist.all_reduce(t, group=group_info.get('group'))
     return t
 

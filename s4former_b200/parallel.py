@@ -13,6 +13,68 @@ import torch
 import torch.distributed as dist
 
 
+class PeerAllReduce:
+    """One-shot all-reduce (sum) of small fp32 vectors over NVLink peer memory: SyncBatchNorm's
+    per-layer statistics (``s4_peer_allreduce_f32``, csrc/peer.cu).  Collective constructor (every
+    rank of ``group``, outside a stream capture); ``PeerAllReduce.get`` returns None when symmetric
+    memory cannot be set up on ANY rank, and the callers fall back to ``dist.all_reduce``."""
+
+    _cache = {}
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        lib = _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        n = int(lib.s4_peer_allreduce_buffer_bytes()) // 4
+        self.max_elems = int(lib.s4_peer_allreduce_max_elems())
+        self.buf = symm.empty(n, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        self.ptrs = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        self.seq = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)          # every buffer is zeroed before anybody's first call
+
+    def all_reduce(self, t):
+        from . import _lib, ops
+        _lib.call('s4_peer_allreduce_f32', t.data_ptr(), t.numel(), self.ptrs.data_ptr(), self.rank, self.world,
+                  self.seq.data_ptr(), ops._st())
+        return t
+
+    def usable(self, t):
+        return (t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.max_elems
+                and t.device == self.buf.device)
+
+    @classmethod
+    def get(cls, group=None):
+        """The group's reducer, created on first use (collective).  S4_PEER_SYNCBN=0 disables it."""
+        import os
+        key = id(group) if group is not None else 0
+        if key in cls._cache:
+            return cls._cache[key]
+        obj = None
+        ok = 0
+        if (os.environ.get('S4_PEER_SYNCBN', '1') != '0' and dist.get_backend(group) == 'nccl'
+                and not torch.cuda.is_current_stream_capturing()):
+            try:
+                obj = cls(group, torch.device('cuda', torch.cuda.current_device()))
+                ok = 1
+            except Exception as e:       # no symmetric memory on this box / build: every rank falls back
+                import warnings
+                warnings.warn(f'PeerAllReduce unavailable ({type(e).__name__}: {e}); SyncBN statistics use NCCL')
+                obj = None
+            flag = torch.tensor([ok], dtype=torch.int32, device='cuda')
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                obj = None
+        elif torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            return None                  # not cached: try again outside the capture
+        cls._cache[key] = obj
+        return obj
+
+
 class GradReducer:
     def __init__(self, model, flat_grads, bucket_bytes=25 * 1024 * 1024, group=None):
         self.model, self.fg, self.group = model, flat_grads, group

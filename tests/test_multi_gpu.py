@@ -101,7 +101,9 @@ def _worker(rank, world, port, variant, dtype_name, n_sup, n_unsup, out_dir):
         img, gt, metas = _batch(n_sup, n_unsup)
         img, gt, metas = _shard(img, gt, metas, rank, world, n_sup, n_unsup)
         logs, grads, sd, late = _steps(m, img, gt, metas, dev)
-        torch.save(dict(logs=logs, grads=grads, sd=sd, late=late), os.path.join(out_dir, f'rank{rank}.pt'))
+        from s4former_b200.parallel import PeerAllReduce
+        peer = bool(PeerAllReduce._cache) and all(v is not None for v in PeerAllReduce._cache.values())
+        torch.save(dict(logs=logs, grads=grads, sd=sd, late=late, peer=peer), os.path.join(out_dir, f'rank{rank}.pt'))
     finally:
         dist.destroy_process_group()
 
@@ -135,7 +137,8 @@ def test_two_ranks_syncbn_equal_one_rank_bn(variant, dtype_name, tol):
         np.random.rand, torch.randperm = saved
         from s4former_b200 import ops
         ops.set_compute_dtype(torch.bfloat16)
-    rep = dict(variant=variant, dtype=dtype_name, late_buckets=[r['late'] for r in ranks])
+    rep = dict(variant=variant, dtype=dtype_name, late_buckets=[r['late'] for r in ranks],
+               syncbn_over_peer_memory=[r.get('peer') for r in ranks])
     # both ranks hold the same reduced quantities
     for k in ranks[0]['grads']:
         assert _rel(ranks[0]['grads'][k], ranks[1]['grads'][k]) < 1e-6, ('ranks disagree on reduced grad', k)
@@ -168,3 +171,83 @@ def test_two_ranks_syncbn_equal_one_rank_bn(variant, dtype_name, tol):
     assert not bad, bad
     # every gradient bucket was signalled ready during backward (overlapped all-reduce), none late
     assert all(l == 0 for l in rep['late_buckets']), rep['late_buckets']
+
+
+def _peer_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    warnings.filterwarnings('ignore')
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        from s4former_b200.parallel import PeerAllReduce
+        peer = PeerAllReduce.get(None)
+        res = dict(available=peer is not None)
+        if peer is not None:
+            g = torch.Generator().manual_seed(100 + rank)
+            worst = 0.0
+            for i in range(64):                      # eager calls of varying length
+                n = [512, 1, 2048, 37, 1024][i % 5]
+                t = torch.randn(n, generator=g).to(dev)
+                want = t.clone()
+                dist.all_reduce(want)
+                got = peer.all_reduce(t.clone())
+                worst = max(worst, float((got - want).abs().max()))
+            res['eager_worst_abs'] = worst
+            # the same kernel inside a CUDA graph, replayed (sequence numbers live on the device)
+            x = torch.randn(2, 256, generator=g).to(dev)
+            y = torch.empty_like(x)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(s):
+                with torch.cuda.graph(graph, stream=s, capture_error_mode='thread_local'):
+                    y.copy_(x)
+                    peer.all_reduce(y)
+                    y.mul_(0.5)
+                    peer.all_reduce(y)
+            torch.cuda.synchronize()
+            gw = 0.0
+            for it in range(20):
+                x.copy_(torch.randn(2, 256, generator=g))
+                want = x.clone()
+                dist.all_reduce(want)
+                want.mul_(0.5)
+                dist.all_reduce(want)
+                graph.replay()
+                torch.cuda.synchronize()
+                gw = max(gw, float((y - want).abs().max() / want.abs().max()))
+            res['graph_worst_rel'] = gw
+            # every rank holds bit-identical sums (same order of additions)
+            z = torch.randn(1024, generator=g).to(dev)
+            peer.all_reduce(z)
+            both = [torch.empty_like(z) for _ in range(world)]
+            dist.all_gather(both, z)
+            res['ranks_bit_identical'] = all(torch.equal(both[0], b) for b in both)
+        torch.save(res, os.path.join(out_dir, f'peer{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_allreduce_two_gpus():
+    """SyncBN's statistics sum over NVLink peer memory (csrc/peer.cu) == NCCL all_reduce, eagerly and
+    replayed inside a CUDA graph; identical bits on every rank."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    out_dir = tempfile.mkdtemp()
+    port = 29500 + (os.getpid() % 150)
+    mp.spawn(_peer_worker, args=(2, port, out_dir), nprocs=2, join=True)
+    rs = [torch.load(os.path.join(out_dir, f'peer{r}.pt'), weights_only=False) for r in range(2)]
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    import json
+    with open(os.path.join(ROOT, 'gpurun_out', 'peer_allreduce.json'), 'w') as f:
+        json.dump(rs, f, indent=1)
+    assert rs[0]['available'] == rs[1]['available']
+    if not rs[0]['available']:
+        pytest.skip('symmetric memory is not available on this box: SyncBN statistics use NCCL')
+    for r in rs:
+        assert r['eager_worst_abs'] < 1e-5, r
+        assert r['graph_worst_rel'] < 1e-6, r
+        assert r['ranks_bit_identical'], r
