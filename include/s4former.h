@@ -327,6 +327,14 @@ long long s4_peer_allreduce_buffer_bytes(void);
 int s4_peer_allreduce_max_elems(void);
 int s4_peer_allreduce_f32(float* data, int n, const void* peer_bufs_dev, int rank, int world,
                           unsigned* seq_state, cudaStream_t stream);
+/* SyncBN forward in one kernel: the same exchange of the LOCAL stats [2, C] = (sum, sumsq) followed by
+ * s4_bn_finalize's arithmetic on the rank-ordered sums (count = total elements per channel over all
+ * ranks).  stats is not modified. */
+int s4_bn_finalize_peer(const float* stats, double count, float eps, float momentum,
+                        const float* gamma, const float* beta, float* mean, float* invstd,
+                        float* scale, float* shift, float* running_mean, float* running_var,
+                        long long* num_batches_tracked, int C, const void* peer_bufs_dev, int rank,
+                        int world, unsigned* seq_state, cudaStream_t stream);
 
 /* ---- GPU-side input pipeline -------------------------------------
  * configs/setr/..._MT_w_ours.py:42-126 strong / weak / sup branch pipelines after RandomCrop / RandomFlip:

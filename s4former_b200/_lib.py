@@ -97,6 +97,7 @@ _SPEC = {
     's4_peer_allreduce_buffer_bytes': (_L, []),
     's4_peer_allreduce_max_elems': (_I, []),
     's4_peer_allreduce_f32': (_I, [_P, _I, _P, _I, _I, _P, _P]),
+    's4_bn_finalize_peer': (_I, [_P, _D, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P]),
     's4_sgd_ema_multi_tensor': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P]),
 }
 

@@ -35,14 +35,11 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(256)
-peer_allreduce_kernel(float* __restrict__ data, int n, const unsigned long long* __restrict__ peers, int rank,
-                      int world, unsigned* __restrict__ seq_state) {
-  __shared__ unsigned long long sp[PEER_MAXW];
+// steps 1-3 for the calling block: publish `data`, signal, wait.  Returns the parity of the call.
+__device__ __forceinline__ unsigned peer_exchange(const float* __restrict__ data, int n,
+                                                  const unsigned long long* sp, int rank, int world,
+                                                  unsigned seq) {
   const int tid = threadIdx.x;
-  if (tid < world) sp[tid] = peers[tid];
-  const unsigned seq = *seq_state + 1u;
-  __syncthreads();
   const unsigned par = seq & 1u;
   float* mine = reinterpret_cast<float*>(sp[rank]) + par * PEER_NMAX;
   for (int i = tid; i < n; i += blockDim.x) mine[i] = data[i];
@@ -64,6 +61,18 @@ peer_allreduce_kernel(float* __restrict__ data, int n, const unsigned long long*
     }
   }
   __syncthreads();
+  return par;
+}
+
+__global__ void __launch_bounds__(256)
+peer_allreduce_kernel(float* __restrict__ data, int n, const unsigned long long* __restrict__ peers, int rank,
+                      int world, unsigned* __restrict__ seq_state) {
+  __shared__ unsigned long long sp[PEER_MAXW];
+  const int tid = threadIdx.x;
+  if (tid < world) sp[tid] = peers[tid];
+  const unsigned seq = *seq_state + 1u;
+  __syncthreads();
+  const unsigned par = peer_exchange(data, n, sp, rank, world, seq);
   for (int i = tid; i < n; i += blockDim.x) {
     float acc = 0.f;
     for (int r = 0; r < world; ++r)
@@ -71,6 +80,50 @@ peer_allreduce_kernel(float* __restrict__ data, int n, const unsigned long long*
     data[i] = acc;
   }
   if (tid == 0) *seq_state = seq;
+}
+
+// SyncBN forward in ONE kernel: exchange the local (sum, sumsq) [2, C] over peer memory, add them in
+// rank order, and finalize (mean, invstd, scale = gamma invstd, shift, running statistics) exactly as
+// bn_finalize_kernel (head.cu) does from NCCL-reduced sums.
+__global__ void __launch_bounds__(256)
+peer_bn_finalize_kernel(const float* __restrict__ stats, double count, float eps, float momentum,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
+                        float* __restrict__ shift, float* __restrict__ rmean, float* __restrict__ rvar,
+                        long long* __restrict__ nbt, int C, const unsigned long long* __restrict__ peers,
+                        int rank, int world, unsigned* __restrict__ seq_state) {
+  __shared__ unsigned long long sp[PEER_MAXW];
+  const int tid = threadIdx.x;
+  if (tid < world) sp[tid] = peers[tid];
+  const unsigned seq = *seq_state + 1u;
+  __syncthreads();
+  const unsigned par = peer_exchange(stats, 2 * C, sp, rank, world, seq);
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < world; ++r) {
+      const float* pr = reinterpret_cast<const float*>(sp[r]) + par * PEER_NMAX;
+      s1 += ld_relaxed_sys(pr + c);
+      s2 += ld_relaxed_sys(pr + C + c);
+    }
+    const double mu = (double)s1 / count;
+    double var = (double)s2 / count - mu * mu;
+    if (var < 0) var = 0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    mean[c] = (float)mu;
+    invstd[c] = is;
+    const float sc = gamma[c] * is;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mu * sc;
+    if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mu;
+    if (rvar) {
+      const double unb = count > 1 ? var * count / (count - 1.0) : var;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+    }
+  }
+  if (tid == 0) {
+    *seq_state = seq;
+    if (nbt) *nbt += 1;
+  }
 }
 
 }  // namespace
@@ -91,4 +144,20 @@ extern "C" int s4_peer_allreduce_f32(float* data, int n, const void* peer_bufs_d
   peer_allreduce_kernel<<<1, 256, 0, stream>>>(data, n, (const unsigned long long*)peer_bufs_dev, rank, world,
                                                seq_state);
   return s4_check_launch("peer_allreduce");
+}
+
+extern "C" int s4_bn_finalize_peer(const float* stats, double count, float eps, float momentum,
+                                   const float* gamma, const float* beta, float* mean, float* invstd,
+                                   float* scale, float* shift, float* running_mean, float* running_var,
+                                   long long* num_batches_tracked, int C, const void* peer_bufs_dev, int rank,
+                                   int world, unsigned* seq_state, cudaStream_t stream) {
+  S4ProfScope prof_("bn_finalize_peer", 0.0, 1, stream);
+  S4_REQUIRE(C >= 1 && 2 * C <= PEER_NMAX, "bn_finalize_peer: C=%d not in [1,%d]", C, PEER_NMAX / 2);
+  S4_REQUIRE(world >= 1 && world <= PEER_MAXW && rank >= 0 && rank < world, "bn_finalize_peer: rank %d / world %d",
+             rank, world);
+  S4_REQUIRE(stats && peer_bufs_dev && seq_state, "bn_finalize_peer: null pointer");
+  peer_bn_finalize_kernel<<<1, 256, 0, stream>>>(stats, count, eps, momentum, gamma, beta, mean, invstd, scale,
+                                                 shift, running_mean, running_var, num_batches_tracked, C,
+                                                 (const unsigned long long*)peer_bufs_dev, rank, world, seq_state);
+  return s4_check_launch("bn_finalize_peer");
 }

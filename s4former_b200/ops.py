@@ -302,7 +302,19 @@ def reset_pending():
     return stale
 
 
+_frozen_scratch = {}
+
+
 def grad_buffer(p):
+    """The tensor a kernel accumulates ``p``'s gradient into.  A frozen parameter
+    (``requires_grad=False``) gets a shared scratch buffer nobody reads — its ``.grad`` stays None,
+    as autograd would leave it; the weight-gradient GEMMs of frozen weights are skipped altogether."""
+    if not p.requires_grad:
+        key = (tuple(p.shape), p.device)
+        buf = _frozen_scratch.get(key)
+        if buf is None:
+            buf = _frozen_scratch[key] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+        return buf
     if p.grad is None:
         flat = getattr(p, '_s4_flat_view', None)     # a foreign zero_grad(set_to_none=True) dropped it:
         if flat is not None:                         # re-attach the slice of the flat gradient buffer
@@ -386,9 +398,10 @@ def linear_wgrad(dy, x, w_param, b_param):
     """w.grad [N,K] += dy^T x ; b.grad [N] += colsum(dy)."""
     M, N = dy.shape
     K = x.shape[1]
-    gw = grad_buffer(w_param)
-    gemm(dy, x, gw, N, K, M, (1, N), (K, 1), K, accumulate=True, split_k=_wgrad_split(N, K, M))
-    if b_param is not None:
+    if w_param.requires_grad:
+        gw = grad_buffer(w_param)
+        gemm(dy, x, gw, N, K, M, (1, N), (K, 1), K, accumulate=True, split_k=_wgrad_split(N, K, M))
+    if b_param is not None and b_param.requires_grad:
         gb = grad_buffer(b_param)
         L.call('s4_colsum', _p(dy), _p(gb), None, M, N, _code(dy.dtype), _st())
 
@@ -639,12 +652,21 @@ def _bn_scale_shift(conv_bn, y2d, rows, training, group_info, stats=None):
         stats = arena_zeros((2, Cc), dev)
         L.call('s4_colsum', _p(y2d), _p(stats[0]), _p(stats[1]), rows, Cc, _code(y2d.dtype), _st())
     count = float(rows)
-    if group_info is not None and group_info.get('world', 1) > 1:
-        _all_reduce_stats(stats, group_info)
-        count *= group_info['world']
     mean = torch.empty_like(scale)
     invstd = torch.empty_like(scale)
     mom = bn.momentum if bn.momentum is not None else 0.1
+    if group_info is not None and group_info.get('world', 1) > 1:
+        count *= group_info['world']
+        peer = group_info.get('peer')
+        if peer is not None and peer.usable(stats):
+            # SyncBN forward in one kernel: exchange the local sums over NVLink peer memory, add them in
+            # rank order, finalize (csrc/peer.cu)
+            L.call('s4_bn_finalize_peer', _p(stats), count, bn.eps, mom, _p(bn.weight.detach()),
+                   _p(bn.bias.detach()), _p(mean), _p(invstd), _p(scale), _p(shift), _p(bn.running_mean),
+                   _p(bn.running_var), _p(bn.num_batches_tracked), Cc, _p(peer.ptrs), peer.rank, peer.world,
+                   _p(peer.seq), _st())
+            return scale, shift, mean, invstd, count
+        _all_reduce_stats(stats, group_info)
     L.call('s4_bn_finalize', _p(stats[0]), _p(stats[1]), count, bn.eps, mom, _p(bn.weight.detach()),
            _p(bn.bias.detach()), _p(mean), _p(invstd), _p(scale), _p(shift), _p(bn.running_mean),
            _p(bn.running_var), _p(bn.num_batches_tracked), Cc, _st())
@@ -688,8 +710,9 @@ def _conv_grads(stage, x, dyc, B, H, W, Cin, Cout, need_dx=True):
     """conv3x3 weight gradient (accumulated into conv.weight.grad) and input gradient."""
     conv = stage.conv
     dt = _code(x.dtype)
-    L.call('s4_conv3x3_wgrad', _p(x), _p(dyc), _p(grad_buffer(conv.weight)), B, H, W, Cin, Cout, dt,
-           backend(), _st())
+    if conv.weight.requires_grad:
+        L.call('s4_conv3x3_wgrad', _p(x), _p(dyc), _p(grad_buffer(conv.weight)), B, H, W, Cin, Cout, dt,
+               backend(), _st())
     dx = None
     if need_dx:
         _, wd = conv_packed(conv.weight)

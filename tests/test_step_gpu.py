@@ -458,3 +458,40 @@ def test_pasa_bias_only_on_peeled_key():
     plain, _ = ops.attention_fwd(qkv, B, L_, H, hd, None, None, 0.0)
     assert float((out.float()[:L_] - plain.float()[:L_]).norm()) > 1e-2 * float(plain.float()[:L_].norm())
     assert float((out.float()[L_:] - plain.float()[L_:]).norm()) < 1e-3 * float(plain.float()[L_:].norm())
+
+
+def test_frozen_parameters_get_no_gradient_and_change_nothing_else():
+    """requires_grad=False on an encoder layer / a head conv / a LayerNorm: their .grad stays None
+    (autograd semantics; the weight-gradient GEMMs are skipped), every other gradient is unchanged."""
+    def run(freeze):
+        ops.set_compute_dtype(torch.float32)
+        try:
+            m, _ = _build('sup')
+            frozen = []
+            if freeze:
+                for p in list(m.backbone.layers[1].parameters()) + list(m.decode_head.up_convs[0][0].conv.parameters()) \
+                        + list(m.backbone.layers[0].ln1.parameters()):
+                    p.requires_grad_(False)
+                    frozen.append(id(p))
+            img, gt, metas = gc.tiny_batch('sup')
+            O.seed_host_rng(1999)
+            losses = m.forward_train(img.to(DEV), metas, gt_semantic_seg=gt.to(DEV), iter=0)
+            total, _ = m._parse_losses(losses)
+            total.backward()
+            torch.cuda.synchronize()
+            return m, frozen
+        finally:
+            ops.set_compute_dtype(torch.bfloat16)
+    m0, _ = run(False)
+    m1, frozen = run(True)
+    g0 = dict(m0.named_parameters())
+    checked = 0
+    for n, p in m1.named_parameters():
+        if id(p) in frozen:
+            assert p.grad is None, n
+            continue
+        if g0[n].grad is None:
+            continue
+        assert torch.allclose(p.grad, g0[n].grad, rtol=1e-4, atol=1e-7), n
+        checked += 1
+    assert frozen and checked > 50
