@@ -80,8 +80,8 @@ def main():
     print('semi-supervised SegFormer configs in the tree:',
           [f for f in os.listdir(os.path.join(LR.REF, 'configs', 'segformer'))])
     for variant in ('mt', 'ours'):
-        for coin, coin_name in ((0.0, 'CutMix / shuffle coin = heads (np.random.rand() -> 0.0)'),
-                                (0.99, 'coin = tails (np.random.rand() -> 0.99)')):
+        for coin, coin_name in ((0.0, 'CutMix coin = heads (np.random.uniform(0, 1) -> 0.0)'),
+                                (0.99, 'CutMix coin = tails (np.random.uniform(0, 1) -> 0.99)')):
             print(f'\n=== variant {variant!r}: {coin_name}')
             torch.manual_seed(0)
             np.random.seed(0)
@@ -89,12 +89,15 @@ def main():
                 m = ns.builder.build_segmentor(cfg(variant))
                 m.train()
                 img, gt, metas = O.synthetic_batch(2, 2, 128, 5, seed=3, grid=16)
-                real_rand = np.random.rand
-                np.random.rand = lambda *a: coin if not a else real_rand(*a)
+                # the strong-augmentation coin is np.random.uniform(0, 1) < strong_aug_prob
+                # (encoder_decoder.py:604, :634); np.random.rand drives the cut-out box / shuffle draws
+                real_rand, real_uniform = np.random.rand, np.random.uniform
+                np.random.uniform = lambda lo=0.0, hi=1.0, size=None: (
+                    coin if (size is None and lo == 0 and hi == 1) else real_uniform(lo, hi, size))
                 try:
                     losses = m.forward_train(img, metas, gt_semantic_seg=gt, iter=10)
                 finally:
-                    np.random.rand = real_rand
+                    np.random.rand, np.random.uniform = real_rand, real_uniform
                 print('ran; loss keys:', sorted(losses.keys()))
                 for k, v in sorted(losses.items()):
                     if torch.is_tensor(v):
