@@ -98,6 +98,33 @@ def checksum(sd):
     return float(sum(v.double().abs().sum() for v in sd.values()))
 
 
+def tiny_segformer_cfg(variant='ours'):
+    """SegFormer / MiT variant (BASELINE config 5) shrunk to TINY: the
+    backbone / head of configs/segformer/segformer_mit-b4_..._CPS_sup.py with the semi-supervised
+    settings of the SETR configs ('to be synthesised', SURVEY.md hazard 7).  PatchMix_N = 4 keeps the
+    stage-4 un-shuffle block (PatchMix_N / 2 tokens) integral on a 128-pixel crop."""
+    t = TINY
+    norm_cfg = dict(type='SyncBN', requires_grad=True)
+    bb = dict(type='MixVisionTransformer', in_channels=3, embed_dims=16, num_stages=4, num_layers=[1, 2, 1, 2],
+              num_heads=[1, 2, 4, 8], patch_sizes=[7, 3, 3, 3], sr_ratios=[8, 4, 2, 1], out_indices=(0, 1, 2, 3),
+              mlp_ratio=2, qkv_bias=True, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0)
+    dh = dict(type='SegformerHead', in_channels=[16, 32, 64, 128], in_index=[0, 1, 2, 3], channels=32,
+              dropout_ratio=0.0, num_classes=t['classes'], norm_cfg=norm_cfg, align_corners=False,
+              loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0))
+    model = dict(type='EncoderDecoder', pretrained=None, backbone=bb, decode_head=dh, test_cfg=dict(mode='whole'),
+                 backbone_ema=copy.deepcopy(bb), decode_head_ema=copy.deepcopy(dh), ema=True, ema_momentum=0.999,
+                 unsup_confidence=0.95)
+    if variant == 'sup':
+        model.update(unsup_weight=0.0)
+    elif variant == 'ours':
+        model.update(unsup_weight=1.0, attn_mask_seperate_head=True, attn_mask_weight=5, adaptive_attn_mask=True,
+                     use_PatchShuffle_w_Cutmix=True, PatchMix_N=4, negative_class_ranking=True,
+                     negative_class_ranking_mode='unsup_only')
+    else:
+        raise KeyError(variant)
+    return model
+
+
 def tiny_batch(variant='ours', seed=1999):
     from oracle.s4former_oracle import synthetic_batch
     n_unsup = 0 if variant == 'sup' else 2

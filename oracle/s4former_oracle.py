@@ -115,14 +115,19 @@ def cutout_box(img_size, ratio=2):
 
 
 def cutmix(img, hard, boxes):
-    """generate_unsup_data.py:400-453: img_i*M_i + img_{(i+1)%B}*(1-M_i), same on labels."""
+    """generate_unsup_data.py:400-453: img_i*M_i + img_{(i+1)%B}*(1-M_i), same on labels.
+    Labels below the image resolution (SegFormer's quarter-resolution teacher) are nearest-resized
+    up to the image, mixed there and nearest-resized back (:407-408, :449-450): label pixel (oy, ox)
+    takes the neighbour's value iff image pixel (s*oy, s*ox) lies in the box."""
     b = img.shape[0]
+    s = img.shape[-1] // hard.shape[-1]
     out_img, out_lab = img.clone(), hard.clone()
     for i in range(b):
         y0, y1, x0, x1 = boxes[i]
         j = (i + 1) % b
         out_img[i, :, y0:y1, x0:x1] = img[j, :, y0:y1, x0:x1]
-        out_lab[i, y0:y1, x0:x1] = hard[j, y0:y1, x0:x1]
+        ly0, ly1, lx0, lx1 = -(-y0 // s), -(-y1 // s), -(-x0 // s), -(-x1 // s)
+        out_lab[i, ly0:ly1, lx0:lx1] = hard[j, ly0:ly1, lx0:lx1]
     return out_img, out_lab
 
 
@@ -430,14 +435,20 @@ class OracleEncoderDecoder(nn.Module):
 
         def mk_head(cfg):
             cfg = dict(cfg)
-            cfg.pop('type', None)
+            typ = cfg.pop('type', 'SETRUPHead')
             lw = cfg.pop('loss_decode', {}).get('loss_weight', 1.0)
+            if typ == 'SegformerHead':          # oracle only, no CUDA path yet
+                from .segformer_oracle import OracleSegformerHead
+                return OracleSegformerHead(loss_weight=lw, **cfg)
             return OracleSETRUPHead(loss_weight=lw, **cfg)
 
         def mk_bb(cfg):
             cfg = dict(cfg)
-            cfg.pop('type', None)
+            typ = cfg.pop('type', 'VisionTransformer')
             cfg.pop('norm_cfg', None)
+            if typ == 'MixVisionTransformer':
+                from .segformer_oracle import OracleMiT
+                return OracleMiT(**cfg)
             return OracleViT(**cfg)
 
         self.backbone = mk_bb(backbone)
@@ -533,8 +544,11 @@ class OracleEncoderDecoder(nn.Module):
         smetas = student_data['metas']
         if record is not None:
             record.update(teacher_logits=z_t, hard0=hard.clone(), conf=conf)
+        # :548-551 -- a confidence map at the image resolution is "VIT style" (patches of
+        # self.patchsize); SegFormer's quarter-resolution map uses patches of 8
+        apatch = self.patchsize if conf.shape[-1] == simg.shape[-1] else 8
         if self.attn_mask_seperate_head:   # :547-567
-            u = patch_unconfidence(conf, self.patchsize)
+            u = patch_unconfidence(conf, apatch)
             feat = self.backbone(simg, attn_mask=u, attn_mask_weight=self.attn_mask_weight,
                                  adaptive_attn_mask=self.adaptive_attn_mask, topk_idx=topk_idx)
             loss_unsup['loss_seg_unsup_attn_mask'] = \
@@ -557,7 +571,7 @@ class OracleEncoderDecoder(nn.Module):
         if record is not None:
             record.update(student_img_mixed=simg, hard_mixed=teacher['hard_seg_label'])
         if not self.attn_mask_seperate_head:   # :650-670 (MT as shipped: loss-less pass)
-            u = patch_unconfidence(conf, self.patchsize)
+            u = patch_unconfidence(conf, apatch)
             feat = self.backbone(simg, attn_mask=u, attn_mask_weight=self.attn_mask_weight,
                                  adaptive_attn_mask=self.adaptive_attn_mask, topk_idx=topk_idx)
         else:   # :671-677

@@ -173,3 +173,92 @@ def test_oracle_full_size_step_vs_reference_fixture(golden_dir):
     for k, gs in G['grad_samples'].items():
         got = gc.strided_sample(named[k].grad, 4096)
         assert float((got - gs).norm() / gs.norm()) < 2e-3, k
+
+
+# --------------------------------------------------------------------------------------------
+# SegFormer / MiT variant: the ORACLE pinned against the reference's own
+# mit.py / segformer_head.py / encoder_decoder.py (oracle/make_golden_segformer.py).  No CUDA path yet.
+# --------------------------------------------------------------------------------------------
+def _segformer_oracle(variant):
+    cfg = gc.tiny_segformer_cfg(variant)
+    m = O.OracleEncoderDecoder(**{k: v for k, v in cfg.items() if k != 'type'})
+    sd = gc.seeded_state_dict(m.state_dict(), seed=5, ema_cls_std=20.0)
+    m.load_state_dict(sd)
+    m.train()
+    return m, sd
+
+
+@pytest.mark.parametrize('variant', ['sup', 'ours'])
+def test_segformer_train_step_golden(golden_dir, variant):
+    G = _load(golden_dir, f'segformer_{variant}.pt')
+    m, sd = _segformer_oracle(variant)
+    assert abs(gc.checksum(sd) - G['sd_checksum']) < 1e-6 * G['sd_checksum']
+    img, gt, metas = gc.tiny_batch(variant)
+    assert abs(float(img.double().abs().sum()) - G['img_checksum']) < 1e-9 * G['img_checksum']
+    O.seed_host_rng(1999)
+    losses = m.forward_train(img, metas, gt)
+    assert {k for k in G['losses'] if 'loss' in k} <= set(losses)
+    for k, v in G['losses'].items():
+        if 'loss' in k:
+            assert torch.allclose(losses[k], v, rtol=2e-5, atol=1e-7), k
+    O.parse_losses(losses).backward()
+    named = dict(m.named_parameters())
+    assert len(G['grads']) >= 10
+    for k, g in G['grads'].items():
+        rel = (named[k].grad - g).norm() / (g.norm() + 1e-12)
+        assert rel < 1e-4, (k, float(rel))
+    gmax = max(G['grad_norms'].values())
+    for k, n in G['grad_norms'].items():
+        if k in G['zero_grad_keys']:        # analytically zero (a shift in front of conv -> BN): rounding noise
+            assert float(named[k].grad.norm()) < 1e-6 * gmax, k
+            continue
+        assert abs(float(named[k].grad.norm()) - n) <= 1e-3 * n + 1e-9, k
+    post = m.state_dict()
+    for k, v in G['bn_after'].items():
+        assert torch.allclose(post[k], v, rtol=1e-4, atol=1e-6), k
+    if variant == 'ours':
+        sm = [mm for mm in metas if mm['tag'] == 'unsup_student']
+        assert len(sm) == len(G['perms']) > 0
+        for mm, p in zip(sm, G['perms']):
+            assert torch.equal(torch.as_tensor(mm['PatchMixIndex']), torch.as_tensor(p))
+
+
+def test_segformer_backbone_mask_and_head_unshuffle_golden(golden_dir):
+    from oracle import segformer_oracle as SO
+    G = _load(golden_dir, 'segformer_ours.pt')
+    m, _ = _segformer_oracle('ours')
+    m.eval()
+    g2 = torch.Generator().manual_seed(G['mit_seed'])
+    u = torch.rand(2, 4, 4, generator=g2).mul(64).round().div(64)
+    x = torch.randn(2, 3, 128, 128, generator=g2)
+    perms = torch.stack([torch.randperm(4, generator=g2) for _ in range(2)])
+    assert torch.equal(u, G['mit_u']) and torch.equal(perms, G['mit_perms'])
+    assert abs(float(x.double().abs().sum()) - G['mit_x_checksum']) < 1e-6
+    with torch.no_grad():
+        feats = m.backbone(x, attn_mask=u, attn_mask_weight=5, adaptive_attn_mask=True, topk_idx=G['mit_topk'])
+        plain = m.backbone(x)
+        logits = m.decode_head.forward(plain, PatchMix_N=4, PatchMixIndex=perms)
+        logits_plain = m.decode_head.forward(plain)
+    assert [tuple(f.shape[1:]) for f in plain] == [(16, 32, 32), (32, 16, 16), (64, 8, 8), (128, 4, 4)]
+    for a, b in zip(feats, G['mit_feats']):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    for a, b in zip(plain, G['mit_feats_plain']):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(logits, G['head_logits_unshuffled'], rtol=1e-4, atol=1e-5)
+    # the mask reaches only the sr == 1 stage (stage 4): stages 1-3 are untouched, stage 4 changes
+    for a, b in zip(feats[:3], plain[:3]):
+        assert torch.equal(a, b)
+    assert (feats[3] - plain[3]).abs().max() > 1e-5
+    assert (logits - logits_plain).abs().max() > 1e-4
+    # mit.py:470-472: the "confident half" is taken over u[:, 1:] and its indices are used as row numbers
+    # of the full L x L bias (no cls token here): row 0 can never be selected through the slice's index 0
+    # standing for patch 1 -- the reference's off-by-one, reproduced
+    bias = SO.mit_pasa_bias(u, 5.0, True)
+    flat = u.reshape(2, -1)
+    idx = torch.topk(flat[:, 1:], 7, dim=-1, largest=False)[1]
+    assert torch.equal(idx, G['mit_topk'])
+    for b in range(2):
+        rows_zero = {int(r) for r in range(16) if float(bias[b, r].abs().max()) == 0.0}
+        assert rows_zero == {int(i) for i in idx[b]}
+        live = [r for r in range(16) if r not in rows_zero]
+        assert torch.allclose(bias[b, live[0]], 5.0 * (1.0 - flat[b]))
