@@ -400,6 +400,13 @@ def _reducer_worker(rank, world, port, q):
         vals = [float(p.grad.flatten()[0]) for p in net.parameters()]
         want = [1.5 * (i + 1) + step for i in range(len(vals))]
         assert all(abs(a - b) < 1e-6 for a, b in zip(vals, want)), (vals, want)
+    # SyncBN statistics: no peer-memory reducer without NCCL; the plain collective is used
+    from s4former_b200.parallel import PeerAllReduce
+    from s4former_b200 import ops
+    assert PeerAllReduce.get(None) is None
+    t = torch.full((2, 4), float(rank + 1))
+    ops._all_reduce_stats(t, dict(world=world, group=None, peer=None))
+    assert torch.equal(t, torch.full((2, 4), 3.0))
     q.put(rank)
     dist.destroy_process_group()
 
