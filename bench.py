@@ -585,6 +585,15 @@ def main():
                                kernel_nodes_per_replay=getattr(step, 'graph_kernel_launches', None)),
                clocks=clk, roofline=roofline,
                kernels=sorted(kinds, key=lambda k: -k["ms_per_step"])[:40])
+    try:    # which multi-GPU mechanisms this run used
+        from s4former_b200.parallel import PeerAllReduce
+        peer = [v for v in PeerAllReduce._cache.values()]
+        out['data_parallel'] = dict(
+            gemm_tile_scheduler='dynamic' if lib.s4_set_tc_sched(-1) == 1 else 'static',
+            syncbn_statistics=('nvlink_peer_memory' if any(v is not None for v in peer) else 'nccl')
+            if world > 1 else None)
+    except Exception as e:      # informational only
+        out['data_parallel'] = dict(error=str(e))
     if world == 1 and not (a.no_gpu_eager and a.no_extra_configs and a.no_cpu_baseline):
         # the comparison legs need the memory: drop this arm's model, graph and staging buffers
         step._graph = None

@@ -21,6 +21,7 @@
 // one), so no per-pixel weight evaluation is needed in the forward; the transpose (backward)
 // folds the clamped taps' weights into the edge pixel explicitly.
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -652,7 +653,9 @@ bool s4_stream_upsample_bwd(const void* dout, const void* x, const float* scale,
   if ((long long)B * H * ((W + 7) / 8) >= (1ll << 30)) return false;
   // bulk-copy strip kernel (C a multiple of 8 with C/8 dividing 256, 16-byte aligned rows)
   static const bool no_strip = getenv("S4_NO_BWD_STRIP") != nullptr;
-  if (!no_strip && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && H >= 2 && W >= 2) {
+  // (cp.async.bulk needs 16-byte aligned global addresses: an oddly offset view takes the walker)
+  if (!no_strip && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && H >= 2 && W >= 2 &&
+      (((uintptr_t)dout) & 15) == 0) {
     const int npl = 256 / (C / 8);
     bool ok = false;
     if (s == 2 && W >= 4 * npl) ok = launch_bwd_strip<2, 2>(dout, x, scale, shift, mean, invstd, dact, dsum, ddot, B, H, W, C, st);
