@@ -430,3 +430,24 @@ def test_poly_lr_and_lr_mult():
     assert abs(poly_lr(1e-3, 0, 80000) - 1e-3) < 1e-12
     assert abs(poly_lr(1e-3, 80000, 80000) - 1e-4) < 1e-12
     assert abs(poly_lr(1e-2, 40000, 80000) - ((1e-2 - 1e-4) * 0.5 ** 0.9 + 1e-4)) < 1e-12
+
+
+def test_row_map_covers_segformer_level_unshuffles():
+    """The head's row-gather map (host index arithmetic, no cls row) reproduces the reference's
+    ``_repatchmix_inputs`` at the per-level block sizes SegformerHead uses (PatchMix_N * 4 / 2^level
+    tokens, segformer_head.py:167-170) — the building block a SegFormer path would reuse."""
+    import s4former_b200 as s4
+    from oracle import golden_common as gc
+    from oracle import s4former_oracle as O
+    head = s4.build_segmentor(gc.tiny_cfg('ours')).decode_head
+    g0 = torch.Generator().manual_seed(4)
+    B, N = 2, 4
+    for level, g in enumerate((32, 16, 8, 4)):                # 128-pixel crop: strides 4 / 8 / 16 / 32
+        n = int(N * (4 / (2 ** level)))
+        gb = g // n
+        perms = torch.stack([torch.randperm(gb * gb, generator=g0) for _ in range(B)])
+        tok = torch.randn(B, g * g, 3, generator=g0)
+        want = O.token_unshuffle(tok, perms, n)
+        m = head._row_map(B, g, False, 'cpu', n, perms).long()
+        got = tok.reshape(B * g * g, 3)[m].reshape(B, g * g, 3)
+        assert torch.equal(got, want), (level, g, n)
