@@ -307,7 +307,7 @@ def test_tc_attention_fwd(B, H, Lt, pasa):
     assert ops.backend() == L.BACKEND_AUTO
     out, lse = ops.attention_fwd(qkv, B, Lt, H, hd, u0, gate, w)
     o_ref, lse_ref, _ = _attn_ref(qkv, B, Lt, H, hd, u0, gate, w)
-    assert rel(out.float(), o_ref) < 2e-2
+    assert rel(out.float(), o_ref) < 8e-3      # measured 2.2-2.5e-3 = rounding P and O to bf16
     assert torch.allclose(lse.cpu(), lse_ref, rtol=1e-3, atol=2e-3)
 
 
@@ -347,9 +347,12 @@ def test_tc_attention_bwd(B, H, Lt, pasa):
     _, _, g_ref = _attn_ref(qkv, B, Lt, H, hd, u0, gate, w, dout)
     gq, gk, gv = dqkv.float().cpu().view(B * Lt, 3, D).unbind(1)
     rq, rk, rv = g_ref.view(B * Lt, 3, D).unbind(1)
-    assert rel(gv, rv) < 2e-2, ('dV', rel(gv, rv))
-    assert rel(gk, rk) < 3e-2, ('dK', rel(gk, rk))
-    assert rel(gq, rq) < 3e-2, ('dQ', rel(gq, rq))
+    # Measured (tools/attn_bwd_error.py, these very inputs): 2.3-2.4e-3 for all three at every shape, which
+    # IS the unavoidable part - P, dS, O and the outputs rounded to bf16, everything else exact
+    # (tests/test_tolerance_yardsticks.py: 2.3-2.4e-3 on the CPU).  Gate = 2.5x that.
+    assert rel(gv, rv) < 6e-3, ('dV', rel(gv, rv))
+    assert rel(gk, rk) < 6e-3, ('dK', rel(gk, rk))
+    assert rel(gq, rq) < 6e-3, ('dQ', rel(gq, rq))
 
 
 # ------------------------------------------------------------------------------------------ last head stage (bf16)
