@@ -70,3 +70,64 @@ def test_bf16_attention_backward_inherent_rounding_error(B, H, Lt, pasa):
     print(f'inherent bf16 rounding error B={B} H={H} L={Lt} pasa={pasa}: dV {ev:.2e} dK {ek:.2e} dQ {eq:.2e}')
     # the unavoidable part is a few 1e-3; the GPU gates (2e-2 / 3e-2) sit within one order of magnitude
     assert 1e-3 < ev < 2e-2 and 1e-3 < ek < 3e-2 and 1e-3 < eq < 3e-2
+
+
+# --------------------------------------------------------------------------------------------------
+# last head stage: conv3x3 -> BN(train) -> ReLU -> conv_seg -> bilinear.  tests/test_tc_gpu.py::
+# test_cls_stage_bf16 gates bn_b / conv_w / dx at 6e-2 and bn_w at 3e-2.  Model of the roundings a
+# bf16-STORAGE pipeline cannot avoid (operands of every tensor-core product in bf16, the conv output
+# y, the activation, dz and dy stored in bf16; accumulation, statistics and the BN algebra exact):
+# the ReLU mask is then decided on the ROUNDED y, and every pixel whose y sits within half a bf16 ulp
+# of the BN zero crossing may flip - that, not the arithmetic, dominates the error behind the BN.
+# --------------------------------------------------------------------------------------------------
+class _RoundBoth(torch.autograd.Function):
+    """value and gradient both rounded to bf16 at this point (a tensor stored in bf16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _bf(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf(g)
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,NC,s', [(2, 16, 16, 64, 64, 5, 2), (1, 32, 32, 64, 256, 21, 2),
+                                                  (2, 8, 8, 64, 256, 19, 4), (1, 24, 24, 64, 128, 21, 2)])
+def test_bf16_cls_stage_inherent_rounding_error(B, H, W, Cin, Cout, NC, s):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(21)
+    conv = torch.nn.Conv2d(Cin, Cout, 3, padding=1, bias=False)
+    bn = torch.nn.BatchNorm2d(Cout)
+    seg = torch.nn.Conv2d(Cout, NC, 1)
+    with torch.no_grad():
+        bn.weight.copy_(1.0 + 0.2 * torch.randn(Cout, generator=g))
+        bn.bias.copy_(0.2 * torch.randn(Cout, generator=g))
+        seg.weight.mul_(3.0)
+    x = _bf(torch.randn(B, H, W, Cin, generator=g)).permute(0, 3, 1, 2).contiguous()
+    dout = torch.randn(B, NC, H * s, W * s, generator=g)
+    params = [conv.weight, bn.weight, bn.bias, seg.weight, seg.bias]
+
+    def run(rounded):
+        for p in params:
+            p.grad = None
+        xr = x.clone().requires_grad_(True)
+        rb = _RoundBoth.apply if rounded else (lambda t: t)
+        y = F.conv2d(xr, rb(conv.weight), padding=1)
+        y = rb(y)                                                   # conv output stored in bf16
+        a = F.relu(F.batch_norm(y, None, None, bn.weight, bn.bias, True, 0.1, bn.eps))
+        z = F.conv2d(rb(a), rb(seg.weight), seg.bias)               # mma.sync operands
+        z = rb(z) if rounded else z                                 # dz handed back in bf16
+        out = F.interpolate(z, scale_factor=s, mode='bilinear', align_corners=False)
+        out.backward(dout)
+        return dict(out=out.detach(), seg_w=seg.weight.grad.clone(), seg_b=seg.bias.grad.clone(),
+                    bn_w=bn.weight.grad.clone(), bn_b=bn.bias.grad.clone(), conv_w=conv.weight.grad.clone(),
+                    dx=xr.grad.clone())
+    ref, got = run(False), run(True)
+    errs = {k: _rel(got[k], ref[k]) for k in ref}
+    print(f'inherent bf16-storage error of the cls stage {B}x{H}x{W} {Cin}->{Cout}->{NC} s={s}: '
+          + '  '.join(f'{k} {v:.1e}' for k, v in errs.items()))
+    # forward and conv_seg gradients: plain bf16 accuracy; behind the BatchNorm backward several 1e-3..1e-2
+    assert errs['out'] < 1e-2 and errs['seg_w'] < 1e-2
+    for k in ('bn_w', 'bn_b', 'conv_w', 'dx'):
+        assert 5e-4 < errs[k] < 6e-2, (k, errs[k])
